@@ -1,0 +1,2 @@
+"""TEST INFRASTRUCTURE: CPU oracle for the Metalign database-selection hot path (PARITY UNPINNED).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this."""
