@@ -1,0 +1,130 @@
+/* metalign_b200 -- C ABI of the B200-native database-selection hot path of Metalign.
+ *
+ * The reference (nlapier2/Metalign) has no FFI: its hot path is four subprocesses started from
+ * scripts/select_db.py.  Each entry point below names the reference step it replaces:
+ *
+ *   mlg_db_*               the CMash training database that select_db.py:69-70 hands to
+ *                          StreamingQueryDNADatabase.py (cmash_db_n1000_k60.h5 + its .tst trie + the
+ *                          30-60-10 Bloom prefilter) and the KMC database of its k-mers that
+ *                          select_db.py:44 hands to kmc_tools (built at
+ *                          local_tests/retrain_and_test_metalign.sh:49-66 via local_tests/dump_kmers.py:7-14)
+ *   mlg_query_push_*       `kmc -k60 -fq|-fa -ci2 -cs3` + `kmc_tools simple ... intersect`
+ *                          (select_db.py:50-56): canonical K-mer occurrence counting of the reads,
+ *                          restricted to the database's k-mers
+ *   mlg_query_counts_*     (new) the seam for the one multi-GPU exchange: per-k-mer occurrence
+ *                          counters, clamped to ci_min, summed over ranks by the caller (NCCL)
+ *   mlg_query_finish       `kmc_dump` + the FASTA rewrite + `StreamingQueryDNADatabase.py <fa> <h5> <csv>
+ *                          30-60-10 -c 0 -r 1000000 -v -f <bf> --sensitive` (select_db.py:58-76) up to, but
+ *                          not including, the pandas filter/sort/to_csv tail, which stays on the host
+ *   mlg_query_intersection the contents of `60mers_intersection_dump` (select_db.py:58-59)
+ *
+ * Conventions
+ *   - every function returns MLG_OK (0) or a negative error code; mlg_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every call fails.
+ *   - one context == one GPU == one host thread (one process per GPU; ranks combine through
+ *     mlg_query_counts_export/import).  Work is asynchronous on the context's streams and joined in
+ *     mlg_query_finish / mlg_query_counts_export / mlg_query_sync.
+ *   - the caller owns every buffer it passes.  Host buffers given to mlg_query_push_* must stay valid
+ *     until the next push/sync/finish on that query (pinned memory makes the copies asynchronous).
+ *   - k-mer key: 2K-bit integer, first base most significant, A=0 C=1 G=2 T=3, as two uint64 (hi, lo);
+ *     an empty CMash sketch slot ('' in CE._kmers) is (~0, ~0).
+ *   - packed read stream: reads back to back at base granularity; base i in byte i/4, bits
+ *     7-2*(i%4)..6-2*(i%4); N (any non-ACGT symbol) is flagged in nmask (bit i in byte i/8, bit 7-(i%8))
+ *     and its 2-bit code is ignored.  `bases` must be readable up to a multiple of 16 bytes covering
+ *     ceil(nbases/64) 16-byte words, `nmask` up to a multiple of 16 bytes covering ceil(nbases/64) 8-byte words.
+ */
+#ifndef METALIGN_B200_H
+#define METALIGN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLG_OK 0
+#define MLG_ERR_CUDA (-1)
+#define MLG_ERR_ARG (-2)
+#define MLG_ERR_IO (-3)
+#define MLG_ERR_STATE (-4)
+#define MLG_ERR_NOMEM (-5)
+
+#define MLG_GATE_EXACT 0 /* smallest-k prefilter with zero false positives */
+#define MLG_GATE_NONE 1  /* no prefilter */
+
+typedef struct mlg_ctx mlg_ctx;
+typedef struct mlg_db mlg_db;
+typedef struct mlg_query mlg_query;
+
+typedef struct mlg_stats {
+    uint64_t n_reads;        /* reads pushed */
+    uint64_t n_bases;        /* bases pushed (N included) */
+    uint64_t n_kmers;        /* N-free K-long windows probed (the metric's unit of work) */
+    uint64_t n_intersect;    /* |I|: database k-mers seen >= ci_min times */
+    uint64_t n_db_entries;   /* non-empty sketch slots */
+    uint64_t n_db_distinct;  /* |D|: distinct canonical sketch k-mers */
+    uint64_t n_buckets;      /* level-1 fingerprint buckets */
+    uint32_t bucket_bytes;   /* bytes fetched per membership probe */
+    uint32_t gpu_launches;   /* kernels of this library launched for this query so far */
+    uint64_t h2d_bytes;      /* host->device bytes copied for this query */
+    uint64_t d2h_bytes;      /* device->host bytes copied for this query */
+    double ms_probe;         /* sum of CUDA-event durations of the probe kernel launches */
+    double ms_query;         /* CUDA-event duration of the finish stage (compact, expand, popcount, finalize) */
+    uint32_t probe_launches; /* number of probe kernel launches in ms_probe */
+    uint32_t reserved;
+} mlg_stats;
+
+const char* mlg_last_error(void);
+int mlg_version(void);
+
+/* context: one GPU */
+int mlg_ctx_create(int device, mlg_ctx** out);
+int mlg_ctx_destroy(mlg_ctx* ctx);
+/* the context's cudaStream_t handles: kernels run on *compute_stream, host<->device copies on *copy_stream
+ * (for callers that bracket work with CUDA events or order their own work against it) */
+int mlg_ctx_streams(mlg_ctx* ctx, void** compute_stream, void** copy_stream);
+/* pinned host memory for callers that have no other way to get it */
+int mlg_host_alloc(void** out, uint64_t bytes);
+int mlg_host_free(void* p);
+
+/* database: G genomes x n sketch slots of K-mers, queried at nk prefix lengths ks[] (ascending, ks[nk-1] <= K) */
+int mlg_db_from_keys(mlg_ctx* ctx, const uint64_t* keys /* host, G*n (hi,lo) pairs */, uint32_t G, uint32_t n,
+                     uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db** out);
+int mlg_db_from_keys_device(mlg_ctx* ctx, const uint64_t* d_keys /* device, 16-byte aligned */, uint32_t G, uint32_t n,
+                            uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db** out);
+int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers /* host, G*n*K chars; a slot starting with NUL is empty */,
+                      uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db** out);
+int mlg_db_load(mlg_ctx* ctx, const char* path /* .mlgdb file */, mlg_db** out);
+int mlg_db_info(const mlg_db* db, uint32_t* G, uint32_t* n, uint32_t* K, uint32_t* nk, uint32_t* ks /* 8 */,
+                uint64_t* n_entries, uint64_t* n_distinct);
+/* static denominators: distinct k-prefixes per genome (+1 for '' where the genome has an empty slot) */
+int mlg_db_denominators(const mlg_db* db, int count_empty_in_den, int64_t* den /* host, G*nk */);
+int mlg_db_free(mlg_db* db);
+
+/* query */
+int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode, int count_empty_in_den, mlg_query** out);
+/* host buffers; read_off (n_reads+1 entries, in bases) or NULL with every read read_len long */
+int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint8_t* nmask_or_null,
+                          const uint64_t* read_off_or_null, uint64_t n_reads, uint32_t read_len);
+/* same, buffers already on the device (16-byte aligned); they must stay valid until the next sync/finish */
+int mlg_query_push_packed_device(mlg_query* q, const uint8_t* d_bases, const uint8_t* d_nmask_or_null,
+                                 const uint64_t* d_read_off_or_null, uint64_t n_reads, uint32_t read_len);
+/* host ASCII: read i = text[read_off[i] .. read_off[i+1]); anything outside ACGTacgt is N */
+int mlg_query_push_ascii(mlg_query* q, const char* text, const uint64_t* read_off, uint64_t n_reads);
+int mlg_query_sync(mlg_query* q);
+/* multi-GPU seam: device pointer to the |D| uint8 occurrence counters, clamped to ci_min, work joined.
+ * After the caller has summed them over ranks in place, mlg_query_counts_import() tells the query to
+ * derive presence from the summed table. */
+int mlg_query_counts_export(mlg_query* q, uint8_t** d_counts, uint64_t* n_counts);
+int mlg_query_counts_import(mlg_query* q);
+/* num/den: int64 [G*nk]; ci: double [G*nk] (num/den where num > 0, else 0.0); any pointer may be NULL */
+int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect);
+/* after finish: I as (hi,lo) canonical keys in increasing order; writes at most cap pairs, *n = |I| */
+int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n);
+int mlg_query_stats(mlg_query* q, mlg_stats* out);
+int mlg_query_free(mlg_query* q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METALIGN_B200_H */

@@ -1,0 +1,225 @@
+"""Python objects over the C ABI (include/metalign_b200.h).  Thin by design: every method is one or two
+C calls; all compute is in the CUDA library.  Host arrays are numpy; device arrays are raw pointers
+(e.g. ``torch_tensor.data_ptr()``)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import MlgError, Stats, check  # noqa: F401
+
+GATE = {"exact": 0, "none": 1}
+DEFAULT_KS = (30, 40, 50, 60)   # '30-60-10' at scripts/select_db.py:75 of the reference
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One GPU.  One process (host thread) per context."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(_lib.lib().mlg_ctx_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def streams(self):
+        """(compute, copy) cudaStream_t handles as ints, e.g. for torch.cuda.ExternalStream."""
+        a, b = C.c_void_p(), C.c_void_p()
+        check(_lib.lib().mlg_ctx_streams(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if self._h:
+            _lib.lib().mlg_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class Database:
+    """G genomes x n sketch slots of K-mers (stored in genome-strand orientation, '' = empty slot),
+    queried at the prefix lengths ``ks``.  Replaces cmash_db_n1000_k60.h5 / .tst / .bf and
+    cmash_db_n1000_k60_dump.kmc_* of the reference (scripts/select_db.py:44,69,70)."""
+
+    def __init__(self, ctx: Context, handle, names=None):
+        self.ctx = ctx
+        self._h = handle
+        G, n, K, nk = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        ks = (C.c_uint32 * 8)()
+        ne, nd = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().mlg_db_info(self._h, C.byref(G), C.byref(n), C.byref(K), C.byref(nk), C.byref(ks),
+                                     C.byref(ne), C.byref(nd)))
+        self.G, self.n, self.K = G.value, n.value, K.value
+        self.ks = tuple(ks[i] for i in range(nk.value))
+        self.n_entries, self.n_distinct = ne.value, nd.value
+        self.names = list(names) if names is not None else None
+
+    # -- constructors -------------------------------------------------------------------------
+    @classmethod
+    def from_keys(cls, ctx: Context, keys: np.ndarray, G: int, n: int, K: int = 60,
+                  ks: Sequence[int] = DEFAULT_KS, names=None) -> "Database":
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1)
+        if keys.size != 2 * G * n:
+            raise ValueError("keys must hold G*n (hi, lo) pairs")
+        ksa = np.asarray(ks, dtype=np.uint32)
+        h = C.c_void_p()
+        check(_lib.lib().mlg_db_from_keys(ctx._h, keys.ctypes.data, G, n, K, ksa.ctypes.data, ksa.size, C.byref(h)))
+        return cls(ctx, h, names)
+
+    @classmethod
+    def from_device_keys(cls, ctx: Context, d_keys_ptr: int, G: int, n: int, K: int = 60,
+                         ks: Sequence[int] = DEFAULT_KS, names=None) -> "Database":
+        ksa = np.asarray(ks, dtype=np.uint32)
+        h = C.c_void_p()
+        check(_lib.lib().mlg_db_from_keys_device(ctx._h, d_keys_ptr, G, n, K, ksa.ctypes.data, ksa.size, C.byref(h)))
+        return cls(ctx, h, names)
+
+    @classmethod
+    def from_sketches(cls, ctx: Context, sketches, K: int = 60, ks: Sequence[int] = DEFAULT_KS, names=None) -> "Database":
+        """sketches: list of G lists of n strings ('' for an unused slot) -- what
+        local_tests/dump_kmers.py:7-14 walks (`CE._kmers`).  Goes through mlg_db_from_ascii."""
+        G = len(sketches)
+        n = len(sketches[0])
+        buf = bytearray(G * n * K)
+        for g, sk in enumerate(sketches):
+            if len(sk) != n:
+                raise ValueError("every sketch must have the same number of slots")
+            for j, s in enumerate(sk):
+                if s:
+                    if len(s) != K:
+                        raise ValueError("sketch k-mer of length %d, expected %d" % (len(s), K))
+                    o = (g * n + j) * K
+                    buf[o:o + K] = s.encode()
+        ksa = np.asarray(ks, dtype=np.uint32)
+        h = C.c_void_p()
+        check(_lib.lib().mlg_db_from_ascii(ctx._h, bytes(buf), G, n, K, ksa.ctypes.data, ksa.size, C.byref(h)))
+        return cls(ctx, h, names)
+
+    @classmethod
+    def load(cls, ctx: Context, path: str) -> "Database":
+        from . import dbformat
+        names = dbformat.read_names(path)
+        h = C.c_void_p()
+        check(_lib.lib().mlg_db_load(ctx._h, path.encode(), C.byref(h)))
+        return cls(ctx, h, names)
+
+    # -- queries ------------------------------------------------------------------------------
+    def denominators(self, count_empty_in_den: bool = True) -> np.ndarray:
+        den = np.zeros((self.G, len(self.ks)), dtype=np.int64)
+        check(_lib.lib().mlg_db_denominators(self._h, int(count_empty_in_den), den.ctypes.data))
+        return den
+
+    def query(self, ci_min: int = 2, gate: str = "exact", count_empty_in_den: bool = True) -> "Query":
+        return Query(self, ci_min, gate, count_empty_in_den)
+
+    def close(self):
+        if self._h:
+            _lib.lib().mlg_db_free(self._h)
+            self._h = C.c_void_p()
+
+
+class Query:
+    """One read set against one database: push batches, then finish().  Replaces run_kmc_steps and the
+    CMash subprocess of run_cmash_and_cutoff (scripts/select_db.py:43-76)."""
+
+    def __init__(self, db: Database, ci_min: int = 2, gate: str = "exact", count_empty_in_den: bool = True):
+        self.db = db
+        self.ci_min = int(ci_min)
+        self._h = C.c_void_p()
+        check(_lib.lib().mlg_query_begin(db.ctx._h, db._h, int(ci_min), GATE[gate], int(count_empty_in_den),
+                                         C.byref(self._h)))
+        self._keep = []   # host buffers that must outlive the asynchronous copies
+
+    def push_packed(self, bases: np.ndarray, nmask: Optional[np.ndarray], off: Optional[np.ndarray],
+                    n_reads: int, read_len: int = 0):
+        """Host buffers (pinned for asynchronous copies).  off: uint64[n_reads+1] in bases, or None with
+        fixed read_len.  Buffers must cover whole 16-byte units (see the header)."""
+        if off is not None:
+            off = np.ascontiguousarray(off, dtype=np.uint64)
+        self._keep = self._keep[-3:] + [bases, nmask, off]
+        check(_lib.lib().mlg_query_push_packed(self._h, _ptr(bases), _ptr(nmask), _ptr(off), int(n_reads), int(read_len)))
+
+    def push_packed_ptr(self, bases_ptr: int, nmask_ptr: Optional[int], off_ptr: Optional[int], n_reads: int,
+                        read_len: int = 0, device: bool = False):
+        """Raw-pointer variant (pinned host tensors or device tensors from torch)."""
+        fn = _lib.lib().mlg_query_push_packed_device if device else _lib.lib().mlg_query_push_packed
+        check(fn(self._h, bases_ptr, nmask_ptr, off_ptr, int(n_reads), int(read_len)))
+
+    def push_ascii(self, text, off: np.ndarray):
+        """text: bytes / uint8 array of concatenated reads; off: uint64[n_reads+1]."""
+        if isinstance(text, (bytes, bytearray)):
+            text = np.frombuffer(text, dtype=np.uint8)
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        self._keep = self._keep[-3:] + [text, off]
+        check(_lib.lib().mlg_query_push_ascii(self._h, text.ctypes.data, off.ctypes.data, off.size - 1))
+
+    def push_reads(self, reads: Sequence[str]):
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        if len(reads):
+            off[1:] = np.cumsum([len(r) for r in reads], dtype=np.uint64)
+        self.push_ascii("".join(reads).encode(), off)
+
+    def sync(self):
+        check(_lib.lib().mlg_query_sync(self._h))
+
+    def counts_export(self):
+        """(device pointer, length) of the per-database-k-mer uint8 counters clamped to ci_min."""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().mlg_query_counts_export(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def counts_import(self):
+        check(_lib.lib().mlg_query_counts_import(self._h))
+
+    def finish(self):
+        G, nk = self.db.G, len(self.db.ks)
+        num = np.zeros((G, nk), dtype=np.int64)
+        den = np.zeros((G, nk), dtype=np.int64)
+        ci = np.zeros((G, nk), dtype=np.float64)
+        ni = C.c_uint64()
+        check(_lib.lib().mlg_query_finish(self._h, num.ctypes.data, den.ctypes.data, ci.ctypes.data, C.byref(ni)))
+        self._keep = []
+        st = self.stats()
+        return dict(num=num, den=den, ci=ci, n_intersect=ni.value, n_kmers=st["n_kmers"], stats=st)
+
+    def finish_into(self, num_ptr: int, den_ptr: int, ci_ptr: int) -> int:
+        """finish() writing into caller-provided (pinned) host buffers; returns |I|."""
+        ni = C.c_uint64()
+        check(_lib.lib().mlg_query_finish(self._h, num_ptr, den_ptr, ci_ptr, C.byref(ni)))
+        self._keep = []
+        return ni.value
+
+    def intersection(self) -> np.ndarray:
+        n = C.c_uint64()
+        check(_lib.lib().mlg_query_intersection(self._h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 2), dtype=np.uint64)
+        if n.value:
+            check(_lib.lib().mlg_query_intersection(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(_lib.lib().mlg_query_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def close(self):
+        if self._h:
+            _lib.lib().mlg_query_free(self._h)
+            self._h = C.c_void_p()
+            self._keep = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

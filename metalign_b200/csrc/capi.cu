@@ -1,0 +1,490 @@
+// C ABI of libmetalign_b200.so (declared in include/metalign_b200.h).  Host-side orchestration only:
+// buffers, streams, chunked host->device copies overlapped with the probe kernel, and the finish stage.
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include "mlg_internal.h"
+
+#define MLG_API __attribute__((visibility("default")))
+
+static thread_local char g_err[512] = "";
+
+void mlg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr unsigned long long CHUNK_WORDS = 64ull * MLG_TILE_WORDS * 32ull;   // 524288 words = 8 MiB of packed bases per copy chunk
+
+struct Staging {
+    DevBuf<unsigned char> bases, nmask;
+    DevBuf<unsigned long long> smask, off;
+    DevBuf<unsigned char> text;
+    cudaEvent_t done = nullptr;   // last kernel reading this staging set
+    bool used = false;
+};
+
+inline unsigned long long round_up(unsigned long long x, unsigned long long m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct mlg_query {
+    mlg_ctx* ctx = nullptr;
+    mlg_db* db = nullptr;
+    int ci_min = 2, gate = MLG_GATE_EXACT, count_empty = 1;
+    DevBuf<unsigned char> cnt8;
+    DevBuf<unsigned long long> d_nkmers, d_scalar;
+    Staging stg[2];
+    int cur = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> probe_events;
+    std::vector<cudaEvent_t> chunk_events;
+    cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr;
+    mlg_stats st{};
+    bool finished = false, reduced = false;
+    // results kept for mlg_query_intersection
+    DevBuf<uint32_t> present;
+    uint32_t n_present = 0;
+};
+
+namespace {
+
+int ensure_device(mlg_ctx* ctx) { CUDA_TRY(cudaSetDevice(ctx->device)); return MLG_OK; }
+
+// device-side part common to every push: build the read-start mask, launch the probe over [0, nwords)
+// in chunks, each chunk waiting for its copy event (if any)
+int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsigned char* d_nmask,
+              const unsigned long long* d_off, unsigned long long n_reads, uint32_t read_len, unsigned long long nbases,
+              const std::vector<std::pair<unsigned long long, cudaEvent_t>>* chunk_ready) {
+    mlg_ctx* ctx = q->ctx;
+    const unsigned long long nwords = (nbases + 63) / 64;
+    const unsigned long long nwords_alloc = round_up(nwords + 2, 2);
+    MLG_TRY(s.smask.ensure(nwords_alloc));
+    if (d_off) {
+        CUDA_TRY(cudaMemsetAsync(s.smask.p, 0, nwords_alloc * 8, ctx->s_comp));
+        MLG_TRY(launch_build_smask_offsets(s.smask.p, d_off, n_reads, ctx->s_comp));
+    } else {
+        MLG_TRY(launch_build_smask_fixed(s.smask.p, nwords_alloc, nbases, read_len, ctx->s_comp));
+    }
+    q->st.gpu_launches += 1;
+    ProbeArgs a{};
+    a.bases = reinterpret_cast<const uint4*>(d_bases);
+    a.nmask = reinterpret_cast<const unsigned long long*>(d_nmask);
+    a.smask = s.smask.p;
+    a.nwords = nwords; a.nbases = nbases;
+    a.cnt8 = q->cnt8.p; a.n_kmers = q->d_nkmers.p;
+    auto launch_range = [&](unsigned long long w0, unsigned long long w1) -> int {
+        cudaEvent_t e0, e1;
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        a.w_begin = w0; a.w_end = w1;
+        CUDA_TRY(cudaEventRecord(e0, ctx->s_comp));
+        MLG_TRY(launch_probe(ctx, q->db->v, a, ctx->s_comp));
+        CUDA_TRY(cudaEventRecord(e1, ctx->s_comp));
+        q->probe_events.emplace_back(e0, e1);
+        q->st.gpu_launches += 1; q->st.probe_launches += 1;
+        return MLG_OK;
+    };
+    if (chunk_ready) {
+        unsigned long long w0 = 0;
+        for (auto& cr : *chunk_ready) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, cr.second, 0));
+            MLG_TRY(launch_range(w0, cr.first));
+            w0 = cr.first;
+        }
+    } else if (nwords) {
+        MLG_TRY(launch_range(0, nwords));
+    }
+    if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(s.done, ctx->s_comp));
+    s.used = true;
+    q->st.n_reads += n_reads; q->st.n_bases += nbases;
+    return MLG_OK;
+}
+
+int check_push(mlg_query* q) {
+    if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
+    if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
+    if (q->reduced) { mlg_set_error("counters were already reduced; no more reads can be pushed"); return MLG_ERR_STATE; }
+    return ensure_device(q->ctx);
+}
+
+// total bases of a batch; for offsets given on the host read it there, on the device copy one word back
+int batch_bases_host(const uint64_t* off, uint64_t n_reads, uint32_t read_len, unsigned long long* nbases) {
+    if (off) {
+        if (off[0] != 0) { mlg_set_error("read_off[0] must be 0"); return MLG_ERR_ARG; }
+        *nbases = off[n_reads];
+    } else {
+        if (read_len == 0 && n_reads) { mlg_set_error("read_len must be > 0 when read_off is NULL"); return MLG_ERR_ARG; }
+        *nbases = n_reads * (unsigned long long)read_len;
+    }
+    return MLG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+MLG_API const char* mlg_last_error(void) { return g_err; }
+MLG_API int mlg_version(void) { return 100; }
+
+MLG_API int mlg_ctx_create(int device, mlg_ctx** out) {
+    if (!out) { mlg_set_error("null out pointer"); return MLG_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        mlg_set_error("no CUDA device available (%s); metalign_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        return MLG_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { mlg_set_error("device %d out of range (0..%d)", device, ndev - 1); return MLG_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { mlg_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return MLG_ERR_CUDA; }
+    mlg_ctx* ctx = new mlg_ctx();
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking) != cudaSuccess) {
+        mlg_set_error("cudaStreamCreate failed"); delete ctx; return MLG_ERR_CUDA;
+    }
+    *out = ctx;
+    return MLG_OK;
+}
+MLG_API int mlg_ctx_destroy(mlg_ctx* ctx) {
+    if (!ctx) return MLG_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    delete ctx;
+    return MLG_OK;
+}
+MLG_API int mlg_ctx_streams(mlg_ctx* ctx, void** compute_stream, void** copy_stream) {
+    if (!ctx) { mlg_set_error("null ctx"); return MLG_ERR_ARG; }
+    if (compute_stream) *compute_stream = (void*)ctx->s_comp;
+    if (copy_stream) *copy_stream = (void*)ctx->s_copy;
+    return MLG_OK;
+}
+MLG_API int mlg_host_alloc(void** out, uint64_t bytes) {
+    if (!out) { mlg_set_error("null out pointer"); return MLG_ERR_ARG; }
+    CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return MLG_OK;
+}
+MLG_API int mlg_host_free(void* p) { if (p) CUDA_TRY(cudaFreeHost(p)); return MLG_OK; }
+
+// ------------------------------------------------------------------ database
+MLG_API int mlg_db_from_keys_device(mlg_ctx* ctx, const uint64_t* d_keys, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks,
+                            uint32_t nk, mlg_db** out) {
+    if (!ctx || !d_keys || !ks || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(ctx));
+    return mlg_db_build_device(ctx, reinterpret_cast<const key128*>(d_keys), G, n, K, ks, nk, out);
+}
+MLG_API int mlg_db_from_keys(mlg_ctx* ctx, const uint64_t* keys, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk,
+                     mlg_db** out) {
+    if (!ctx || !keys || !ks || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(ctx));
+    size_t total = (size_t)G * n;
+    DevBuf<key128> d; MLG_TRY(d.alloc(total));
+    CUDA_TRY(cudaMemcpy(d.p, keys, total * sizeof(key128), cudaMemcpyHostToDevice));
+    return mlg_db_build_device(ctx, d.p, G, n, K, ks, nk, out);
+}
+MLG_API int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk,
+                      mlg_db** out) {
+    if (!ctx || !kmers || !ks || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (K < 1 || K > 63) { mlg_set_error("K=%u out of range 1..63", K); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(ctx));
+    size_t total = (size_t)G * n;
+    DevBuf<unsigned char> t; MLG_TRY(t.alloc(total * K));
+    DevBuf<key128> d; MLG_TRY(d.alloc(total));
+    CUDA_TRY(cudaMemcpy(t.p, kmers, total * K, cudaMemcpyHostToDevice));
+    MLG_TRY(launch_ascii_to_keys(t.p, total, K, d.p, ctx->s_comp));
+    t.release();
+    return mlg_db_build_device(ctx, d.p, G, n, K, ks, nk, out);
+}
+
+// .mlgdb: "MLGDB001", u32 K, u32 n, u64 G, u32 nk, u32 ks[8], u64 names_bytes, names, pad to 16, keys (G*n * 16 bytes)
+MLG_API int mlg_db_load(mlg_ctx* ctx, const char* path, mlg_db** out) {
+    if (!ctx || !path || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(ctx));
+    FILE* f = fopen(path, "rb");
+    if (!f) { mlg_set_error("cannot open %s", path); return MLG_ERR_IO; }
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    char magic[8]; uint32_t K, n, nk, ks[8]; uint64_t G, names_bytes;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "MLGDB001", 8) != 0) { mlg_set_error("%s: not a .mlgdb file", path); return MLG_ERR_IO; }
+    if (fread(&K, 4, 1, f) != 1 || fread(&n, 4, 1, f) != 1 || fread(&G, 8, 1, f) != 1 || fread(&nk, 4, 1, f) != 1 ||
+        fread(ks, 4, 8, f) != 8 || fread(&names_bytes, 8, 1, f) != 1) { mlg_set_error("%s: truncated header", path); return MLG_ERR_IO; }
+    if (G == 0 || G > 0xFFFFFFFFull || nk < 1 || nk > 8) { mlg_set_error("%s: bad header", path); return MLG_ERR_IO; }
+    uint64_t pos = 8 + 4 + 4 + 8 + 4 + 32 + 8 + names_bytes;
+    pos = round_up(pos, 16);
+    if (fseek(f, (long)pos, SEEK_SET) != 0) { mlg_set_error("%s: truncated", path); return MLG_ERR_IO; }
+    size_t total = (size_t)G * n;
+    DevBuf<key128> d; MLG_TRY(d.alloc(total));
+    const size_t CH = (size_t)1 << 22;   // keys per staging chunk (64 MiB)
+    void* h = nullptr;
+    CUDA_TRY(cudaMallocHost(&h, std::min(CH, total ? total : 1) * sizeof(key128)));
+    struct HFree { void* p; ~HFree() { cudaFreeHost(p); } } hfree{h};
+    for (size_t o = 0; o < total; o += CH) {
+        size_t m = std::min(CH, total - o);
+        if (fread(h, sizeof(key128), m, f) != m) { mlg_set_error("%s: truncated key block", path); return MLG_ERR_IO; }
+        CUDA_TRY(cudaMemcpy(d.p + o, h, m * sizeof(key128), cudaMemcpyHostToDevice));
+    }
+    return mlg_db_build_device(ctx, d.p, (uint32_t)G, n, K, ks, nk, out);
+}
+MLG_API int mlg_db_info(const mlg_db* db, uint32_t* G, uint32_t* n, uint32_t* K, uint32_t* nk, uint32_t* ks, uint64_t* n_entries,
+                uint64_t* n_distinct) {
+    if (!db) { mlg_set_error("null db"); return MLG_ERR_ARG; }
+    if (G) *G = db->v.G; if (n) *n = db->v.n; if (K) *K = db->v.K; if (nk) *nk = db->v.nk;
+    if (ks) for (int i = 0; i < MLG_MAX_KS; ++i) ks[i] = db->v.ks[i];
+    if (n_entries) *n_entries = db->v.np; if (n_distinct) *n_distinct = db->v.nd;
+    return MLG_OK;
+}
+MLG_API int mlg_db_denominators(const mlg_db* db, int count_empty_in_den, int64_t* den) {
+    if (!db || !den) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(db->ctx));
+    size_t cells = (size_t)db->v.G * db->v.nk;
+    std::vector<unsigned char> he(db->v.G);
+    CUDA_TRY(cudaMemcpy(den, db->den_real.p, cells * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(he.data(), db->has_empty.p, db->v.G, cudaMemcpyDeviceToHost));
+    if (count_empty_in_den)
+        for (uint32_t g = 0; g < db->v.G; ++g) if (he[g]) for (uint32_t k = 0; k < db->v.nk; ++k) den[(size_t)g * db->v.nk + k] += 1;
+    return MLG_OK;
+}
+MLG_API int mlg_db_free(mlg_db* db) {
+    if (!db) return MLG_OK;
+    cudaSetDevice(db->ctx->device);
+    delete db;
+    return MLG_OK;
+}
+
+// ------------------------------------------------------------------ query
+MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode, int count_empty_in_den, mlg_query** out) {
+    if (!ctx || !db || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (ci_min < 1 || ci_min > 255) { mlg_set_error("ci_min=%d out of range 1..255", ci_min); return MLG_ERR_ARG; }
+    if (gate_mode != MLG_GATE_EXACT && gate_mode != MLG_GATE_NONE) { mlg_set_error("bad gate_mode %d", gate_mode); return MLG_ERR_ARG; }
+    if (db->ctx != ctx) { mlg_set_error("database belongs to another context"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(ctx));
+    mlg_query* q = new mlg_query();
+    struct Guard { mlg_query* q; ~Guard() { if (q) mlg_query_free(q); } } guard{q};
+    q->ctx = ctx; q->db = db; q->ci_min = ci_min; q->gate = gate_mode; q->count_empty = count_empty_in_den ? 1 : 0;
+    size_t cbytes = round_up((size_t)db->v.nd + 4, 16);
+    MLG_TRY(q->cnt8.alloc(cbytes));
+    MLG_TRY(q->d_nkmers.alloc(1)); MLG_TRY(q->d_scalar.alloc(2));
+    CUDA_TRY(cudaMemsetAsync(q->cnt8.p, 0, cbytes, ctx->s_comp));
+    CUDA_TRY(cudaMemsetAsync(q->d_nkmers.p, 0, 8, ctx->s_comp));
+    CUDA_TRY(cudaEventCreate(&q->ev_q0)); CUDA_TRY(cudaEventCreate(&q->ev_q1));
+    q->st.n_db_entries = db->v.np; q->st.n_db_distinct = db->v.nd;
+    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4;
+    guard.q = nullptr;
+    *out = q;
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_push_packed_device(mlg_query* q, const uint8_t* d_bases, const uint8_t* d_nmask, const uint64_t* d_off,
+                                 uint64_t n_reads, uint32_t read_len) {
+    MLG_TRY(check_push(q));
+    if (!n_reads) return MLG_OK;
+    if (!d_bases) { mlg_set_error("null bases"); return MLG_ERR_ARG; }
+    if (((uintptr_t)d_bases & 15) || ((uintptr_t)d_nmask & 15)) { mlg_set_error("device buffers must be 16-byte aligned"); return MLG_ERR_ARG; }
+    unsigned long long nbases = 0;
+    if (d_off) CUDA_TRY(cudaMemcpy(&nbases, d_off + n_reads, 8, cudaMemcpyDeviceToHost));
+    else {
+        if (!read_len) { mlg_set_error("read_len must be > 0 when read_off is NULL"); return MLG_ERR_ARG; }
+        nbases = n_reads * (unsigned long long)read_len;
+    }
+    Staging& s = q->stg[q->cur];
+    if (s.used) CUDA_TRY(cudaEventSynchronize(s.done));
+    MLG_TRY(run_probe(q, s, d_bases, d_nmask, reinterpret_cast<const unsigned long long*>(d_off), n_reads, read_len, nbases, nullptr));
+    q->cur ^= 1;
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint8_t* nmask, const uint64_t* off, uint64_t n_reads,
+                          uint32_t read_len) {
+    MLG_TRY(check_push(q));
+    if (!n_reads) return MLG_OK;
+    if (!bases) { mlg_set_error("null bases"); return MLG_ERR_ARG; }
+    unsigned long long nbases = 0;
+    MLG_TRY(batch_bases_host(off, n_reads, read_len, &nbases));
+    if (!nbases) return MLG_OK;
+    mlg_ctx* ctx = q->ctx;
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));          // host buffers of the previous push are free from here on
+    Staging& s = q->stg[q->cur];
+    if (s.used) CUDA_TRY(cudaEventSynchronize(s.done));   // previous batch that used this set has been consumed
+    const unsigned long long nwords = (nbases + 63) / 64;
+    const unsigned long long cap_words = round_up(nwords + 2, 2);
+    MLG_TRY(s.bases.ensure(cap_words * 16));
+    if (nmask) MLG_TRY(s.nmask.ensure(cap_words * 8));
+    if (off) {
+        MLG_TRY(s.off.ensure(n_reads + 1));
+        CUDA_TRY(cudaMemcpyAsync(s.off.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+        cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(e, ctx->s_copy));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, e, 0));
+        q->chunk_events.push_back(e);
+        q->st.h2d_bytes += (n_reads + 1) * 8;
+    }
+    // chunked copies: chunk c of the packed stream is probed while chunk c+1 is still in flight
+    const unsigned long long bases_bytes = (nbases + 3) / 4, nmask_bytes = (nbases + 7) / 8;
+    std::vector<std::pair<unsigned long long, cudaEvent_t>> ready;
+    for (unsigned long long w0 = 0; w0 < nwords; w0 += CHUNK_WORDS) {
+        const unsigned long long w1 = std::min(nwords, w0 + CHUNK_WORDS);
+        const unsigned long long b0 = w0 * 16, b1 = std::min(bases_bytes, w1 * 16);
+        CUDA_TRY(cudaMemcpyAsync(s.bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_copy));
+        q->st.h2d_bytes += b1 - b0;
+        if (nmask) {
+            const unsigned long long m0 = w0 * 8, m1 = std::min(nmask_bytes, w1 * 8);
+            CUDA_TRY(cudaMemcpyAsync(s.nmask.p + m0, nmask + m0, m1 - m0, cudaMemcpyHostToDevice, ctx->s_copy));
+            q->st.h2d_bytes += m1 - m0;
+        }
+        cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(e, ctx->s_copy));
+        q->chunk_events.push_back(e);
+        ready.emplace_back(w1, e);
+    }
+    MLG_TRY(run_probe(q, s, s.bases.p, nmask ? s.nmask.p : nullptr, off ? s.off.p : nullptr, n_reads, read_len, nbases, &ready));
+    q->cur ^= 1;
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_push_ascii(mlg_query* q, const char* text, const uint64_t* off, uint64_t n_reads) {
+    MLG_TRY(check_push(q));
+    if (!n_reads) return MLG_OK;
+    if (!text || !off) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (off[0] != 0) { mlg_set_error("read_off[0] must be 0"); return MLG_ERR_ARG; }
+    const unsigned long long nbases = off[n_reads];
+    if (!nbases) return MLG_OK;
+    mlg_ctx* ctx = q->ctx;
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    Staging& s = q->stg[q->cur];
+    if (s.used) CUDA_TRY(cudaEventSynchronize(s.done));
+    const unsigned long long nwords = (nbases + 63) / 64;
+    const unsigned long long cap_words = round_up(nwords + 2, 2);
+    MLG_TRY(s.bases.ensure(cap_words * 16)); MLG_TRY(s.nmask.ensure(cap_words * 8));
+    MLG_TRY(s.text.ensure(nbases)); MLG_TRY(s.off.ensure(n_reads + 1));
+    CUDA_TRY(cudaMemcpyAsync(s.text.p, text, nbases, cudaMemcpyHostToDevice, ctx->s_copy));
+    CUDA_TRY(cudaMemcpyAsync(s.off.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+    q->st.h2d_bytes += nbases + (n_reads + 1) * 8;
+    cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(e, ctx->s_copy));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, e, 0));
+    q->chunk_events.push_back(e);
+    MLG_TRY(launch_pack_ascii(s.text.p, nbases, s.bases.p, s.nmask.p, ctx->s_comp));
+    q->st.gpu_launches += 1;
+    MLG_TRY(run_probe(q, s, s.bases.p, s.nmask.p, s.off.p, n_reads, 0, nbases, nullptr));
+    q->cur ^= 1;
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_sync(mlg_query* q) {
+    if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(q->ctx));
+    CUDA_TRY(cudaStreamSynchronize(q->ctx->s_copy));
+    CUDA_TRY(cudaStreamSynchronize(q->ctx->s_comp));
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_counts_export(mlg_query* q, uint8_t** d_counts, uint64_t* n_counts) {
+    if (!q || !d_counts || !n_counts) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
+    MLG_TRY(ensure_device(q->ctx));
+    MLG_TRY(launch_clamp_counts(q->cnt8.p, q->db->v.nd, (uint32_t)q->ci_min, q->ctx->s_comp));
+    q->st.gpu_launches += 1;
+    MLG_TRY(mlg_query_sync(q));
+    *d_counts = q->cnt8.p; *n_counts = q->db->v.nd;
+    return MLG_OK;
+}
+MLG_API int mlg_query_counts_import(mlg_query* q) {
+    if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
+    q->reduced = true;
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect) {
+    if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
+    if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
+    mlg_ctx* ctx = q->ctx; mlg_db* db = q->db; const DbView& v = db->v;
+    MLG_TRY(ensure_device(ctx));
+    cudaStream_t st = ctx->s_comp;
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    CUDA_TRY(cudaEventRecord(q->ev_q0, st));
+    // I = database k-mers seen >= ci_min times
+    MLG_TRY(launch_count_present(q->cnt8.p, v.nd, (uint32_t)q->ci_min, q->d_scalar.p, st));
+    unsigned long long ni = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ni, q->d_scalar.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    q->n_present = (uint32_t)ni;
+    MLG_TRY(q->present.alloc(ni));
+    MLG_TRY(launch_compact_present(q->cnt8.p, v.nd, (uint32_t)q->ci_min, q->present.p, q->d_scalar.p + 1, st));
+    // hit bitmap: nk planes of G*n bits
+    const unsigned long long total = (unsigned long long)v.G * v.n;
+    const unsigned long long words_per_k = (total + 31) / 32;
+    DevBuf<uint32_t> hitbits; MLG_TRY(hitbits.alloc(words_per_k * v.nk));
+    CUDA_TRY(cudaMemsetAsync(hitbits.p, 0, words_per_k * v.nk * 4, st));
+    MLG_TRY(launch_expand_hits(v, q->present.p, q->n_present, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, st));
+    const size_t cells = (size_t)v.G * v.nk;
+    DevBuf<unsigned long long> d_num; MLG_TRY(d_num.alloc(cells));
+    DevBuf<long long> o_num, o_den; DevBuf<double> o_ci;
+    MLG_TRY(o_num.alloc(cells)); MLG_TRY(o_den.alloc(cells)); MLG_TRY(o_ci.alloc(cells));
+    CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
+    MLG_TRY(launch_popcount_table(hitbits.p, words_per_k, v.G, v.n, v.nk, d_num.p, st));
+    MLG_TRY(launch_finalize(d_num.p, db->den_real.p, db->has_empty.p, v.G, v.nk, q->count_empty, o_num.p, o_den.p, o_ci.p, st));
+    q->st.gpu_launches += 4 + (q->n_present ? 1 : 0);
+    CUDA_TRY(cudaEventRecord(q->ev_q1, st));
+    if (num) { CUDA_TRY(cudaMemcpyAsync(num, o_num.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
+    if (den) { CUDA_TRY(cudaMemcpyAsync(den, o_den.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
+    if (ci) { CUDA_TRY(cudaMemcpyAsync(ci, o_ci.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
+    unsigned long long nk_host = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nk_host, q->d_nkmers.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    q->st.n_kmers = nk_host; q->st.n_intersect = ni;
+    q->st.d2h_bytes += 16;
+    // timings
+    float ms = 0; double probe_ms = 0;
+    for (auto& pe : q->probe_events) { if (cudaEventElapsedTime(&ms, pe.first, pe.second) == cudaSuccess) probe_ms += ms; }
+    q->st.ms_probe = probe_ms;
+    if (cudaEventElapsedTime(&ms, q->ev_q0, q->ev_q1) == cudaSuccess) q->st.ms_query = ms;
+    if (n_intersect) *n_intersect = ni;
+    q->finished = true;
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n) {
+    if (!q || !n) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (!q->finished) { mlg_set_error("call mlg_query_finish first"); return MLG_ERR_STATE; }
+    MLG_TRY(ensure_device(q->ctx));
+    *n = q->n_present;
+    if (!keys_out || !cap || !q->n_present) return MLG_OK;
+    DevBuf<key128> d; MLG_TRY(d.alloc(q->n_present));
+    MLG_TRY(launch_gather_keys(q->db->D_key.p, q->present.p, q->n_present, d.p, q->ctx->s_comp));
+    std::vector<key128> h(q->n_present);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), d.p, (size_t)q->n_present * sizeof(key128), cudaMemcpyDeviceToHost, q->ctx->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(q->ctx->s_comp));
+    std::sort(h.begin(), h.end(), [](const key128& a, const key128& b) { return key_lt(a, b); });
+    uint64_t m = std::min<uint64_t>(cap, q->n_present);
+    for (uint64_t i = 0; i < m; ++i) { keys_out[2 * i] = h[i].hi; keys_out[2 * i + 1] = h[i].lo; }
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_stats(mlg_query* q, mlg_stats* out) {
+    if (!q || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    *out = q->st;
+    return MLG_OK;
+}
+
+MLG_API int mlg_query_free(mlg_query* q) {
+    if (!q) return MLG_OK;
+    cudaSetDevice(q->ctx->device);
+    cudaStreamSynchronize(q->ctx->s_copy);
+    cudaStreamSynchronize(q->ctx->s_comp);
+    for (auto& pe : q->probe_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+    for (auto& e : q->chunk_events) cudaEventDestroy(e);
+    for (auto& s : q->stg) if (s.done) cudaEventDestroy(s.done);
+    if (q->ev_q0) cudaEventDestroy(q->ev_q0);
+    if (q->ev_q1) cudaEventDestroy(q->ev_q1);
+    delete q;
+    return MLG_OK;
+}
+
+}  // extern "C"

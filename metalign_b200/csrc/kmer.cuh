@@ -1,0 +1,95 @@
+// 2K-bit k-mer arithmetic shared by every kernel (and unit-tested on the host, tests/test_kmer_math.py).
+//
+// A K-mer (K <= 63) is a 2K-bit integer with the FIRST base in the most significant position
+// (A=0 C=1 G=2 T=3), so integer order == lexicographic order == KMC's canonical order
+// (reference: `kmc -k60` at scripts/select_db.py:50).  Held as (hi, lo) uint64.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define MLG_HD __host__ __device__ __forceinline__
+#else
+#define MLG_HD static inline
+#endif
+
+struct __attribute__((aligned(16))) key128 {
+    unsigned long long hi, lo;
+};
+
+MLG_HD bool key_eq(const key128& a, const key128& b) { return a.hi == b.hi && a.lo == b.lo; }
+MLG_HD bool key_lt(const key128& a, const key128& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+MLG_HD bool key_is_empty(const key128& a) { return a.hi == ~0ull; }
+
+// logical shifts of the 128-bit value, 0 <= s <= 127
+MLG_HD key128 key_shr(const key128& a, unsigned s) {
+    key128 r;
+    if (s == 0) return a;
+    if (s >= 64) { r.hi = 0; r.lo = a.hi >> (s - 64); }
+    else { r.lo = (a.lo >> s) | (a.hi << (64 - s)); r.hi = a.hi >> s; }
+    return r;
+}
+MLG_HD key128 key_shl(const key128& a, unsigned s) {
+    key128 r;
+    if (s == 0) return a;
+    if (s >= 64) { r.lo = 0; r.hi = a.lo << (s - 64); }
+    else { r.hi = (a.hi << s) | (a.lo >> (64 - s)); r.lo = a.lo << s; }
+    return r;
+}
+// mask of the low `bits` bits, 0 <= bits <= 128
+MLG_HD key128 key_mask(unsigned bits) {
+    key128 m;
+    if (bits >= 128) { m.hi = ~0ull; m.lo = ~0ull; }
+    else if (bits >= 64) { m.lo = ~0ull; m.hi = (bits == 64) ? 0ull : ((1ull << (bits - 64)) - 1ull); }
+    else { m.hi = 0; m.lo = (bits == 0) ? 0ull : ((1ull << bits) - 1ull); }
+    return m;
+}
+MLG_HD key128 key_and(const key128& a, const key128& b) { key128 r; r.hi = a.hi & b.hi; r.lo = a.lo & b.lo; return r; }
+
+// reverse the order of the 32 two-bit groups of a 64-bit word
+MLG_HD unsigned long long rev2_64(unsigned long long x) {
+    x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+    return (x >> 32) | (x << 32);
+}
+// reverse complement of a k-base value (k <= 64)
+MLG_HD key128 key_rc(const key128& a, unsigned k) {
+    key128 full;                       // reverse all 64 groups of the complemented 128-bit value ...
+    full.hi = rev2_64(~a.lo);
+    full.lo = rev2_64(~a.hi);
+    return key_shr(full, 128 - 2 * k); // ... then drop the (64-k) groups that came from the zero padding
+}
+MLG_HD key128 key_canon(const key128& a, unsigned K) {
+    key128 r = key_rc(a, K);
+    return key_lt(r, a) ? r : a;
+}
+// the k-base window starting `off` bases into a K-base value
+MLG_HD key128 key_sub(const key128& x, unsigned K, unsigned off, unsigned k) {
+    return key_and(key_shr(x, 2 * (K - off - k)), key_mask(2 * k));
+}
+// the leading k bases of a K-base value
+MLG_HD key128 key_prefix(const key128& x, unsigned K, unsigned k) { return key_shr(x, 2 * (K - k)); }
+
+// 64-bit mix of a canonical key: bucket index comes from the high bits, fingerprint from the low bits
+MLG_HD unsigned long long key_hash(const key128& c) {
+    unsigned long long x = c.lo ^ (c.hi * 0x9E3779B97F4A7C15ull);
+    x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
+MLG_HD unsigned long long mulhi64(unsigned long long a, unsigned long long b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+// monotone in h, so entries sorted by hash are grouped by bucket
+MLG_HD unsigned long long hash_bucket(unsigned long long h, unsigned long long nbuckets) { return mulhi64(h, nbuckets); }
+// 31-bit non-zero fingerprint (bit 31 of a bucket's first word is the overflow flag, 0 = empty slot)
+MLG_HD unsigned hash_fp(unsigned long long h) {
+    unsigned f = (unsigned)h & 0x7FFFFFFFu;
+    return f ? f : 1u;
+}

@@ -1,0 +1,127 @@
+// Internal declarations shared by the translation units of libmetalign_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "kmer.cuh"
+#include "../../include/metalign_b200.h"
+
+#define MLG_MAX_KS 8
+#define MLG_TILE_WORDS 256u     // 64-base words per K1 tile == threads per CTA
+
+void mlg_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            mlg_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return MLG_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define MLG_TRY(expr)                \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != MLG_OK) return _r; \
+    } while (0)
+
+// owning device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            mlg_set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            return MLG_ERR_NOMEM;
+        }
+        n = count;
+        return MLG_OK;
+    }
+    int ensure(size_t count) { return (count <= n && p) ? MLG_OK : alloc(count); }
+};
+
+struct mlg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t s_comp = nullptr;   // kernels
+    cudaStream_t s_copy = nullptr;   // host<->device copies
+};
+
+// device view of a database (plain pointers, passed to kernels by value)
+struct DbView {
+    uint32_t G, n, K, nk;
+    uint32_t ks[MLG_MAX_KS];
+    uint32_t np;                 // non-empty sketch entries
+    uint32_t nd;                 // distinct canonical k-mers
+    // P: stored-orientation entries sorted by key
+    const key128* P_key;
+    const uint32_t* P_slot;      // g*n + j
+    uint32_t pbits;              // bucket index on the top pbits bits of the 2K-bit key
+    const uint32_t* pidx;        // 2^pbits + 1
+    const uint32_t* rep;         // nk * (G*n): representative slot of the (genome, k-prefix) class
+    // D: distinct canonical keys sorted by hash; level-1 fingerprint buckets
+    const key128* D_key;
+    const uint32_t* bstart;      // nbuckets + 1
+    const uint32_t* T1;          // nbuckets * slots
+    unsigned long long nbuckets;
+    uint32_t slots;              // 4 (16-byte buckets) or 8 (32-byte buckets)
+};
+
+struct mlg_db {
+    mlg_ctx* ctx = nullptr;
+    DbView v{};
+    DevBuf<key128> P_key;
+    DevBuf<uint32_t> P_slot, pidx, rep, bstart, T1;
+    DevBuf<key128> D_key;
+    DevBuf<long long> den_real;      // G*nk
+    DevBuf<unsigned char> has_empty; // G
+    double build_ms = 0;
+};
+
+int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t n, uint32_t K,
+                        const uint32_t* ks, uint32_t nk, mlg_db** out);
+
+// ---- kernels' host launchers (probe.cu / query.cu) ----
+struct ProbeArgs {
+    const uint4* bases;                 // 16 bytes (64 bases) per word
+    const unsigned long long* nmask;    // 8 bytes per word, may be null
+    const unsigned long long* smask;    // 8 bytes per word (read starts)
+    unsigned long long nwords;          // words in the stream
+    unsigned long long nbases;          // bases in the stream
+    unsigned long long w_begin, w_end;  // word range of this launch (w_begin multiple of MLG_TILE_WORDS)
+    unsigned char* cnt8;                // nd saturating occurrence counters
+    unsigned long long* n_kmers;        // device accumulator of valid windows
+};
+int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaStream_t st);
+int launch_build_smask_fixed(unsigned long long* smask, unsigned long long nwords_alloc, unsigned long long nbases,
+                             uint32_t read_len, cudaStream_t st);
+int launch_build_smask_offsets(unsigned long long* smask, const unsigned long long* off, unsigned long long nreads,
+                               cudaStream_t st);
+int launch_pack_ascii(const unsigned char* text, unsigned long long nbases, unsigned char* bases, unsigned char* nmask,
+                      cudaStream_t st);
+int launch_ascii_to_keys(const unsigned char* text, unsigned long long nslots, uint32_t K, key128* keys, cudaStream_t st);
+
+int launch_clamp_counts(unsigned char* cnt8, uint32_t nd, uint32_t ci_min, cudaStream_t st);
+int launch_count_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, unsigned long long* d_count, cudaStream_t st);
+int launch_compact_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* d_cursor,
+                           cudaStream_t st);
+int launch_expand_hits(const DbView& db, const uint32_t* present, uint32_t n_present, int gate_none, uint32_t* hitbits,
+                       unsigned long long words_per_k, cudaStream_t st);
+int launch_popcount_table(const uint32_t* hitbits, unsigned long long words_per_k, uint32_t G, uint32_t n, uint32_t nk,
+                          unsigned long long* num, cudaStream_t st);
+int launch_finalize(const unsigned long long* num, const long long* den_real, const unsigned char* has_empty, uint32_t G,
+                    uint32_t nk, int count_empty, long long* out_num, long long* out_den, double* out_ci, cudaStream_t st);
+int launch_gather_keys(const key128* D_key, const uint32_t* present, uint32_t n_present, key128* out, cudaStream_t st);

@@ -1,0 +1,12 @@
+// Host build of metalign_b200/csrc/kmer.cuh for tests/test_kmer_math.py (the header is __host__ __device__).
+#include "../metalign_b200/csrc/kmer.cuh"
+extern "C" {
+void t_rc(unsigned long long hi, unsigned long long lo, unsigned k, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_rc(a, k); out[0] = r.hi; out[1] = r.lo; }
+void t_canon(unsigned long long hi, unsigned long long lo, unsigned k, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_canon(a, k); out[0] = r.hi; out[1] = r.lo; }
+void t_sub(unsigned long long hi, unsigned long long lo, unsigned K, unsigned off, unsigned k, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_sub(a, K, off, k); out[0] = r.hi; out[1] = r.lo; }
+void t_prefix(unsigned long long hi, unsigned long long lo, unsigned K, unsigned k, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_prefix(a, K, k); out[0] = r.hi; out[1] = r.lo; }
+void t_shl(unsigned long long hi, unsigned long long lo, unsigned s, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_shl(a, s); out[0] = r.hi; out[1] = r.lo; }
+unsigned long long t_hash(unsigned long long hi, unsigned long long lo) { key128 a{hi, lo}; return key_hash(a); }
+unsigned long long t_bucket(unsigned long long h, unsigned long long nb) { return hash_bucket(h, nb); }
+unsigned t_fp(unsigned long long h) { return hash_fp(h); }
+}

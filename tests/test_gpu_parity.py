@@ -1,0 +1,298 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+Bit-exact for counts / denominators / the intersection set; containment compared with == as well
+(both sides do one IEEE double division of identical integers; the north-star tolerance is 1e-12)."""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+
+import synth
+from metalign_b200 import codec, dbformat
+from metalign_b200.api import Database, MlgError
+from oracle import oracle_py
+
+from helpers import adversarial_case, oracle_c_run
+
+pytestmark = pytest.mark.gpu
+KS = (30, 40, 50, 60)
+
+
+def _check(res, I_gpu, ref, I_ref, tag=""):
+    assert res["n_kmers"] == ref["n_kmers"], tag
+    assert res["n_intersect"] == ref["n_intersect"], tag
+    assert np.array_equal(I_gpu, I_ref), tag
+    assert np.array_equal(res["den"], ref["den"]), tag
+    assert np.array_equal(res["num"], ref["num"]), tag
+    assert np.array_equal(res["ci"], ref["ci"]), tag
+    assert np.max(np.abs(res["ci"] - ref["ci"]), initial=0.0) <= 1e-12, tag
+
+
+def test_golden_cases(ctx, golden_cases):
+    for c in golden_cases:
+        db = Database.from_sketches(ctx, c["sketches"], c["K"], c["ks"])
+        for e in c["expect"]:
+            q = db.query(e["ci_min"], e["gate"], e["count_empty_in_den"])
+            q.push_reads(c["reads"])
+            r = q.finish()
+            I = [codec.key_to_kmer(a, b, c["K"]) for a, b in q.intersection()]
+            q.close()
+            assert r["num"].tolist() == e["num"], (c["name"], e["gate"])
+            assert r["den"].tolist() == e["den"], (c["name"], e["gate"])
+            assert I == e["I"], (c["name"], e["gate"])
+        db.close()
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_adversarial_vs_oracle(ctx, seed):
+    rng = random.Random(1000 + seed)
+    c = adversarial_case(rng)
+    G, n = len(c["sketches"]), len(c["sketches"][0])
+    keys = codec.sketches_to_keys(c["sketches"], c["K"])
+    db = Database.from_keys(ctx, keys, G, n, c["K"], c["ks"])
+    for gate in ("exact", "none"):
+        ci_min = rng.choice([1, 2, 3])
+        ce = rng.random() < 0.5
+        ref, I_ref = oracle_c_run(keys, G, n, c["K"], c["ks"], lambda q: q.push_reads(c["reads"]), ci_min, gate, ce)
+        q = db.query(ci_min, gate, ce)
+        q.push_reads(c["reads"])
+        res = q.finish()
+        _check(res, q.intersection(), ref, I_ref, (seed, gate))
+        q.close()
+        py = oracle_py.run(c["reads"], c["sketches"], K=c["K"], ks=c["ks"], ci_min=ci_min, gate=gate, count_empty_in_den=ce)
+        assert res["num"].tolist() == py["num"]
+    db.close()
+
+
+@pytest.fixture(scope="module")
+def workload(ctx):
+    p = synth.params(G=300, n=200, seed=11, len_min=20000, len_max=60000, n_present=40)
+    keys = synth.sketch_keys(p)
+    nreads = 60000
+    bases, nmask = synth.reads_packed(p, 0, nreads)
+    refs = {}
+    for gate in ("exact", "none"):
+        refs[gate] = oracle_c_run(keys, p.G, p.n, 60, KS, lambda q: q.push_packed(bases, nmask, None, nreads, p.read_len), 2, gate, True)
+    db = Database.from_keys(ctx, keys, p.G, p.n, 60, KS)
+    yield dict(p=p, keys=keys, nreads=nreads, bases=bases, nmask=nmask, refs=refs, db=db)
+    db.close()
+
+
+def test_synthetic_packed_host_fixed_len(workload):
+    w = workload
+    assert w["refs"]["exact"][0]["n_intersect"] > 100
+    for gate in ("exact", "none"):
+        q = w["db"].query(2, gate, True)
+        q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+        res = q.finish()
+        _check(res, q.intersection(), *w["refs"][gate], tag=gate)
+        assert res["stats"]["gpu_launches"] >= 5 and res["stats"]["ms_probe"] > 0
+        q.close()
+
+
+def test_synthetic_packed_host_offsets_and_split_batches(workload):
+    w = workload
+    L = w["p"].read_len
+    reads = codec.unpack_reads(w["bases"], w["nmask"], None, w["nreads"], L)
+    q = w["db"].query()
+    cut = [0, 1, 7000, 7001, 31000, w["nreads"]]
+    for a, b in zip(cut[:-1], cut[1:]):
+        bs, nm, off = codec.pack_reads(reads[a:b])
+        q.push_packed(bs, nm, off, b - a)
+        q.sync()
+    res = q.finish()
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+
+
+def test_synthetic_ascii_push(workload):
+    w = workload
+    text = synth.reads_ascii(w["p"], 0, w["nreads"]).reshape(-1)
+    off = np.arange(w["nreads"] + 1, dtype=np.uint64) * np.uint64(w["p"].read_len)
+    q = w["db"].query()
+    q.push_ascii(text, off)
+    res = q.finish()
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+
+
+def test_no_nmask_means_no_n(workload):
+    w = workload
+    ref, I_ref = oracle_c_run(w["keys"], w["p"].G, w["p"].n, 60, KS,
+                              lambda q: q.push_packed(w["bases"], None, None, w["nreads"], w["p"].read_len))
+    q = w["db"].query()
+    q.push_packed(w["bases"], None, None, w["nreads"], w["p"].read_len)
+    res = q.finish()
+    _check(res, q.intersection(), ref, I_ref)
+    q.close()
+
+
+def test_device_generator_and_device_push(ctx, workload):
+    import torch
+    w = workload
+    p = w["p"]
+    nbb, nmb = synth.packed_sizes(w["nreads"], p.read_len)
+    d_b = torch.empty(nbb, dtype=torch.uint8, device="cuda")
+    d_m = torch.empty(nmb, dtype=torch.uint8, device="cuda")
+    assert synth.cuda_lib().syn_cuda_gen_reads_packed(C.byref(p), 0, w["nreads"], d_b.data_ptr(), d_m.data_ptr(), None) == 0
+    assert np.array_equal(d_b.cpu().numpy(), w["bases"]) and np.array_equal(d_m.cpu().numpy(), w["nmask"])
+    d_k = torch.empty(p.G * p.n * 2, dtype=torch.int64, device="cuda")
+    assert synth.cuda_lib().syn_cuda_gen_sketch_keys(C.byref(p), d_k.data_ptr(), None) == 0
+    assert np.array_equal(d_k.cpu().numpy().view(np.uint64).reshape(-1, 2), w["keys"])
+    db2 = Database.from_device_keys(ctx, d_k.data_ptr(), p.G, p.n, 60, KS)
+    assert db2.n_distinct == w["db"].n_distinct and db2.n_entries == w["db"].n_entries
+    q = db2.query()
+    q.push_packed_ptr(d_b.data_ptr(), d_m.data_ptr(), None, w["nreads"], p.read_len, device=True)
+    res = q.finish()
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+    # device offsets
+    d_off = torch.arange(w["nreads"] + 1, dtype=torch.int64, device="cuda") * p.read_len
+    q = db2.query()
+    q.push_packed_ptr(d_b.data_ptr(), d_m.data_ptr(), d_off.data_ptr(), w["nreads"], 0, device=True)
+    res = q.finish()
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+    db2.close()
+
+
+def test_counter_export_import_equals_single_run(workload):
+    """the multi-GPU seam on one GPU: two half queries, counters summed, presence derived from the sum"""
+    import torch
+    w = workload
+    L = w["p"].read_len
+    reads = codec.unpack_reads(w["bases"], w["nmask"], None, w["nreads"], L)
+    halves = []
+    for part in (reads[0::2], reads[1::2]):
+        q = w["db"].query()
+        bs, nm, off = codec.pack_reads(part)
+        q.push_packed(bs, nm, off, len(part))
+        halves.append(q)
+    from metalign_b200.dist import device_view_u8
+    views = [device_view_u8(*q.counts_export()) for q in halves]
+    assert int((views[0].to(torch.int32) + views[1].to(torch.int32)).max()) <= 4
+    views[0] += views[1]            # what the all-reduce does, on one GPU
+    torch.cuda.synchronize()
+    halves[0].counts_import()
+    res = halves[0].finish()
+    ref, I_ref = w["refs"]["exact"]
+    assert np.array_equal(res["num"], ref["num"]) and res["n_intersect"] == ref["n_intersect"]
+    assert np.array_equal(halves[0].intersection(), I_ref)
+    with pytest.raises(MlgError):
+        halves[0].push_reads(["ACGT"])
+    for q in halves:
+        q.close()
+
+
+def test_mlgdb_roundtrip(ctx, workload, tmp_path):
+    w = workload
+    p = w["p"]
+    names = ["taxid_%d_genomic.fna.gz" % g for g in range(p.G)]
+    path = str(tmp_path / "db.mlgdb")
+    dbformat.write(path, w["keys"], names, p.G, p.n, 60, KS)
+    assert np.array_equal(dbformat.read_keys(path), w["keys"])
+    db = Database.load(ctx, path)
+    assert db.names == names and (db.G, db.n, db.K, db.ks) == (p.G, p.n, 60, KS)
+    q = db.query()
+    q.push_packed(w["bases"], w["nmask"], None, w["nreads"], p.read_len)
+    res = q.finish()
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    assert np.array_equal(db.denominators(True), w["refs"]["exact"][0]["den"])
+    q.close()
+    db.close()
+
+
+def test_sixteen_byte_buckets(ctx, workload, monkeypatch):
+    w = workload
+    monkeypatch.setenv("MLG_BUCKET_SLOTS", "4")
+    monkeypatch.setenv("MLG_BUCKET_LOAD", "3.0")   # forces many overflowing buckets through the exact path
+    db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
+    q = db.query()
+    q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+    res = q.finish()
+    assert res["stats"]["bucket_bytes"] == 16
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+    db.close()
+
+
+def test_overfull_32_byte_buckets(ctx, workload, monkeypatch):
+    w = workload
+    monkeypatch.setenv("MLG_BUCKET_LOAD", "7.5")
+    db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
+    q = db.query(2, "none", False)
+    q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+    res = q.finish()
+    ref, I_ref = oracle_c_run(w["keys"], w["p"].G, w["p"].n, 60, KS,
+                              lambda oq: oq.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len), 2, "none", False)
+    _check(res, q.intersection(), ref, I_ref)
+    q.close()
+    db.close()
+
+
+def test_other_k_and_ranges(ctx):
+    """K=31 (key fits one word), K=45 with a 3-value k range, K=63 (largest)."""
+    for K, ks, seed in ((31, (15, 21, 31), 3), (45, (20, 33, 45), 4), (63, (31, 47, 63), 5), (60, (60,), 6)):
+        p = synth.params(G=40, n=50, K=K, seed=seed, len_min=5000, len_max=9000, n_present=10, read_len=100)
+        keys = synth.sketch_keys(p)
+        nreads = 20000
+        bases, nmask = synth.reads_packed(p, 0, nreads)
+        db = Database.from_keys(ctx, keys, p.G, p.n, K, ks)
+        for gate in ("exact", "none"):
+            ref, I_ref = oracle_c_run(keys, p.G, p.n, K, ks, lambda q: q.push_packed(bases, nmask, None, nreads, 100), 2, gate, True)
+            q = db.query(2, gate, True)
+            q.push_packed(bases, nmask, None, nreads, 100)
+            res = q.finish()
+            _check(res, q.intersection(), ref, I_ref, (K, gate))
+            assert ref["n_intersect"] > 0
+            q.close()
+        db.close()
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    p = synth.params(G=5, n=8, seed=2, len_min=3000, len_max=4000, n_present=3)
+    keys = synth.sketch_keys(p)
+    db = Database.from_keys(ctx, keys, p.G, p.n, 60, KS)
+    q = db.query()
+    r = q.finish()          # no reads at all
+    assert r["num"].sum() == 0 and r["n_kmers"] == 0 and r["n_intersect"] == 0 and q.intersection().shape == (0, 2)
+    q.close()
+    q = db.query()
+    q.push_reads(["", "ACGT", "N" * 200, "acgtn" * 30])   # nothing long enough / valid
+    q.push_reads([])
+    r = q.finish()
+    assert r["n_intersect"] == 0 and r["n_kmers"] == oracle_py.run(["", "ACGT", "N" * 200, "acgtn" * 30], [[]], K=60)["n_kmers"]
+    q.close()
+    db.close()
+    # a database whose slots are all empty
+    empty = np.full((6, 2), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    db = Database.from_keys(ctx, empty, 2, 3, 60, KS)
+    assert db.n_distinct == 0 and db.n_entries == 0
+    q = db.query()
+    q.push_reads(["ACGT" * 40])
+    r = q.finish()
+    assert r["num"].sum() == 0 and r["den"].tolist() == [[1] * 4, [1] * 4] and r["n_kmers"] == 101
+    q.close()
+    db.close()
+    with pytest.raises(MlgError):
+        Database.from_keys(ctx, keys, p.G, p.n, 60, (40, 30))   # not ascending
+    with pytest.raises(MlgError):
+        Database.from_sketches(ctx, [["ACGN" * 15]], 60, KS)     # non-ACGT sketch k-mer
+
+
+def test_midsize_against_oracle(ctx):
+    """1M reads x 150 against 2000 genomes x 1000 slots: full table compared with the C oracle."""
+    p = synth.params(G=2000, n=1000, seed=20200529, n_present=60)
+    keys = synth.sketch_keys(p)
+    nreads = 1_000_000
+    bases, nmask = synth.reads_packed(p, 0, nreads)
+    ref, I_ref = oracle_c_run(keys, p.G, p.n, 60, KS, lambda q: q.push_packed(bases, nmask, None, nreads, p.read_len))
+    db = Database.from_keys(ctx, keys, p.G, p.n, 60, KS)
+    q = db.query()
+    q.push_packed(bases, nmask, None, nreads, p.read_len)
+    res = q.finish()
+    _check(res, q.intersection(), ref, I_ref)
+    assert res["n_intersect"] > 1000
+    q.close()
+    db.close()

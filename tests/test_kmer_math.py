@@ -1,0 +1,74 @@
+"""The 2K-bit k-mer arithmetic of csrc/kmer.cuh, compiled for the host and checked against strings."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import pytest
+
+from metalign_b200 import codec
+from oracle import oracle_py
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def kh(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("kmer") / "libkmer_host.so")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-O2", "-shared", "-fPIC", "-x", "c++", os.path.join(HERE, "kmer_host.cpp"), "-o", out])
+    L = C.CDLL(out)
+    u64 = C.c_ulonglong
+    for f in (L.t_rc, L.t_canon):
+        f.argtypes = [u64, u64, C.c_uint, C.POINTER(u64 * 2)]
+    L.t_sub.argtypes = [u64, u64, C.c_uint, C.c_uint, C.c_uint, C.POINTER(u64 * 2)]
+    L.t_prefix.argtypes = [u64, u64, C.c_uint, C.c_uint, C.POINTER(u64 * 2)]
+    L.t_shl.argtypes = [u64, u64, C.c_uint, C.POINTER(u64 * 2)]
+    L.t_hash.argtypes = [u64, u64]
+    L.t_hash.restype = u64
+    L.t_bucket.argtypes = [u64, u64]
+    L.t_bucket.restype = u64
+    L.t_fp.argtypes = [u64]
+    L.t_fp.restype = C.c_uint
+    return L
+
+
+def _call(fn, s, *args):
+    hi, lo = codec.kmer_to_key(s)
+    out = (C.c_ulonglong * 2)()
+    fn(hi, lo, *args, C.byref(out))
+    return out[0], out[1]
+
+
+def test_rc_canon_sub_prefix(kh):
+    rng = random.Random(3)
+    for _ in range(400):
+        K = rng.randint(1, 63)
+        s = "".join(rng.choice("ACGT") for _ in range(K))
+        assert codec.key_to_kmer(*_call(kh.t_rc, s, K), K) == oracle_py.rc(s)
+        assert codec.key_to_kmer(*_call(kh.t_canon, s, K), K) == oracle_py.canon(s)
+        k = rng.randint(1, K)
+        off = rng.randint(0, K - k)
+        assert codec.key_to_kmer(*_call(kh.t_sub, s, K, off, k), k) == s[off:off + k]
+        assert codec.key_to_kmer(*_call(kh.t_prefix, s, K, k), k) == s[:k]
+        hi, lo = _call(kh.t_shl, s[:k], 2 * (K - k))
+        assert codec.key_to_kmer(hi, lo, K) == s[:k] + "A" * (K - k)
+
+
+def test_extremes(kh):
+    for K in (1, 31, 32, 33, 60, 63):
+        for ch in "ACGT":
+            s = ch * K
+            assert codec.key_to_kmer(*_call(kh.t_rc, s, K), K) == oracle_py.rc(s)
+
+
+def test_hash_bucket_monotone_and_fp_nonzero(kh):
+    rng = random.Random(5)
+    hs = sorted(rng.getrandbits(64) for _ in range(2000))
+    for nb in (1, 7, 1000, 2**31 + 11):
+        b = [kh.t_bucket(h, nb) for h in hs]
+        assert b == sorted(b) and max(b) < nb
+    assert kh.t_fp(0) == 1 and kh.t_fp(1 << 31) == 1
+    assert all(0 < kh.t_fp(h) < 2**31 for h in hs)
+    # different keys hash differently (sanity, not a guarantee)
+    assert len({kh.t_hash(rng.getrandbits(56), rng.getrandbits(64)) for _ in range(5000)}) == 5000
