@@ -16,6 +16,83 @@ void mlg_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---------------------------------------------------------------- caching device-memory pool
+#include <map>
+#include <mutex>
+namespace {
+struct PoolBlock { void* p; size_t bytes; };
+struct Pool {
+    std::mutex mu;
+    std::map<int, std::vector<PoolBlock>> free_blocks;   // per device
+    std::map<void*, std::pair<int, size_t>> live;        // ptr -> (device, bytes)
+};
+Pool& pool() { static Pool* p = new Pool(); return *p; }
+constexpr size_t POOL_MAX_CACHED_PER_DEVICE = 64;
+}  // namespace
+
+void* mlg_pool_alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Pool& P = pool();
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        auto& v = P.free_blocks[dev];
+        int best = -1;
+        for (int i = 0; i < (int)v.size(); ++i)
+            if (v[i].bytes >= bytes && v[i].bytes <= bytes + bytes / 4 + 4096 && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+        if (best >= 0) {
+            PoolBlock b = v[best];
+            v.erase(v.begin() + best);
+            P.live[b.p] = {dev, b.bytes};
+            return b.p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        mlg_pool_trim(dev);                      // give cached blocks back and retry once
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        mlg_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(P.mu);
+    P.live[p] = {dev, bytes};
+    return p;
+}
+void mlg_pool_free(void* p) {
+    if (!p) return;
+    Pool& P = pool();
+    std::unique_lock<std::mutex> g(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) { g.unlock(); cudaFree(p); return; }
+    int dev = it->second.first; size_t bytes = it->second.second;
+    P.live.erase(it);
+    auto& v = P.free_blocks[dev];
+    if (v.size() >= POOL_MAX_CACHED_PER_DEVICE) {
+        // evict the largest cached block rather than growing without bound
+        size_t big = 0;
+        for (size_t i = 1; i < v.size(); ++i) if (v[i].bytes > v[big].bytes) big = i;
+        void* victim = v[big].p;
+        v[big] = {p, bytes};
+        g.unlock();
+        cudaFree(victim);
+        return;
+    }
+    v.push_back({p, bytes});
+}
+void mlg_pool_trim(int device) {
+    Pool& P = pool();
+    std::vector<PoolBlock> blocks;
+    {
+        std::lock_guard<std::mutex> g(P.mu);
+        blocks.swap(P.free_blocks[device]);
+    }
+    for (auto& b : blocks) cudaFree(b.p);
+}
+
 namespace {
 
 constexpr unsigned long long CHUNK_WORDS = 64ull * MLG_TILE_WORDS * 32ull;   // 524288 words = 8 MiB of packed bases per copy chunk
@@ -157,6 +234,7 @@ MLG_API int mlg_ctx_destroy(mlg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    mlg_pool_trim(ctx->device);
     delete ctx;
     return MLG_OK;
 }
@@ -274,7 +352,7 @@ MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode,
     CUDA_TRY(cudaMemsetAsync(q->d_nkmers.p, 0, 8, ctx->s_comp));
     CUDA_TRY(cudaEventCreate(&q->ev_q0)); CUDA_TRY(cudaEventCreate(&q->ev_q1));
     q->st.n_db_entries = db->v.np; q->st.n_db_distinct = db->v.nd;
-    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4;
+    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4; q->st.filter_log2_words = db->v.fbits;
     guard.q = nullptr;
     *out = q;
     return MLG_OK;

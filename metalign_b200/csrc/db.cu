@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "mlg_internal.h"
 
 namespace {
@@ -107,15 +108,19 @@ __global__ void k_gather_key(const key128* src, const uint32_t* idx, uint32_t n,
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
 }
-__global__ void k_hbucket_hist(const unsigned long long* h, uint32_t nd, unsigned long long nbuckets, uint32_t* counts) {
+__global__ void k_hbucket_hist(const unsigned long long* h, uint32_t nd, uint32_t bbits, uint32_t* counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nd) atomicAdd(&counts[hash_bucket(h[i], nbuckets)], 1u);
+    if (i < nd) atomicAdd(&counts[hash_bucket(h[i], bbits)], 1u);
 }
-__global__ void k_fill_t1(const unsigned long long* h, uint32_t nd, unsigned long long nbuckets, const uint32_t* bstart,
+__global__ void k_fill_filter(const unsigned long long* h, uint32_t nd, uint32_t fbits, unsigned long long* F) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nd) atomicOr(&F[filter_word(h[i], fbits)], filter_mask(h[i]));
+}
+__global__ void k_fill_t1(const unsigned long long* h, uint32_t nd, uint32_t bbits, const uint32_t* bstart,
                           uint32_t slots, uint32_t* T1) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nd) return;
-    unsigned long long b = hash_bucket(h[e], nbuckets);
+    unsigned long long b = hash_bucket(h[e], bbits);
     uint32_t s = e - bstart[b];
     uint32_t c = bstart[b + 1] - bstart[b];
     if (s < slots) {
@@ -337,20 +342,56 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
     {
         uint32_t slots_per_bucket = 8;
         if (const char* s = getenv("MLG_BUCKET_SLOTS")) { int x = atoi(s); if (x == 4 || x == 8) slots_per_bucket = (uint32_t)x; }
-        double load = slots_per_bucket / 4.0;     // mean entries per bucket
+        double load = slots_per_bucket / 4.0;     // upper bound on the mean entries per bucket
         if (const char* s = getenv("MLG_BUCKET_LOAD")) { double x = atof(s); if (x > 0.01 && x <= slots_per_bucket) load = x; }
-        unsigned long long nb = (unsigned long long)ceil((double)nd / load);
-        if (nb < 1) nb = 1;
-        if (nb >= 0xFFFFFFF0ull) { mlg_set_error("too many buckets"); return MLG_ERR_ARG; }
-        v.nbuckets = nb; v.slots = slots_per_bucket;
+        uint32_t bbits = 0;
+        while (bbits < 31 && (double)(1ull << bbits) * load < (double)nd) ++bbits;
+        if ((double)(1ull << bbits) * load < (double)nd) { mlg_set_error("too many buckets"); return MLG_ERR_ARG; }
+        unsigned long long nb = 1ull << bbits;
+        v.nbuckets = nb; v.bbits = bbits; v.slots = slots_per_bucket;
         MLG_TRY(db->bstart.alloc(nb + 1));
         CUDA_TRY(cudaMemsetAsync(db->bstart.p, 0, (nb + 1) * 4, st));
-        if (nd) k_hbucket_hist<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, nb, db->bstart.p);
+        if (nd) k_hbucket_hist<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p);
         MLG_TRY(exclusive_scan_u32(db->bstart.p, nb, st));
         MLG_TRY(db->T1.alloc(nb * slots_per_bucket + 8));
         CUDA_TRY(cudaMemsetAsync(db->T1.p, 0, (nb * slots_per_bucket + 8) * 4, st));
-        if (nd) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, nb, db->bstart.p, slots_per_bucket, db->T1.p);
+        if (nd) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p, slots_per_bucket, db->T1.p);
         v.bstart = db->bstart.p; v.T1 = db->T1.p;
+        // Bloom prefilter sized to stay L2-resident: at most MLG_FILTER_MB (default 64 MiB), at most ~16 bits per key;
+        // below 2 bits per key it would pass almost everything and is left out.
+        double max_mb = 64.0;
+        if (const char* s = getenv("MLG_FILTER_MB")) max_mb = atof(s);
+        uint32_t fbits = 0;
+        if (nd && max_mb >= 1.0 / 1024) {
+            while (fbits < 40 && (double)(1ull << fbits) * 64.0 < 16.0 * (double)nd) ++fbits;
+            while (fbits > 0 && ((double)(1ull << fbits) * 8.0 > max_mb * 1048576.0 || fbits > 26)) --fbits;
+            if ((double)(1ull << fbits) * 64.0 < 2.0 * (double)nd) fbits = 0;
+        }
+        v.fbits = fbits; v.F = nullptr;
+        if (fbits) {
+            MLG_TRY(db->F.alloc(1ull << fbits));
+            CUDA_TRY(cudaMemsetAsync(db->F.p, 0, (1ull << fbits) * 8, st));
+            k_fill_filter<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, fbits, db->F.p);
+            v.F = db->F.p;
+            // optional: pin the prefilter in L2 (persisting access-policy window on the compute stream)
+            const char* pe = getenv("MLG_L2_PERSIST");
+            if (pe && atoi(pe) > 0) {
+                cudaDeviceProp prop;
+                if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                    size_t fbytes = (size_t)8 << fbits;
+                    size_t carve = fbytes < (size_t)prop.persistingL2CacheMaxSize ? fbytes : (size_t)prop.persistingL2CacheMaxSize;
+                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+                    cudaStreamAttrValue attr;
+                    memset(&attr, 0, sizeof(attr));
+                    attr.accessPolicyWindow.base_ptr = (void*)db->F.p;
+                    attr.accessPolicyWindow.num_bytes = fbytes < (size_t)prop.accessPolicyMaxWindowSize ? fbytes : (size_t)prop.accessPolicyMaxWindowSize;
+                    attr.accessPolicyWindow.hitRatio = (float)((double)carve / (double)fbytes);
+                    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+                }
+            }
+        }
     }
     CUDA_TRY(cudaEventRecord(e1, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -358,6 +399,7 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); db->build_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     guard.d = nullptr;
+    mlg_pool_trim(ctx->device);   // the build's multi-GB temporaries should not stay cached
     *out = db;
     return MLG_OK;
 }

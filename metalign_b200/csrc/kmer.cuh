@@ -79,15 +79,14 @@ MLG_HD unsigned long long key_hash(const key128& c) {
     x ^= x >> 32;
     return x;
 }
-MLG_HD unsigned long long mulhi64(unsigned long long a, unsigned long long b) {
-#ifdef __CUDA_ARCH__
-    return __umul64hi(a, b);
-#else
-    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
-#endif
+// Tables have power-of-two sizes, indexed by the TOP bits of the hash: monotone in h, so entries sorted
+// by hash are grouped by bucket.
+MLG_HD unsigned long long hash_bucket(unsigned long long h, unsigned bbits) { return bbits ? (h >> (64 - bbits)) : 0ull; }
+// L2-resident prefilter: one 64-bit word per probe (top fbits bits of h), two bits inside it
+MLG_HD unsigned long long filter_word(unsigned long long h, unsigned fbits) { return fbits ? (h >> (64 - fbits)) : 0ull; }
+MLG_HD unsigned long long filter_mask(unsigned long long h) {
+    return (1ull << ((h >> 35) & 63ull)) | (1ull << ((h >> 29) & 63ull));
 }
-// monotone in h, so entries sorted by hash are grouped by bucket
-MLG_HD unsigned long long hash_bucket(unsigned long long h, unsigned long long nbuckets) { return mulhi64(h, nbuckets); }
 // 31-bit non-zero fingerprint (bit 31 of a bucket's first word is the overflow flag, 0 = empty slot)
 MLG_HD unsigned hash_fp(unsigned long long h) {
     unsigned f = (unsigned)h & 0x7FFFFFFFu;

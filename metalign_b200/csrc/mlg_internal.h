@@ -28,6 +28,13 @@ void mlg_set_error(const char* fmt, ...);
         if (_r != MLG_OK) return _r; \
     } while (0)
 
+// Device memory comes from a small per-device caching pool (capi.cu): a query allocates and frees a dozen
+// buffers, and cudaMalloc/cudaFree would otherwise cost more than the kernels on small batches.  Blocks are
+// only returned to the pool after the stream work that used them has been joined.
+void* mlg_pool_alloc(size_t bytes);
+void mlg_pool_free(void* p);
+void mlg_pool_trim(int device);
+
 // owning device buffer
 template <typename T>
 struct DevBuf {
@@ -37,16 +44,12 @@ struct DevBuf {
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) mlg_pool_free(p); p = nullptr; n = 0; }
     int alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e != cudaSuccess) {
-            p = nullptr;
-            mlg_set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-            return MLG_ERR_NOMEM;
-        }
+        p = (T*)mlg_pool_alloc(count * sizeof(T));
+        if (!p) return MLG_ERR_NOMEM;
         n = count;
         return MLG_OK;
     }
@@ -76,8 +79,12 @@ struct DbView {
     const key128* D_key;
     const uint32_t* bstart;      // nbuckets + 1
     const uint32_t* T1;          // nbuckets * slots
-    unsigned long long nbuckets;
+    unsigned long long nbuckets; // 2^bbits
+    uint32_t bbits;
     uint32_t slots;              // 4 (16-byte buckets) or 8 (32-byte buckets)
+    // L2-resident Bloom prefilter over D: 2^fbits 64-bit words, two bits per key (fbits == 0: disabled)
+    const unsigned long long* F;
+    uint32_t fbits;
 };
 
 struct mlg_db {
@@ -85,6 +92,7 @@ struct mlg_db {
     DbView v{};
     DevBuf<key128> P_key;
     DevBuf<uint32_t> P_slot, pidx, rep, bstart, T1;
+    DevBuf<unsigned long long> F;
     DevBuf<key128> D_key;
     DevBuf<long long> den_real;      // G*nk
     DevBuf<unsigned char> has_empty; // G

@@ -82,10 +82,10 @@ __device__ __forceinline__ void bump_counter(unsigned char* cnt8, uint32_t i) {
         if (old == assumed) break;
     }
 }
-// exact path: compare against the bucket's run of D
-__device__ __noinline__ void probe_exact(const key128* __restrict__ D_key, const uint32_t* __restrict__ bstart,
-                                         unsigned char* cnt8, unsigned long long bucket, unsigned long long khi,
-                                         unsigned long long klo) {
+// exact path: compare the full key against the bucket's run of D, bump the counter on a match
+__device__ __forceinline__ void probe_exact(const key128* __restrict__ D_key, const uint32_t* __restrict__ bstart,
+                                            unsigned char* cnt8, unsigned long long bucket, unsigned long long khi,
+                                            unsigned long long klo) {
     uint32_t s = bstart[bucket], e = bstart[bucket + 1];
     for (uint32_t i = s; i < e; ++i) {
         key128 d = D_key[i];
@@ -107,17 +107,60 @@ __device__ __forceinline__ unsigned long long smear_low64(unsigned long long hi,
     return lo;
 }
 
-template <int SLOTS, bool HAS_NMASK, int KT>
-__global__ void __launch_bounds__(TILE) k1_decode_canon_probe(ProbeArgs a, DbView db) {
+constexpr unsigned WARPS = TILE / 32;
+constexpr unsigned QCAP = 64;          // per-warp queue of exact-path candidates (drained at >= 32)
+
+// The exact path is rare (true hits, fingerprint collisions, overflowed buckets) but made of dependent
+// DRAM loads; taken inline it would serialise a whole warp on one lane.  Candidates are instead queued
+// per warp in shared memory and drained 32 at a time, one candidate per lane.
+struct WarpQueue {
+    unsigned long long hi[WARPS][QCAP];
+    unsigned long long lo[WARPS][QCAP];
+    unsigned n[WARPS];
+};
+
+__device__ __forceinline__ void queue_drain(WarpQueue& q, unsigned warp, unsigned lane, const DbView& db, unsigned char* cnt8) {
+    __syncwarp();
+    const unsigned n = q.n[warp];
+    for (unsigned i = lane; i < n; i += 32) {
+        const unsigned long long khi = q.hi[warp][i], klo = q.lo[warp][i];
+        key128 c; c.hi = khi; c.lo = klo;
+        probe_exact(db.D_key, db.bstart, cnt8, hash_bucket(key_hash(c), db.bbits), khi, klo);
+    }
+    __syncwarp();
+    if (lane == 0) q.n[warp] = 0;
+    __syncwarp();
+}
+// all 32 lanes call this; `cand` lanes append their key
+__device__ __forceinline__ void queue_push(WarpQueue& q, unsigned warp, unsigned lane, bool cand, unsigned long long khi,
+                                           unsigned long long klo, const DbView& db, unsigned char* cnt8) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
+    if (m == 0) return;                                   // warp-uniform
+    const unsigned base = q.n[warp];
+    if (cand) {
+        const unsigned i = base + __popc(m & ((1u << lane) - 1u));
+        q.hi[warp][i] = khi; q.lo[warp][i] = klo;
+    }
+    __syncwarp();
+    const unsigned total = base + __popc(m);
+    if (lane == 0) q.n[warp] = total;
+    __syncwarp();
+    if (total >= 32) queue_drain(q, warp, lane, db, cnt8);
+}
+
+template <int SLOTS, bool HAS_NMASK, int KT, bool USE_FILTER>
+__global__ void __launch_bounds__(TILE, 2) k1_decode_canon_probe(ProbeArgs a, DbView db) {
     __shared__ __align__(16) uint4 sb[2][TILE + 2];
     __shared__ __align__(16) unsigned long long sn[2][TILE + 2];
     __shared__ __align__(16) unsigned long long ss[2][TILE + 2];
     __shared__ __align__(8) unsigned long long mbar[2];
     __shared__ unsigned long long s_total;
+    __shared__ WarpQueue wq;
 
-    const unsigned tid = threadIdx.x;
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const unsigned K = KT ? (unsigned)KT : db.K;
     const unsigned long long ntiles = (a.w_end - a.w_begin + TILE - 1) / TILE;
+    const unsigned fshift = 64u - db.fbits, bshift = 64u - db.bbits;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -125,6 +168,7 @@ __global__ void __launch_bounds__(TILE) k1_decode_canon_probe(ProbeArgs a, DbVie
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_total = 0;
     }
+    if (lane == 0) wq.n[warp] = 0;
     __syncthreads();
 
     auto issue = [&](unsigned stage, unsigned long long t) {
@@ -164,11 +208,11 @@ __global__ void __launch_bounds__(TILE) k1_decode_canon_probe(ProbeArgs a, DbVie
         const unsigned long long w = a.w_begin + t * TILE + tid;
         const bool active = w < a.w_end;
         uint4 cur = make_uint4(0, 0, 0, 0), prv = make_uint4(0, 0, 0, 0);
-        unsigned long long nm_cur = 0, nm_prv = 0, sm_cur = 0, sm_prv = 0;
+        unsigned long long nm_cur = ~0ull, nm_prv = 0, sm_cur = 0, sm_prv = 0;
         if (active) {
             cur = sb[stage][tid + 1];
             sm_cur = bswap64(ss[stage][tid + 2]);
-            if (HAS_NMASK) nm_cur = bswap64(sn[stage][tid + 2]);
+            nm_cur = HAS_NMASK ? bswap64(sn[stage][tid + 2]) : 0ull;
             if (w > 0) {
                 prv = sb[stage][tid];
                 sm_prv = bswap64(ss[stage][tid + 1]);
@@ -183,12 +227,12 @@ __global__ void __launch_bounds__(TILE) k1_decode_canon_probe(ProbeArgs a, DbVie
         }
         __syncthreads();   // everyone has copied its words out of this stage
         if (tid == 0 && t + 2ull * gridDim.x < ntiles) issue(stage, t + 2ull * gridDim.x);
-        if (!active) continue;
 
-        // window-end validity: no N in the K bases ending here, no read start in the last K-1 of them
+        // window-end validity: no N in the K bases ending here, no read start in the last K-1 of them.
+        // (threads past the end of the range carry nm_cur = all ones: nothing valid, but they keep in step
+        //  with their warp for the collectives below)
         const unsigned long long inval = smear_low64(nm_prv, nm_cur, K) | smear_low64(sm_prv, sm_cur, K - 1);
         const unsigned long long vmask = ~inval;
-        if (vmask == 0ull) continue;
         my_valid += __popcll(vmask);
 
         // MSB-first 64-bit halves: bases 0..31 and 32..63 of the word
@@ -205,13 +249,10 @@ __global__ void __launch_bounds__(TILE) k1_decode_canon_probe(ProbeArgs a, DbVie
         for (int half = 0; half < 2; ++half) {
             const unsigned long long word = half ? cur_lo : cur_hi;
             const uint32_t vhalf = half ? (uint32_t)vmask : (uint32_t)(vmask >> 32);
-            if (vhalf == 0u) {
-                // no valid window ends in this half: just advance the rolling registers by 32 bases
-                // (only needed when the other half follows)
+            if (__all_sync(0xFFFFFFFFu, vhalf == 0u)) {
+                // no lane of this warp has a valid window ending in this half: just advance the rolling registers
                 if (half == 0) {
-                    // fwd <- last K bases of (fwd:word); cheaper to rebuild than to roll 32 times
-                    // shift the 2K-bit window left by 64 bits and append the 32 new bases
-                    key128 nf;
+                    key128 nf;                       // (fwd << 64 | word) masked to 2K bits
                     nf.hi = fwd.lo; nf.lo = word;
                     fwd = key_and(nf, kmask);
                     rcv = key_rc(fwd, K);
@@ -220,10 +261,8 @@ __global__ void __launch_bounds__(TILE) k1_decode_canon_probe(ProbeArgs a, DbVie
             }
 #pragma unroll 2
             for (int g0 = 0; g0 < 32; g0 += GROUP) {
-                unsigned long long chi[GROUP], clo[GROUP], bkt[GROUP];
-                uint32_t fp[GROUP];
+                unsigned long long chi[GROUP], clo[GROUP], h[GROUP];
                 bool ok[GROUP];
-                BucketVec<SLOTS> vec[GROUP];
 #pragma unroll
                 for (int j = 0; j < GROUP; ++j) {
                     const int i = g0 + j;
@@ -240,28 +279,43 @@ __global__ void __launch_bounds__(TILE) k1_decode_canon_probe(ProbeArgs a, DbVie
                     chi[j] = use_rc ? rcv.hi : fwd.hi;
                     clo[j] = use_rc ? rcv.lo : fwd.lo;
                     key128 c; c.hi = chi[j]; c.lo = clo[j];
-                    const unsigned long long h = key_hash(c);
-                    bkt[j] = hash_bucket(h, db.nbuckets);
-                    fp[j] = hash_fp(h);
+                    h[j] = key_hash(c);
                 }
+                if (USE_FILTER) {
+                    // level 0: two bits of one 64-bit word of the L2-resident Bloom prefilter
+                    unsigned long long fw[GROUP];
+#pragma unroll
+                    for (int j = 0; j < GROUP; ++j) {
+                        fw[j] = 0ull;
+                        if (ok[j]) fw[j] = __ldg(db.F + (h[j] >> fshift));
+                    }
+#pragma unroll
+                    for (int j = 0; j < GROUP; ++j) {
+                        const unsigned long long m = filter_mask(h[j]);
+                        ok[j] = ok[j] && ((fw[j] & m) == m);
+                    }
+                }
+                // level 1: one bucket of 31-bit fingerprints (a 32- or 16-byte sector of HBM)
+                BucketVec<SLOTS> vec[GROUP];
 #pragma unroll
                 for (int j = 0; j < GROUP; ++j) {
 #pragma unroll
                     for (int s = 0; s < SLOTS; ++s) vec[j].w[s] = 0u;
-                    if (ok[j]) load_bucket(db.T1, bkt[j], vec[j]);
+                    if (ok[j]) load_bucket(db.T1, db.bbits ? (h[j] >> bshift) : 0ull, vec[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < GROUP; ++j) {
-                    if (ok[j] && bucket_candidate<SLOTS>(vec[j], fp[j]))
-                        probe_exact(db.D_key, db.bstart, a.cnt8, bkt[j], chi[j], clo[j]);
+                    const bool cand = ok[j] && bucket_candidate<SLOTS>(vec[j], hash_fp(h[j]));
+                    queue_push(wq, warp, lane, cand, chi[j], clo[j], db, a.cnt8);
                 }
             }
         }
     }
+    queue_drain(wq, warp, lane, db, a.cnt8);
 
     // block-reduce the number of valid windows
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xFFFFFFFFu, my_valid, o);
-    if ((tid & 31u) == 0 && my_valid) atomicAdd(&s_total, my_valid);
+    if (lane == 0 && my_valid) atomicAdd(&s_total, my_valid);
     __syncthreads();
     if (tid == 0 && s_total) atomicAdd(a.n_kmers, s_total);
 }
@@ -328,12 +382,18 @@ __global__ void k_ascii_to_keys(const unsigned char* text, unsigned long long ns
     keys[s] = k;
 }
 
-template <int SLOTS, bool HAS_NMASK>
-int launch_probe_k(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
-    if (db.K == 60) k1_decode_canon_probe<SLOTS, HAS_NMASK, 60><<<grid, TILE, 0, st>>>(a, db);
-    else k1_decode_canon_probe<SLOTS, HAS_NMASK, 0><<<grid, TILE, 0, st>>>(a, db);
+template <int SLOTS, bool HAS_NMASK, bool USE_FILTER>
+int launch_probe_k(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
+    if (db.K == 60) k1_decode_canon_probe<SLOTS, HAS_NMASK, 60, USE_FILTER><<<grid, TILE, 0, st>>>(a, db);
+    else k1_decode_canon_probe<SLOTS, HAS_NMASK, 0, USE_FILTER><<<grid, TILE, 0, st>>>(a, db);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
+}
+template <int SLOTS>
+int launch_probe_s(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
+    const bool nm = a.nmask != nullptr, fl = db.fbits != 0;
+    if (nm) return fl ? launch_probe_k<SLOTS, true, true>(db, a, st, grid) : launch_probe_k<SLOTS, true, false>(db, a, st, grid);
+    return fl ? launch_probe_k<SLOTS, false, true>(db, a, st, grid) : launch_probe_k<SLOTS, false, false>(db, a, st, grid);
 }
 
 }  // namespace
@@ -343,14 +403,12 @@ int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaS
     const unsigned long long ntiles = (a.w_end - a.w_begin + TILE - 1) / TILE;
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        ctas_per_sm = 4;
-        if (const char* s = getenv("MLG_PROBE_CTAS_PER_SM")) { int x = atoi(s); if (x >= 1 && x <= 8) ctas_per_sm = x; }
+        ctas_per_sm = 8;   // more CTAs than are resident: the hardware scheduler evens out the tail
+        if (const char* s = getenv("MLG_PROBE_CTAS_PER_SM")) { int x = atoi(s); if (x >= 1 && x <= 64) ctas_per_sm = x; }
     }
     unsigned long long want = (unsigned long long)ctx->sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(ntiles < want ? ntiles : want);
-    const bool nm = a.nmask != nullptr;
-    if (db.slots == 8) return nm ? launch_probe_k<8, true>(ctx, db, a, st, grid) : launch_probe_k<8, false>(ctx, db, a, st, grid);
-    return nm ? launch_probe_k<4, true>(ctx, db, a, st, grid) : launch_probe_k<4, false>(ctx, db, a, st, grid);
+    return db.slots == 8 ? launch_probe_s<8>(db, a, st, grid) : launch_probe_s<4>(db, a, st, grid);
 }
 
 int launch_build_smask_fixed(unsigned long long* smask, unsigned long long nwords_alloc, unsigned long long nbases,

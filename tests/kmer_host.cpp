@@ -7,6 +7,7 @@ void t_sub(unsigned long long hi, unsigned long long lo, unsigned K, unsigned of
 void t_prefix(unsigned long long hi, unsigned long long lo, unsigned K, unsigned k, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_prefix(a, K, k); out[0] = r.hi; out[1] = r.lo; }
 void t_shl(unsigned long long hi, unsigned long long lo, unsigned s, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_shl(a, s); out[0] = r.hi; out[1] = r.lo; }
 unsigned long long t_hash(unsigned long long hi, unsigned long long lo) { key128 a{hi, lo}; return key_hash(a); }
-unsigned long long t_bucket(unsigned long long h, unsigned long long nb) { return hash_bucket(h, nb); }
+unsigned long long t_bucket(unsigned long long h, unsigned bbits) { return hash_bucket(h, bbits); }
+unsigned long long t_fmask(unsigned long long h) { return filter_mask(h); }
 unsigned t_fp(unsigned long long h) { return hash_fp(h); }
 }

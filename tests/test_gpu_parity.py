@@ -296,3 +296,37 @@ def test_midsize_against_oracle(ctx):
     assert res["n_intersect"] > 1000
     q.close()
     db.close()
+
+
+@pytest.mark.parametrize("filter_mb", ["0", "0.016", "64"])
+def test_prefilter_variants(ctx, workload, monkeypatch, filter_mb):
+    """no prefilter, a starved prefilter (~2 bits per key, most probes pass) and the default one"""
+    w = workload
+    monkeypatch.setenv("MLG_FILTER_MB", filter_mb)
+    db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
+    q = db.query()
+    q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+    res = q.finish()
+    assert (res["stats"]["filter_log2_words"] == 0) == (filter_mb == "0")
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+    db.close()
+
+
+def test_deep_coverage_many_hits(ctx):
+    """every read comes from two small genomes: most windows near sketch positions hit, the exact-path queue
+    is drained many times and counters saturate"""
+    p = synth.params(G=6, n=400, seed=9, len_min=3000, len_max=3500, n_present=2, strain_period=0, tiny_pct=0,
+                     sub_per_64k=0, n_per_64k=0)
+    keys = synth.sketch_keys(p)
+    nreads = 120000
+    bases, nmask = synth.reads_packed(p, 0, nreads)
+    ref, I_ref = oracle_c_run(keys, p.G, p.n, 60, KS, lambda q: q.push_packed(bases, nmask, None, nreads, p.read_len))
+    db = Database.from_keys(ctx, keys, p.G, p.n, 60, KS)
+    q = db.query()
+    q.push_packed(bases, nmask, None, nreads, p.read_len)
+    res = q.finish()
+    _check(res, q.intersection(), ref, I_ref)
+    assert res["n_intersect"] >= 300
+    q.close()
+    db.close()

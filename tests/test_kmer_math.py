@@ -28,6 +28,9 @@ def kh(tmp_path_factory):
     L.t_hash.restype = u64
     L.t_bucket.argtypes = [u64, u64]
     L.t_bucket.restype = u64
+    L.t_bucket.argtypes = [u64, C.c_uint]
+    L.t_fmask.argtypes = [u64]
+    L.t_fmask.restype = u64
     L.t_fp.argtypes = [u64]
     L.t_fp.restype = C.c_uint
     return L
@@ -65,9 +68,11 @@ def test_extremes(kh):
 def test_hash_bucket_monotone_and_fp_nonzero(kh):
     rng = random.Random(5)
     hs = sorted(rng.getrandbits(64) for _ in range(2000))
-    for nb in (1, 7, 1000, 2**31 + 11):
-        b = [kh.t_bucket(h, nb) for h in hs]
-        assert b == sorted(b) and max(b) < nb
+    for bbits in (0, 1, 7, 20, 31):
+        b = [kh.t_bucket(h, bbits) for h in hs]
+        assert b == sorted(b) and max(b) < (1 << bbits)
+    masks = [kh.t_fmask(h) for h in hs]
+    assert all(1 <= bin(m).count("1") <= 2 for m in masks)
     assert kh.t_fp(0) == 1 and kh.t_fp(1 << 31) == 1
     assert all(0 < kh.t_fp(h) < 2**31 for h in hs)
     # different keys hash differently (sanity, not a guarantee)
