@@ -1,0 +1,9 @@
+#! /usr/bin/env python
+"""Same name and command line as scripts/select_db.py of the reference; runs metalign_b200.select_db."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from metalign_b200.select_db import select_main, select_parseargs  # noqa: E402
+
+if __name__ == "__main__":
+    select_main(select_parseargs())
