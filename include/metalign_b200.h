@@ -71,7 +71,7 @@ typedef struct mlg_stats {
     double ms_probe;         /* sum of CUDA-event durations of the probe kernel launches */
     double ms_query;         /* CUDA-event duration of the finish stage (compact, expand, popcount, finalize) */
     uint32_t probe_launches; /* number of probe kernel launches in ms_probe */
-    uint32_t filter_log2_words; /* L2 prefilter: log2 of its 64-bit word count, 0 = no prefilter */
+    uint32_t filter_words;   /* L2 prefilter: number of 32-bit words, 0 = no prefilter */
 } mlg_stats;
 
 const char* mlg_last_error(void);

@@ -25,7 +25,7 @@ class Stats(C.Structure):
                 ("n_intersect", C.c_uint64), ("n_db_entries", C.c_uint64), ("n_db_distinct", C.c_uint64),
                 ("n_buckets", C.c_uint64), ("bucket_bytes", C.c_uint32), ("gpu_launches", C.c_uint32),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("ms_probe", C.c_double),
-                ("ms_query", C.c_double), ("probe_launches", C.c_uint32), ("filter_log2_words", C.c_uint32)]
+                ("ms_query", C.c_double), ("probe_launches", C.c_uint32), ("filter_words", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -99,7 +99,7 @@ constexpr unsigned long long CHUNK_WORDS = 64ull * MLG_TILE_WORDS * 32ull;   // 
 
 struct Staging {
     DevBuf<unsigned char> bases, nmask;
-    DevBuf<unsigned long long> smask, off;
+    DevBuf<unsigned long long> off;
     DevBuf<unsigned char> text;
     cudaEvent_t done = nullptr;   // last kernel reading this staging set
     bool used = false;
@@ -131,32 +131,27 @@ namespace {
 
 int ensure_device(mlg_ctx* ctx) { CUDA_TRY(cudaSetDevice(ctx->device)); return MLG_OK; }
 
-// device-side part common to every push: build the read-start mask, launch the probe over [0, nwords)
-// in chunks, each chunk waiting for its copy event (if any)
+// device-side part common to every push: launch the probe over the batch's reads, in ranges; range i may
+// start once copy event i (if any) has completed
+struct ReadRange { unsigned long long r_end; cudaEvent_t ready; };
+
 int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsigned char* d_nmask,
               const unsigned long long* d_off, unsigned long long n_reads, uint32_t read_len, unsigned long long nbases,
-              const std::vector<std::pair<unsigned long long, cudaEvent_t>>* chunk_ready) {
+              const std::vector<ReadRange>* ranges) {
     mlg_ctx* ctx = q->ctx;
-    const unsigned long long nwords = (nbases + 63) / 64;
-    const unsigned long long nwords_alloc = round_up(nwords + 2, 2);
-    MLG_TRY(s.smask.ensure(nwords_alloc));
-    if (d_off) {
-        CUDA_TRY(cudaMemsetAsync(s.smask.p, 0, nwords_alloc * 8, ctx->s_comp));
-        MLG_TRY(launch_build_smask_offsets(s.smask.p, d_off, n_reads, ctx->s_comp));
-    } else {
-        MLG_TRY(launch_build_smask_fixed(s.smask.p, nwords_alloc, nbases, read_len, ctx->s_comp));
-    }
-    q->st.gpu_launches += 1;
+    const unsigned long long nwords64 = (nbases + 63) / 64;       // 64-base words: 16 bytes of bases, 8 bytes of mask
     ProbeArgs a{};
-    a.bases = reinterpret_cast<const uint4*>(d_bases);
+    a.bases = reinterpret_cast<const unsigned long long*>(d_bases);
     a.nmask = reinterpret_cast<const unsigned long long*>(d_nmask);
-    a.smask = s.smask.p;
-    a.nwords = nwords; a.nbases = nbases;
+    a.off = d_off; a.read_len = read_len;
+    a.base_words = nwords64 * 2;                                  // buffers cover whole 16-byte units
+    a.nmask_words = round_up(nwords64, 2);
     a.cnt8 = q->cnt8.p; a.n_kmers = q->d_nkmers.p;
-    auto launch_range = [&](unsigned long long w0, unsigned long long w1) -> int {
+    auto launch_range = [&](unsigned long long r0, unsigned long long r1) -> int {
+        if (r1 <= r0) return MLG_OK;
         cudaEvent_t e0, e1;
         CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-        a.w_begin = w0; a.w_end = w1;
+        a.r_begin = r0; a.r_end = r1;
         CUDA_TRY(cudaEventRecord(e0, ctx->s_comp));
         MLG_TRY(launch_probe(ctx, q->db->v, a, ctx->s_comp));
         CUDA_TRY(cudaEventRecord(e1, ctx->s_comp));
@@ -164,15 +159,15 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
         q->st.gpu_launches += 1; q->st.probe_launches += 1;
         return MLG_OK;
     };
-    if (chunk_ready) {
-        unsigned long long w0 = 0;
-        for (auto& cr : *chunk_ready) {
-            CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, cr.second, 0));
-            MLG_TRY(launch_range(w0, cr.first));
-            w0 = cr.first;
+    if (ranges) {
+        unsigned long long r0 = 0;
+        for (auto& rr : *ranges) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, rr.ready, 0));
+            MLG_TRY(launch_range(r0, rr.r_end));
+            if (rr.r_end > r0) r0 = rr.r_end;
         }
-    } else if (nwords) {
-        MLG_TRY(launch_range(0, nwords));
+    } else {
+        MLG_TRY(launch_range(0, n_reads));
     }
     if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(s.done, ctx->s_comp));
@@ -352,7 +347,7 @@ MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode,
     CUDA_TRY(cudaMemsetAsync(q->d_nkmers.p, 0, 8, ctx->s_comp));
     CUDA_TRY(cudaEventCreate(&q->ev_q0)); CUDA_TRY(cudaEventCreate(&q->ev_q1));
     q->st.n_db_entries = db->v.np; q->st.n_db_distinct = db->v.nd;
-    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4; q->st.filter_log2_words = db->v.fbits;
+    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4; q->st.filter_words = db->v.nfw;
     guard.q = nullptr;
     *out = q;
     return MLG_OK;
@@ -390,7 +385,7 @@ MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint
     Staging& s = q->stg[q->cur];
     if (s.used) CUDA_TRY(cudaEventSynchronize(s.done));   // previous batch that used this set has been consumed
     const unsigned long long nwords = (nbases + 63) / 64;
-    const unsigned long long cap_words = round_up(nwords + 2, 2);
+    const unsigned long long cap_words = round_up(nwords + 2, 2);   // 64-base words
     MLG_TRY(s.bases.ensure(cap_words * 16));
     if (nmask) MLG_TRY(s.nmask.ensure(cap_words * 8));
     if (off) {
@@ -402,9 +397,9 @@ MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint
         q->chunk_events.push_back(e);
         q->st.h2d_bytes += (n_reads + 1) * 8;
     }
-    // chunked copies: chunk c of the packed stream is probed while chunk c+1 is still in flight
+    // chunked copies: the reads that are complete after chunk c are probed while chunk c+1 is still in flight
     const unsigned long long bases_bytes = (nbases + 3) / 4, nmask_bytes = (nbases + 7) / 8;
-    std::vector<std::pair<unsigned long long, cudaEvent_t>> ready;
+    std::vector<ReadRange> ready;
     for (unsigned long long w0 = 0; w0 < nwords; w0 += CHUNK_WORDS) {
         const unsigned long long w1 = std::min(nwords, w0 + CHUNK_WORDS);
         const unsigned long long b0 = w0 * 16, b1 = std::min(bases_bytes, w1 * 16);
@@ -418,7 +413,12 @@ MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint
         cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(e, ctx->s_copy));
         q->chunk_events.push_back(e);
-        ready.emplace_back(w1, e);
+        // reads whose last base has been copied (base index < 64 * w1)
+        unsigned long long r_end;
+        if (w1 == nwords) r_end = n_reads;
+        else if (off) r_end = (unsigned long long)(std::upper_bound(off, off + n_reads + 1, (uint64_t)(w1 * 64)) - off) - 1;
+        else r_end = (w1 * 64) / read_len;
+        ready.push_back({r_end, e});
     }
     MLG_TRY(run_probe(q, s, s.bases.p, nmask ? s.nmask.p : nullptr, off ? s.off.p : nullptr, n_reads, read_len, nbases, &ready));
     q->cur ^= 1;
@@ -437,7 +437,7 @@ MLG_API int mlg_query_push_ascii(mlg_query* q, const char* text, const uint64_t*
     Staging& s = q->stg[q->cur];
     if (s.used) CUDA_TRY(cudaEventSynchronize(s.done));
     const unsigned long long nwords = (nbases + 63) / 64;
-    const unsigned long long cap_words = round_up(nwords + 2, 2);
+    const unsigned long long cap_words = round_up(nwords + 2, 2);   // 64-base words
     MLG_TRY(s.bases.ensure(cap_words * 16)); MLG_TRY(s.nmask.ensure(cap_words * 8));
     MLG_TRY(s.text.ensure(nbases)); MLG_TRY(s.off.ensure(n_reads + 1));
     CUDA_TRY(cudaMemcpyAsync(s.text.p, text, nbases, cudaMemcpyHostToDevice, ctx->s_copy));

@@ -100,9 +100,9 @@ __global__ void k_flag_heads(const key128* a, uint32_t n, unsigned char* flag) {
     if (i >= n) return;
     flag[i] = (i == 0 || !key_eq(a[i], a[i - 1])) ? 1 : 0;
 }
-__global__ void k_hash_keys(const key128* a, uint32_t n, unsigned long long* h) {
+__global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, unsigned long long* h) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) h[i] = key_hash(a[i]);
+    if (i < n) h[i] = key_hash(a[i], K);
 }
 __global__ void k_gather_key(const key128* src, const uint32_t* idx, uint32_t n, key128* dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,9 +112,9 @@ __global__ void k_hbucket_hist(const unsigned long long* h, uint32_t nd, uint32_
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nd) atomicAdd(&counts[hash_bucket(h[i], bbits)], 1u);
 }
-__global__ void k_fill_filter(const unsigned long long* h, uint32_t nd, uint32_t fbits, unsigned long long* F) {
+__global__ void k_fill_filter(const unsigned long long* h, uint32_t nd, uint32_t nfw, uint32_t* F) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nd) atomicOr(&F[filter_word(h[i], fbits)], filter_mask(h[i]));
+    if (i < nd) atomicOr(&F[filter_word(h[i], nfw)], 1u << filter_bit(h[i]));
 }
 __global__ void k_fill_t1(const unsigned long long* h, uint32_t nd, uint32_t bbits, const uint32_t* bstart,
                           uint32_t slots, uint32_t* T1) {
@@ -329,7 +329,7 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         // order by hash
         DevBuf<unsigned long long> h; DevBuf<uint32_t> iota, perm;
         MLG_TRY(h.alloc(nd)); MLG_TRY(hsorted.alloc(nd)); MLG_TRY(iota.alloc(nd)); MLG_TRY(perm.alloc(nd));
-        k_hash_keys<<<nblk(nd), TPB, 0, st>>>(duniq.p, nd, h.p);
+        k_hash_keys<<<nblk(nd), TPB, 0, st>>>(duniq.p, nd, K, h.p);
         k_iota<<<nblk(nd), TPB, 0, st>>>(iota.p, nd);
         MLG_TRY(sort_pairs_u64(h.p, hsorted.p, iota.p, perm.p, nd, 0, 64, st));
         MLG_TRY(db->D_key.alloc(nd));
@@ -342,9 +342,9 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
     {
         uint32_t slots_per_bucket = 8;
         if (const char* s = getenv("MLG_BUCKET_SLOTS")) { int x = atoi(s); if (x == 4 || x == 8) slots_per_bucket = (uint32_t)x; }
-        double load = slots_per_bucket / 4.0;     // upper bound on the mean entries per bucket
+        double load = slots_per_bucket * 0.3125;  // upper bound on the mean entries per bucket (2.5 of 8 slots)
         if (const char* s = getenv("MLG_BUCKET_LOAD")) { double x = atof(s); if (x > 0.01 && x <= slots_per_bucket) load = x; }
-        uint32_t bbits = 0;
+        uint32_t bbits = 1;                       // at least two buckets: the probe kernel shifts by 32 - bbits
         while (bbits < 31 && (double)(1ull << bbits) * load < (double)nd) ++bbits;
         if ((double)(1ull << bbits) * load < (double)nd) { mlg_set_error("too many buckets"); return MLG_ERR_ARG; }
         unsigned long long nb = 1ull << bbits;
@@ -357,28 +357,30 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         CUDA_TRY(cudaMemsetAsync(db->T1.p, 0, (nb * slots_per_bucket + 8) * 4, st));
         if (nd) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p, slots_per_bucket, db->T1.p);
         v.bstart = db->bstart.p; v.T1 = db->T1.p;
-        // Bloom prefilter sized to stay L2-resident: at most MLG_FILTER_MB (default 64 MiB), at most ~16 bits per key;
-        // below 2 bits per key it would pass almost everything and is left out.
-        double max_mb = 64.0;
+        // One-bit-per-key prefilter sized to stay L2-resident: MLG_FILTER_MB MiB at most (default 48), 16 bits per
+        // key at most; below 1.5 bits per key it would pass most probes and is left out.
+        double max_mb = 48.0;
         if (const char* s = getenv("MLG_FILTER_MB")) max_mb = atof(s);
-        uint32_t fbits = 0;
-        if (nd && max_mb >= 1.0 / 1024) {
-            while (fbits < 40 && (double)(1ull << fbits) * 64.0 < 16.0 * (double)nd) ++fbits;
-            while (fbits > 0 && ((double)(1ull << fbits) * 8.0 > max_mb * 1048576.0 || fbits > 26)) --fbits;
-            if ((double)(1ull << fbits) * 64.0 < 2.0 * (double)nd) fbits = 0;
+        unsigned long long nfw = 0;                       // 32-bit words
+        if (nd && max_mb > 0) {
+            unsigned long long want = ((unsigned long long)nd * 16ull + 31ull) / 32ull;
+            unsigned long long cap = (unsigned long long)(max_mb * 1048576.0 / 4.0);
+            nfw = want < cap ? want : cap;
+            if (nfw > 0xFFFFFFF0ull) nfw = 0xFFFFFFF0ull;
+            if ((double)nfw * 32.0 < 1.5 * (double)nd) nfw = 0;
         }
-        v.fbits = fbits; v.F = nullptr;
-        if (fbits) {
-            MLG_TRY(db->F.alloc(1ull << fbits));
-            CUDA_TRY(cudaMemsetAsync(db->F.p, 0, (1ull << fbits) * 8, st));
-            k_fill_filter<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, fbits, db->F.p);
+        v.nfw = (uint32_t)nfw; v.F = nullptr;
+        if (nfw) {
+            MLG_TRY(db->F.alloc(nfw));
+            CUDA_TRY(cudaMemsetAsync(db->F.p, 0, nfw * 4, st));
+            k_fill_filter<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, (uint32_t)nfw, db->F.p);
             v.F = db->F.p;
             // optional: pin the prefilter in L2 (persisting access-policy window on the compute stream)
             const char* pe = getenv("MLG_L2_PERSIST");
             if (pe && atoi(pe) > 0) {
                 cudaDeviceProp prop;
                 if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-                    size_t fbytes = (size_t)8 << fbits;
+                    size_t fbytes = (size_t)nfw * 4;
                     size_t carve = fbytes < (size_t)prop.persistingL2CacheMaxSize ? fbytes : (size_t)prop.persistingL2CacheMaxSize;
                     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
                     cudaStreamAttrValue attr;

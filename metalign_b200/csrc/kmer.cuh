@@ -71,22 +71,40 @@ MLG_HD key128 key_sub(const key128& x, unsigned K, unsigned off, unsigned k) {
 // the leading k bases of a K-base value
 MLG_HD key128 key_prefix(const key128& x, unsigned K, unsigned k) { return key_shr(x, 2 * (K - k)); }
 
-// 64-bit mix of a canonical key: bucket index comes from the high bits, fingerprint from the low bits
-MLG_HD unsigned long long key_hash(const key128& c) {
-    unsigned long long x = c.lo ^ (c.hi * 0x9E3779B97F4A7C15ull);
+// ---- hashing ------------------------------------------------------------------------------------
+// The probe kernel never materialises the canonical k-mer on its fast path.  It hashes a STRAND-SYMMETRIC
+// digest instead: the four 32-bit words of (forward + reverse complement), both top-aligned in 128 bits and
+// added word by word.  Either strand gives the same digest, so the database hashes each canonical key the
+// same way.  (The digest loses a little information -- e.g. two keys that differ by the same amount at two
+// mirrored positions share it -- which can only cause a fingerprint false positive; the exact path compares
+// full keys.)
+MLG_HD unsigned long long hash_digest(unsigned s3, unsigned s2, unsigned s1, unsigned s0) {
+    unsigned long long lo = ((unsigned long long)s1 << 32) | s0, hi = ((unsigned long long)s3 << 32) | s2;
+    unsigned long long x = lo ^ (hi * 0x9E3779B97F4A7C15ull);
     x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
     x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
     x ^= x >> 32;
     return x;
 }
+// hash of a K-mer given in either orientation (bottom-aligned key, as stored in the database)
+MLG_HD unsigned long long key_hash(const key128& x, unsigned K) {
+    const key128 f = key_shl(x, 128 - 2 * K), r = key_shl(key_rc(x, K), 128 - 2 * K);
+    return hash_digest((unsigned)(f.hi >> 32) + (unsigned)(r.hi >> 32), (unsigned)f.hi + (unsigned)r.hi,
+                       (unsigned)(f.lo >> 32) + (unsigned)(r.lo >> 32), (unsigned)f.lo + (unsigned)r.lo);
+}
 // Tables have power-of-two sizes, indexed by the TOP bits of the hash: monotone in h, so entries sorted
 // by hash are grouped by bucket.
 MLG_HD unsigned long long hash_bucket(unsigned long long h, unsigned bbits) { return bbits ? (h >> (64 - bbits)) : 0ull; }
-// L2-resident prefilter: one 64-bit word per probe (top fbits bits of h), two bits inside it
-MLG_HD unsigned long long filter_word(unsigned long long h, unsigned fbits) { return fbits ? (h >> (64 - fbits)) : 0ull; }
-MLG_HD unsigned long long filter_mask(unsigned long long h) {
-    return (1ull << ((h >> 35) & 63ull)) | (1ull << ((h >> 29) & 63ull));
+// L2-resident prefilter: a plain bit array of nfw 32-bit words, ONE bit per key
+// (at the ~2-3 bits per key that fit in L2 for a 1.6e8-key database one probe bit is as good as two)
+MLG_HD unsigned filter_word(unsigned long long h, unsigned nfw) {
+#ifdef __CUDA_ARCH__
+    return __umulhi((unsigned)(h >> 32), nfw);
+#else
+    return (unsigned)(((unsigned long long)(unsigned)(h >> 32) * nfw) >> 32);
+#endif
 }
+MLG_HD unsigned filter_bit(unsigned long long h) { return ((unsigned)h >> 26) & 31u; }
 // 31-bit non-zero fingerprint (bit 31 of a bucket's first word is the overflow flag, 0 = empty slot)
 MLG_HD unsigned hash_fp(unsigned long long h) {
     unsigned f = (unsigned)h & 0x7FFFFFFFu;

@@ -82,9 +82,9 @@ struct DbView {
     unsigned long long nbuckets; // 2^bbits
     uint32_t bbits;
     uint32_t slots;              // 4 (16-byte buckets) or 8 (32-byte buckets)
-    // L2-resident Bloom prefilter over D: 2^fbits 64-bit words, two bits per key (fbits == 0: disabled)
-    const unsigned long long* F;
-    uint32_t fbits;
+    // L2-resident prefilter over D: nfw 32-bit words, one bit per key (nfw == 0: disabled)
+    const uint32_t* F;
+    uint32_t nfw;
 };
 
 struct mlg_db {
@@ -92,7 +92,7 @@ struct mlg_db {
     DbView v{};
     DevBuf<key128> P_key;
     DevBuf<uint32_t> P_slot, pidx, rep, bstart, T1;
-    DevBuf<unsigned long long> F;
+    DevBuf<uint32_t> F;
     DevBuf<key128> D_key;
     DevBuf<long long> den_real;      // G*nk
     DevBuf<unsigned char> has_empty; // G
@@ -104,20 +104,17 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
 
 // ---- kernels' host launchers (probe.cu / query.cu) ----
 struct ProbeArgs {
-    const uint4* bases;                 // 16 bytes (64 bases) per word
-    const unsigned long long* nmask;    // 8 bytes per word, may be null
-    const unsigned long long* smask;    // 8 bytes per word (read starts)
-    unsigned long long nwords;          // words in the stream
-    unsigned long long nbases;          // bases in the stream
-    unsigned long long w_begin, w_end;  // word range of this launch (w_begin multiple of MLG_TILE_WORDS)
+    const unsigned long long* bases;    // packed stream as 8-byte words (32 bases each, stream byte order)
+    const unsigned long long* nmask;    // N mask as 8-byte words (64 bases each), may be null
+    const unsigned long long* off;      // read offsets in bases (n_reads + 1), or null: every read is read_len long
+    uint32_t read_len;
+    unsigned long long base_words;      // readable 8-byte words of `bases` (loads are clamped to it)
+    unsigned long long nmask_words;     // readable 8-byte words of `nmask`
+    unsigned long long r_begin, r_end;  // reads of this launch
     unsigned char* cnt8;                // nd saturating occurrence counters
     unsigned long long* n_kmers;        // device accumulator of valid windows
 };
 int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaStream_t st);
-int launch_build_smask_fixed(unsigned long long* smask, unsigned long long nwords_alloc, unsigned long long nbases,
-                             uint32_t read_len, cudaStream_t st);
-int launch_build_smask_offsets(unsigned long long* smask, const unsigned long long* off, unsigned long long nreads,
-                               cudaStream_t st);
 int launch_pack_ascii(const unsigned char* text, unsigned long long nbases, unsigned char* bases, unsigned char* nmask,
                       cudaStream_t st);
 int launch_ascii_to_keys(const unsigned char* text, unsigned long long nslots, uint32_t K, key128* keys, cudaStream_t st);

@@ -1,24 +1,35 @@
 // K1: decode + canonicalise + probe + count.   Replaces `kmc -k60 -ci2 -cs3` followed by
-// `kmc_tools simple <db> <reads> intersect` (scripts/select_db.py:50-56): every N-free K-long window
-// of every read is canonicalised (min of forward / reverse complement, A<C<G<T) and its occurrence is
-// counted -- but only for k-mers of the database set D, which is all the intersection keeps.
+// `kmc_tools simple <db> <reads> intersect` (scripts/select_db.py:50-56): every N-free K-long window of every
+// read is counted under its canonical form (min of forward / reverse complement, A<C<G<T) -- but only for
+// k-mers of the database set D, which is all the intersection keeps.
 //
-// Data flow per CTA (persistent, one 256-word tile = 16384 bases at a time, double buffered):
-//   TMA bulk copies (cp.async.bulk + mbarrier) stage the 2-bit packed bases (16 B / word), the N mask and
-//   the read-start mask (8 B / word each) of the tile plus one halo word into shared memory;
-//   each thread owns one 64-base word: it seeds the forward / reverse-complement 2K-bit registers from
-//   the halo word, then rolls them base by base; window validity (no N inside, no read boundary inside)
-//   is one 64-bit mask computed by shift-or smearing of the two bit masks;
-//   each valid window: 64-bit hash of the canonical key -> bucket -> ONE 32-byte (or 16-byte) load of
-//   31-bit fingerprints.  No fingerprint match and no overflow flag (> 99.9 % of windows) -> done.
-//   Otherwise the exact path compares the full key against the bucket's run of D and bumps the
-//   saturating 8-bit occurrence counter of that database k-mer (32-bit CAS).
-// HBM traffic per window: one 32-byte sector of the fingerprint table.
+// Mapping: one lane per read, WMAX = 96 window starts at a time ("segment"; a 150-base read is one segment of
+// 91 windows), so no lane ever spends work on a window that straddles two reads.
+//   per segment (once):  the lane gathers its 160 bases and 160 N bits from the packed stream into registers,
+//                        top-aligned, and builds the reverse complement of the whole segment (brev + bit-pair
+//                        swap); window validity (no N inside) is a bit mask made by shift-or smearing;
+//   per window:          forward and reverse-complement k-mers are funnel-shift extractions from those
+//                        register arrays (no loop-carried dependency); their word-wise sum is a strand-symmetric
+//                        digest, hashed once (kmer.cuh);
+//                        level 0: ONE bit of an L2-resident bit array (prefilter); level 1, only if that bit is
+//                        set: ONE 32-byte bucket of 31-bit fingerprints from HBM;
+//   rare:                fingerprint match or overflowed bucket -> the canonical key is queued per warp and the
+//                        queue is drained 32 at a time, one candidate per lane (exact compare against the bucket's
+//                        run of D, saturating 8-bit counter bump by 32-bit CAS).
+// The tile of 256 reads a CTA works on is staged global -> shared by TMA bulk copies (cp.async.bulk + mbarrier,
+// double buffered) when it fits; lanes then gather from shared memory.  Tiles that do not fit (very long reads)
+// are gathered straight from global memory.
 #include "mlg_internal.h"
 
 namespace {
 
-constexpr unsigned TILE = MLG_TILE_WORDS;
+constexpr unsigned RT = 256;            // reads per tile == threads per CTA
+constexpr unsigned WARPS = RT / 32;
+constexpr unsigned WMAX = 96;           // window starts per segment
+constexpr unsigned SEGW = 10;           // 32-bit words of bases per segment (160 bases >= WMAX + 63 - 1)
+constexpr unsigned QCAP = 64;           // per-warp queue of exact-path candidates (drained at >= 32)
+constexpr unsigned STAGE_B = 16384 + 64;   // staged bytes of packed bases per tile (256 reads x 250 bases fit)
+constexpr unsigned STAGE_M = 8192 + 64;    // staged bytes of N mask per tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
@@ -26,6 +37,9 @@ __device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
     asm volatile(
@@ -39,33 +53,58 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                  : "memory");
 }
 __device__ __forceinline__ unsigned long long bswap64(unsigned long long v) {
     uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
     return ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
 }
+// (a:b) << s, upper 32 bits; a is the more significant word; 0 <= s <= 31
+__device__ __forceinline__ uint32_t fsl(uint32_t a, uint32_t b, unsigned s) { return __funnelshift_l(b, a, s); }
+// reverse the order of the 16 two-bit groups of a word
+__device__ __forceinline__ uint32_t rev2_32(uint32_t x) {
+    x = __brev(x);
+    return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
 template <int SLOTS> struct BucketVec;
 template <> struct BucketVec<8> { uint32_t w[8]; };
 template <> struct BucketVec<4> { uint32_t w[4]; };
 
-__device__ __forceinline__ void load_bucket(const uint32_t* T1, unsigned long long b, BucketVec<8>& v) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+// L2 cache policies: the fingerprint table is touched once per probe at random (evict first, do not displace
+// anything), the prefilter is the working set that must stay resident (evict last)
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void load_bucket(const uint32_t* T1, unsigned long long b, BucketVec<8>& v, unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
-                 : "l"(T1 + b * 8));
+                 : "l"(T1 + b * 8), "l"(pol));
 }
-__device__ __forceinline__ void load_bucket(const uint32_t* T1, unsigned long long b, BucketVec<4>& v) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+__device__ __forceinline__ void load_bucket(const uint32_t* T1, unsigned long long b, BucketVec<4>& v, unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
-                 : "l"(T1 + b * 4));
+                 : "l"(T1 + b * 4), "l"(pol));
 }
-// does this bucket need the exact path for fingerprint fp?
+__device__ __forceinline__ uint32_t load_filter(const uint32_t* p, unsigned long long pol) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+// does this bucket need the exact path for fingerprint fp?  (bit 31 of word 0 = bucket overflowed)
 template <int SLOTS>
 __device__ __forceinline__ bool bucket_candidate(const BucketVec<SLOTS>& v, uint32_t fp) {
-    bool hit = ((v.w[0] & 0x7FFFFFFFu) == fp) | ((v.w[0] >> 31) != 0);
+    bool hit = ((v.w[0] & 0x7FFFFFFFu) == fp) | ((int)v.w[0] < 0);
 #pragma unroll
     for (int s = 1; s < SLOTS; ++s) hit |= (v.w[s] == fp);
     return hit;
@@ -83,84 +122,69 @@ __device__ __forceinline__ void bump_counter(unsigned char* cnt8, uint32_t i) {
     }
 }
 // exact path: compare the full key against the bucket's run of D, bump the counter on a match
-__device__ __forceinline__ void probe_exact(const key128* __restrict__ D_key, const uint32_t* __restrict__ bstart,
-                                            unsigned char* cnt8, unsigned long long bucket, unsigned long long khi,
-                                            unsigned long long klo) {
-    uint32_t s = bstart[bucket], e = bstart[bucket + 1];
+__device__ __forceinline__ void probe_exact(const DbView& db, unsigned char* cnt8, unsigned long long khi, unsigned long long klo) {
+    key128 c; c.hi = khi; c.lo = klo;
+    const unsigned long long bucket = hash_bucket(key_hash(c, db.K), db.bbits);
+    uint32_t s = db.bstart[bucket], e = db.bstart[bucket + 1];
     for (uint32_t i = s; i < e; ++i) {
-        key128 d = D_key[i];
+        key128 d = db.D_key[i];
         if (d.hi == khi && d.lo == klo) { bump_counter(cnt8, i); return; }
     }
 }
 
-// OR of (v >> d) for d = 0 .. span-1 over a 128-bit value; only the low 64 bits of the result are used
-__device__ __forceinline__ unsigned long long smear_low64(unsigned long long hi, unsigned long long lo, unsigned span) {
-    if (span == 0) return 0ull;
-    unsigned cover = 1;
-    while (cover * 2 <= span) {
-        unsigned long long nlo = lo | ((lo >> cover) | (hi << (64 - cover)));   // cover < 64 here
-        unsigned long long nhi = hi | (hi >> cover);
-        lo = nlo; hi = nhi; cover *= 2;
-    }
-    unsigned rest = span - cover;   // < cover <= 32
-    if (rest) lo |= (lo >> rest) | (hi << (64 - rest));
-    return lo;
-}
-
-constexpr unsigned WARPS = TILE / 32;
-constexpr unsigned QCAP = 64;          // per-warp queue of exact-path candidates (drained at >= 32)
-
-// The exact path is rare (true hits, fingerprint collisions, overflowed buckets) but made of dependent
-// DRAM loads; taken inline it would serialise a whole warp on one lane.  Candidates are instead queued
-// per warp in shared memory and drained 32 at a time, one candidate per lane.
+// The exact path is rare (true hits, fingerprint collisions, overflowed buckets) but made of dependent DRAM
+// loads; taken inline it would serialise a whole warp on one lane.  Candidates are queued per warp in shared
+// memory and drained 32 at a time, one candidate per lane.
 struct WarpQueue {
     unsigned long long hi[WARPS][QCAP];
     unsigned long long lo[WARPS][QCAP];
     unsigned n[WARPS];
 };
-
-__device__ __forceinline__ void queue_drain(WarpQueue& q, unsigned warp, unsigned lane, const DbView& db, unsigned char* cnt8) {
+__device__ __noinline__ void queue_drain(WarpQueue& q, unsigned warp, unsigned lane, const DbView& db, unsigned char* cnt8) {
     __syncwarp();
     const unsigned n = q.n[warp];
-    for (unsigned i = lane; i < n; i += 32) {
-        const unsigned long long khi = q.hi[warp][i], klo = q.lo[warp][i];
-        key128 c; c.hi = khi; c.lo = klo;
-        probe_exact(db.D_key, db.bstart, cnt8, hash_bucket(key_hash(c), db.bbits), khi, klo);
-    }
+    for (unsigned i = lane; i < n; i += 32) probe_exact(db, cnt8, q.hi[warp][i], q.lo[warp][i]);
     __syncwarp();
     if (lane == 0) q.n[warp] = 0;
     __syncwarp();
 }
-// all 32 lanes call this; `cand` lanes append their key
-__device__ __forceinline__ void queue_push(WarpQueue& q, unsigned warp, unsigned lane, bool cand, unsigned long long khi,
-                                           unsigned long long klo, const DbView& db, unsigned char* cnt8) {
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
-    if (m == 0) return;                                   // warp-uniform
+// all 32 lanes call this with the ballot of candidate lanes (non-zero); candidate lanes append their key
+__device__ __forceinline__ void queue_push(WarpQueue& q, unsigned warp, unsigned lane, unsigned ballot, bool cand,
+                                           unsigned long long khi, unsigned long long klo, const DbView& db, unsigned char* cnt8) {
     const unsigned base = q.n[warp];
     if (cand) {
-        const unsigned i = base + __popc(m & ((1u << lane) - 1u));
+        const unsigned i = base + __popc(ballot & ((1u << lane) - 1u));
         q.hi[warp][i] = khi; q.lo[warp][i] = klo;
     }
     __syncwarp();
-    const unsigned total = base + __popc(m);
+    const unsigned total = base + __popc(ballot);
     if (lane == 0) q.n[warp] = total;
     __syncwarp();
     if (total >= 32) queue_drain(q, warp, lane, db, cnt8);
 }
 
+struct SharedStage {
+    __align__(16) unsigned char b[2][STAGE_B];
+    __align__(16) unsigned char m[2][STAGE_M];
+};
+
 template <int SLOTS, bool HAS_NMASK, int KT, bool USE_FILTER>
-__global__ void __launch_bounds__(TILE, 2) k1_decode_canon_probe(ProbeArgs a, DbView db) {
-    __shared__ __align__(16) uint4 sb[2][TILE + 2];
-    __shared__ __align__(16) unsigned long long sn[2][TILE + 2];
-    __shared__ __align__(16) unsigned long long ss[2][TILE + 2];
+__global__ void __launch_bounds__(RT, 2) k1_decode_canon_probe(ProbeArgs a, DbView db) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SharedStage& stg = *reinterpret_cast<SharedStage*>(smem_raw);
+    WarpQueue& wq = *reinterpret_cast<WarpQueue*>(smem_raw + sizeof(SharedStage));
     __shared__ __align__(8) unsigned long long mbar[2];
     __shared__ unsigned long long s_total;
-    __shared__ WarpQueue wq;
+    // per stage: first staged 8-byte word of bases / of N mask, and whether the tile was staged at all
+    __shared__ unsigned long long s_bw0[2], s_mw0[2];
+    __shared__ unsigned s_staged[2];
 
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     const unsigned K = KT ? (unsigned)KT : db.K;
-    const unsigned long long ntiles = (a.w_end - a.w_begin + TILE - 1) / TILE;
-    const unsigned fshift = 64u - db.fbits, bshift = 64u - db.bbits;
+    const unsigned long long nreads = a.r_end - a.r_begin;
+    const unsigned long long ntiles = (nreads + RT - 1) / RT;
+    const unsigned bshift = 32u - db.bbits;      // 1 <= bbits <= 31
+    const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -171,29 +195,39 @@ __global__ void __launch_bounds__(TILE, 2) k1_decode_canon_probe(ProbeArgs a, Db
     if (lane == 0) wq.n[warp] = 0;
     __syncthreads();
 
+    // ---- producer side (thread 0): stage the stream range of one tile, if it fits
     auto issue = [&](unsigned stage, unsigned long long t) {
-        const unsigned long long t0 = a.w_begin + t * TILE;
-        const unsigned nv = (unsigned)((a.w_end - t0) < TILE ? (a.w_end - t0) : TILE);
-        uint32_t bytes_b, bytes_m;
-        const uint4* src_b; const unsigned long long *src_n, *src_s;
-        unsigned dst_b, dst_m;
-        if (t0 > 0) {
-            src_b = a.bases + (t0 - 1); dst_b = 0; bytes_b = (nv + 1) * 16u;
-            unsigned words = nv + 2; words += words & 1u;
-            src_n = a.nmask + (t0 - 2); src_s = a.smask + (t0 - 2); dst_m = 0; bytes_m = words * 8u;
+        const unsigned long long r0 = a.r_begin + t * RT;
+        const unsigned long long r1 = (r0 + RT < a.r_end) ? r0 + RT : a.r_end;
+        const unsigned long long p0 = a.off ? a.off[r0] : r0 * (unsigned long long)a.read_len;
+        const unsigned long long p1 = a.off ? a.off[r1] : r1 * (unsigned long long)a.read_len;
+        // bases: 8-byte words [p0/32, (p1+31)/32 + 6) rounded to 16 bytes; lanes read up to 6 words past their start
+        unsigned long long bw0 = (p0 >> 5) & ~1ull;
+        unsigned long long bw1 = ((p1 + 31) >> 5) + 6;
+        if (bw1 > a.base_words) bw1 = a.base_words;
+        bw1 = (bw1 + 1) & ~1ull;                                   // base_words is even (buffers are multiples of 16 bytes)
+        unsigned long long mw0 = (p0 >> 6) & ~1ull;
+        unsigned long long mw1 = ((p1 + 63) >> 6) + 4;
+        if (HAS_NMASK) { if (mw1 > a.nmask_words) mw1 = a.nmask_words; mw1 = (mw1 + 1) & ~1ull; }
+        const unsigned long long bytes_b = (bw1 - bw0) * 8ull, bytes_m = HAS_NMASK ? (mw1 - mw0) * 8ull : 0ull;
+        const bool fits = bw1 > bw0 && bytes_b <= STAGE_B && bytes_m <= STAGE_M;
+        s_bw0[stage] = bw0; s_mw0[stage] = mw0; s_staged[stage] = fits ? 1u : 0u;
+        if (fits) {
+            mbar_expect_tx(&mbar[stage], (uint32_t)(bytes_b + bytes_m));
+            bulk_g2s(&stg.b[stage][0], a.bases + bw0, (uint32_t)bytes_b, &mbar[stage], pol_stream);
+            if (HAS_NMASK && bytes_m) bulk_g2s(&stg.m[stage][0], a.nmask + mw0, (uint32_t)bytes_m, &mbar[stage], pol_stream);
         } else {
-            src_b = a.bases; dst_b = 1; bytes_b = nv * 16u;
-            unsigned words = nv + (nv & 1u);
-            src_n = a.nmask; src_s = a.smask; dst_m = 2; bytes_m = words * 8u;
+            mbar_arrive(&mbar[stage]);                            // nothing to wait for: lanes gather from global
         }
-        mbar_expect_tx(&mbar[stage], bytes_b + bytes_m * (HAS_NMASK ? 2u : 1u));
-        bulk_g2s(&sb[stage][dst_b], src_b, bytes_b, &mbar[stage]);
-        bulk_g2s(&ss[stage][dst_m], src_s, bytes_m, &mbar[stage]);
-        if (HAS_NMASK) bulk_g2s(&sn[stage][dst_m], src_n, bytes_m, &mbar[stage]);
     };
 
-    const key128 kmask = key_mask(2 * K);
-    const unsigned top_shift = 2 * (K - 1);   // position of the first base
+    // top-aligned masks of a 2K-bit value in four 32-bit words (word 3 most significant)
+    uint32_t km[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int hi_bit = 32 * (j + 1), lo_valid = 128 - 2 * (int)K;   // bits >= lo_valid are k-mer bits
+        km[j] = lo_valid <= 32 * j ? 0xFFFFFFFFu : (lo_valid >= hi_bit ? 0u : (0xFFFFFFFFu << (lo_valid - 32 * j)));
+    }
     unsigned long long my_valid = 0;
 
     unsigned it = 0;
@@ -203,117 +237,190 @@ __global__ void __launch_bounds__(TILE, 2) k1_decode_canon_probe(ProbeArgs a, Db
             issue(0, t);
             if (t + gridDim.x < ntiles) issue(1, t + gridDim.x);
         }
+        __syncthreads();                       // s_bw0 / s_staged of this stage are visible
         mbar_wait(&mbar[stage], parity);
 
-        const unsigned long long w = a.w_begin + t * TILE + tid;
-        const bool active = w < a.w_end;
-        uint4 cur = make_uint4(0, 0, 0, 0), prv = make_uint4(0, 0, 0, 0);
-        unsigned long long nm_cur = ~0ull, nm_prv = 0, sm_cur = 0, sm_prv = 0;
+        const unsigned long long r = a.r_begin + t * RT + tid;
+        const bool active = r < a.r_end;
+        unsigned long long R0 = 0, R1 = 0;
         if (active) {
-            cur = sb[stage][tid + 1];
-            sm_cur = bswap64(ss[stage][tid + 2]);
-            nm_cur = HAS_NMASK ? bswap64(sn[stage][tid + 2]) : 0ull;
-            if (w > 0) {
-                prv = sb[stage][tid];
-                sm_prv = bswap64(ss[stage][tid + 1]);
-                if (HAS_NMASK) nm_prv = bswap64(sn[stage][tid + 1]);
-            } else {
-                nm_prv = ~0ull;   // nothing before the stream: every window reaching back is invalid
-            }
-            if (w == a.nwords - 1) {
-                unsigned r = (unsigned)(a.nbases & 63ull);
-                if (r) nm_cur |= (1ull << (64 - r)) - 1ull;   // bases past the end of the stream
-            }
+            R0 = a.off ? a.off[r] : r * (unsigned long long)a.read_len;
+            R1 = a.off ? a.off[r + 1] : R0 + a.read_len;
         }
-        __syncthreads();   // everyone has copied its words out of this stage
-        if (tid == 0 && t + 2ull * gridDim.x < ntiles) issue(stage, t + 2ull * gridDim.x);
+        const unsigned long long len = R1 - R0;
+        const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
+        const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
+        const unsigned max_seg = __reduce_max_sync(0xFFFFFFFFu, nseg);
+        const bool staged = s_staged[stage] != 0;
+        const unsigned long long* bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[stage][0]) - s_bw0[stage] : a.bases;
+        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[stage][0]) - s_mw0[stage] : a.nmask;
 
-        // window-end validity: no N in the K bases ending here, no read start in the last K-1 of them.
-        // (threads past the end of the range carry nm_cur = all ones: nothing valid, but they keep in step
-        //  with their warp for the collectives below)
-        const unsigned long long inval = smear_low64(nm_prv, nm_cur, K) | smear_low64(sm_prv, sm_cur, K - 1);
-        const unsigned long long vmask = ~inval;
-        my_valid += __popcll(vmask);
+        for (unsigned seg = 0; seg < max_seg; ++seg) {
+            const unsigned c = seg < nseg ? (unsigned)((nw - (unsigned long long)seg * WMAX) < WMAX ? (nw - (unsigned long long)seg * WMAX) : WMAX) : 0u;
+            const unsigned long long s = R0 + (unsigned long long)seg * WMAX;
 
-        // MSB-first 64-bit halves: bases 0..31 and 32..63 of the word
-        const unsigned long long cur_hi = ((unsigned long long)__byte_perm(cur.x, 0, 0x0123) << 32) | __byte_perm(cur.y, 0, 0x0123);
-        const unsigned long long cur_lo = ((unsigned long long)__byte_perm(cur.z, 0, 0x0123) << 32) | __byte_perm(cur.w, 0, 0x0123);
-        key128 fwd;
-        fwd.hi = ((unsigned long long)__byte_perm(prv.x, 0, 0x0123) << 32) | __byte_perm(prv.y, 0, 0x0123);
-        fwd.lo = ((unsigned long long)__byte_perm(prv.z, 0, 0x0123) << 32) | __byte_perm(prv.w, 0, 0x0123);
-        fwd = key_and(fwd, kmask);          // the K bases that precede this word
-        key128 rcv = key_rc(fwd, K);
+            // ---- gather 160 bases (and N bits) starting at stream base s, top-aligned, into registers
+            uint32_t loc[SEGW];
+            uint32_t nl[5];
+#pragma unroll
+            for (int k = 0; k < (int)SEGW; ++k) loc[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) nl[k] = 0;
+            if (c) {
+                const unsigned long long q = s >> 5;
+                const unsigned sh = 2u * (unsigned)(s & 31ull);
+                unsigned long long W[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    unsigned long long idx = q + k;
+                    if (idx >= a.base_words) idx = a.base_words - 1;
+                    W[k] = bswap64(bsrc[idx]);
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const unsigned long long v = sh ? ((W[k] << sh) | (W[k + 1] >> (64 - sh))) : W[k];
+                    loc[2 * k] = (uint32_t)(v >> 32); loc[2 * k + 1] = (uint32_t)v;
+                }
+                if (HAS_NMASK) {
+                    const unsigned long long qn = s >> 6;
+                    const unsigned shn = (unsigned)(s & 63ull);
+                    unsigned long long M[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned long long idx = qn + k;
+                        if (idx >= a.nmask_words) idx = a.nmask_words - 1;
+                        M[k] = bswap64(msrc[idx]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const unsigned long long v = shn ? ((M[k] << shn) | (M[k + 1] >> (64 - shn))) : M[k];
+                        if (2 * k < 5) nl[2 * k] = (uint32_t)(v >> 32);
+                        if (2 * k + 1 < 5) nl[2 * k + 1] = (uint32_t)v;
+                    }
+                }
+            }
+            // ---- validity of the 96 window starts: i < c and no N in bases [i, i+K)
+            uint32_t v0, v1, v2;
+            {
+                if (HAS_NMASK && __any_sync(0xFFFFFFFFu, (nl[0] | nl[1] | nl[2] | nl[3] | nl[4]) != 0u)) {
+                    unsigned cover = 1;
+                    while (cover * 2 <= K) {                   // X |= X << cover (towards the smaller base index)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], cover);
+                        nl[4] |= nl[4] << cover;
+                        cover *= 2;
+                    }
+                    const unsigned rest = K - cover;            // < cover <= 32
+                    if (rest) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], rest);
+                        nl[4] |= nl[4] << rest;
+                    }
+                }
+                // first c bits set (MSB first)
+                const uint32_t c0 = c >= 32 ? 0xFFFFFFFFu : (c ? ~(0xFFFFFFFFu >> c) : 0u);
+                const uint32_t c1 = c >= 64 ? 0xFFFFFFFFu : (c > 32 ? ~(0xFFFFFFFFu >> (c - 32)) : 0u);
+                const uint32_t c2 = c >= 96 ? 0xFFFFFFFFu : (c > 64 ? ~(0xFFFFFFFFu >> (c - 64)) : 0u);
+                v0 = ~nl[0] & c0; v1 = ~nl[1] & c1; v2 = ~nl[2] & c2;
+            }
+            my_valid += __popc(v0) + __popc(v1) + __popc(v2);
+            if (__all_sync(0xFFFFFFFFu, (v0 | v1 | v2) == 0u)) continue;
 
-        constexpr int GROUP = 4;
+            // ---- reverse complement of the whole segment, aligned so that the reverse complement of window i
+            //      starts at base (WMAX-1-i) of it, whatever K is
+            uint32_t rcl[SEGW];
+            {
+                uint32_t t160[SEGW + 1];
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) t160[k] = rev2_32(~loc[SEGW - 1 - k]);
+                t160[SEGW] = 0;
+                const unsigned shl = 2u * (160u - (WMAX + K - 1u));      // bits to drop at the front
+                for (unsigned wsh = 0; wsh < (shl >> 5); ++wsh) {
+#pragma unroll
+                    for (int k = 0; k < (int)SEGW; ++k) t160[k] = t160[k + 1];
+                }
+                const unsigned bs = shl & 31u;
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) rcl[k] = fsl(t160[k], t160[k + 1], bs);
+            }
+
+            // ---- 6 blocks of 16 windows; the register windows loc[0..4] / rcl[5..9] slide by one word per block
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const unsigned long long word = half ? cur_lo : cur_hi;
-            const uint32_t vhalf = half ? (uint32_t)vmask : (uint32_t)(vmask >> 32);
-            if (__all_sync(0xFFFFFFFFu, vhalf == 0u)) {
-                // no lane of this warp has a valid window ending in this half: just advance the rolling registers
-                if (half == 0) {
-                    key128 nf;                       // (fwd << 64 | word) masked to 2K bits
-                    nf.hi = fwd.lo; nf.lo = word;
-                    fwd = key_and(nf, kmask);
-                    rcv = key_rc(fwd, K);
-                }
-                continue;
-            }
-#pragma unroll 2
-            for (int g0 = 0; g0 < 32; g0 += GROUP) {
-                unsigned long long chi[GROUP], clo[GROUP], h[GROUP];
-                bool ok[GROUP];
+            for (int blk = 0; blk < (int)(WMAX / 16); ++blk) {
+                const uint32_t vb = v0 & 0xFFFF0000u;            // validity of the 16 windows of this block, MSB first
+                v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
+                if (!__all_sync(0xFFFFFFFFu, vb == 0u)) {
+                    constexpr int GROUP = 4;
 #pragma unroll
-                for (int j = 0; j < GROUP; ++j) {
-                    const int i = g0 + j;
-                    const unsigned long long b = (word >> (62 - 2 * i)) & 3ull;
-                    fwd.hi = (fwd.hi << 2) | (fwd.lo >> 62);
-                    fwd.lo = (fwd.lo << 2) | b;
-                    fwd = key_and(fwd, kmask);
-                    rcv.lo = (rcv.lo >> 2) | (rcv.hi << 62);
-                    rcv.hi = rcv.hi >> 2;
-                    if (top_shift >= 64) rcv.hi |= (3ull - b) << (top_shift - 64);
-                    else rcv.lo |= (3ull - b) << (top_shift & 63u);
-                    ok[j] = (vhalf >> (31 - i)) & 1u;
-                    const bool use_rc = key_lt(rcv, fwd);
-                    chi[j] = use_rc ? rcv.hi : fwd.hi;
-                    clo[j] = use_rc ? rcv.lo : fwd.lo;
-                    key128 c; c.hi = chi[j]; c.lo = clo[j];
-                    h[j] = key_hash(c);
-                }
-                if (USE_FILTER) {
-                    // level 0: two bits of one 64-bit word of the L2-resident Bloom prefilter
-                    unsigned long long fw[GROUP];
+                    for (int g0 = 0; g0 < 16; g0 += GROUP) {
+                        uint32_t f3[GROUP], f2[GROUP], f1[GROUP], f0[GROUP], g3[GROUP], g2[GROUP], g1[GROUP], gz[GROUP];
+                        unsigned long long h[GROUP];
+                        bool ok[GROUP];
 #pragma unroll
-                    for (int j = 0; j < GROUP; ++j) {
-                        fw[j] = 0ull;
-                        if (ok[j]) fw[j] = __ldg(db.F + (h[j] >> fshift));
+                        for (int j = 0; j < GROUP; ++j) {
+                            const int tt = g0 + j;
+                            // forward k-mer of window tt: bases [tt, tt+K) of loc[0..4]
+                            f3[j] = fsl(loc[0], loc[1], 2 * tt) & km[3];
+                            f2[j] = fsl(loc[1], loc[2], 2 * tt) & km[2];
+                            f1[j] = fsl(loc[2], loc[3], 2 * tt) & km[1];
+                            f0[j] = fsl(loc[3], loc[4], 2 * tt) & km[0];
+                            // reverse complement: bases [15-tt, 15-tt+K) of rcl[5..9]
+                            g3[j] = fsl(rcl[5], rcl[6], 2 * (15 - tt)) & km[3];
+                            g2[j] = fsl(rcl[6], rcl[7], 2 * (15 - tt)) & km[2];
+                            g1[j] = fsl(rcl[7], rcl[8], 2 * (15 - tt)) & km[1];
+                            gz[j] = fsl(rcl[8], rcl[9], 2 * (15 - tt)) & km[0];
+                            ok[j] = (vb >> (31 - tt)) & 1u;
+                            h[j] = hash_digest(f3[j] + g3[j], f2[j] + g2[j], f1[j] + g1[j], f0[j] + gz[j]);
+                        }
+                        if (USE_FILTER) {
+                            uint32_t fw[GROUP];
+#pragma unroll
+                            for (int j = 0; j < GROUP; ++j) {
+                                fw[j] = 0u;
+                                if (ok[j]) fw[j] = load_filter(db.F + filter_word(h[j], db.nfw), pol_keep);
+                            }
+#pragma unroll
+                            for (int j = 0; j < GROUP; ++j) ok[j] = ok[j] & (bool)((fw[j] >> filter_bit(h[j])) & 1u);
+                        }
+                        BucketVec<SLOTS> vec[GROUP];
+#pragma unroll
+                        for (int j = 0; j < GROUP; ++j)
+                            if (ok[j]) load_bucket(db.T1, (uint32_t)(h[j] >> 32) >> bshift, vec[j], pol_stream);
+                        bool cand[GROUP];
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < GROUP; ++j) {
+                            cand[j] = ok[j] & bucket_candidate<SLOTS>(vec[j], hash_fp(h[j]));   // no short circuit: stay branch-free
+                            any |= cand[j];
+                        }
+                        if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+                            for (int j = 0; j < GROUP; ++j) {
+                                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, cand[j]);
+                                if (ballot) {
+                                    // canonical = the smaller of the two (top-aligned order == numeric order)
+                                    key128 F, G;
+                                    F.hi = ((unsigned long long)f3[j] << 32) | f2[j]; F.lo = ((unsigned long long)f1[j] << 32) | f0[j];
+                                    G.hi = ((unsigned long long)g3[j] << 32) | g2[j]; G.lo = ((unsigned long long)g1[j] << 32) | gz[j];
+                                    const key128 cn = key_shr(key_lt(G, F) ? G : F, 128 - 2 * K);
+                                    queue_push(wq, warp, lane, ballot, cand[j], cn.hi, cn.lo, db, a.cnt8);
+                                }
+                            }
+                        }
                     }
-#pragma unroll
-                    for (int j = 0; j < GROUP; ++j) {
-                        const unsigned long long m = filter_mask(h[j]);
-                        ok[j] = ok[j] && ((fw[j] & m) == m);
-                    }
                 }
-                // level 1: one bucket of 31-bit fingerprints (a 32- or 16-byte sector of HBM)
-                BucketVec<SLOTS> vec[GROUP];
+                // slide the register windows
 #pragma unroll
-                for (int j = 0; j < GROUP; ++j) {
+                for (int k = 0; k < (int)SEGW - 1; ++k) loc[k] = loc[k + 1];
 #pragma unroll
-                    for (int s = 0; s < SLOTS; ++s) vec[j].w[s] = 0u;
-                    if (ok[j]) load_bucket(db.T1, db.bbits ? (h[j] >> bshift) : 0ull, vec[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < GROUP; ++j) {
-                    const bool cand = ok[j] && bucket_candidate<SLOTS>(vec[j], hash_fp(h[j]));
-                    queue_push(wq, warp, lane, cand, chi[j], clo[j], db, a.cnt8);
-                }
+                for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
             }
         }
+        __syncthreads();                       // every lane is done with this stage's shared memory
+        if (tid == 0 && t + 2ull * gridDim.x < ntiles) issue(stage, t + 2ull * gridDim.x);
     }
     queue_drain(wq, warp, lane, db, a.cnt8);
 
-    // block-reduce the number of valid windows
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xFFFFFFFFu, my_valid, o);
     if (lane == 0 && my_valid) atomicAdd(&s_total, my_valid);
     __syncthreads();
@@ -321,26 +428,6 @@ __global__ void __launch_bounds__(TILE, 2) k1_decode_canon_probe(ProbeArgs a, Db
 }
 
 // ---------------------------------------------------------------- prep kernels
-// store a logical MSB-first 64-bit mask in the stream's byte order (bit i -> byte i/8, bit 7-(i%8))
-__device__ __forceinline__ unsigned long long to_stream_order(unsigned long long m) { return bswap64(m); }
-
-__global__ void k_smask_fixed(unsigned long long* smask, unsigned long long nwords_alloc, unsigned long long nbases, uint32_t L) {
-    unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (w >= nwords_alloc) return;
-    unsigned long long m = 0, base0 = w * 64ull;
-    unsigned long long p = ((base0 + L - 1) / L) * L;
-    for (; p < base0 + 64ull && p < nbases; p += L) m |= 1ull << (63 - (unsigned)(p - base0));
-    smask[w] = to_stream_order(m);
-}
-__global__ void k_smask_offsets(unsigned long long* smask, const unsigned long long* off, unsigned long long nreads) {
-    unsigned long long r = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (r >= nreads) return;
-    unsigned long long p = off[r];
-    if (p >= off[nreads]) return;
-    unsigned long long byte = p >> 3;
-    uint32_t* wp = reinterpret_cast<uint32_t*>(smask) + (byte >> 2);
-    atomicOr(wp, 1u << (8u * (unsigned)(byte & 3ull) + (7u - (unsigned)(p & 7ull))));
-}
 __device__ __forceinline__ uint32_t ascii_code(unsigned char c) {
     switch (c) {
         case 'A': case 'a': return 0;
@@ -382,16 +469,27 @@ __global__ void k_ascii_to_keys(const unsigned char* text, unsigned long long ns
     keys[s] = k;
 }
 
+constexpr size_t K1_SMEM = sizeof(SharedStage) + sizeof(WarpQueue);
+
 template <int SLOTS, bool HAS_NMASK, bool USE_FILTER>
 int launch_probe_k(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
-    if (db.K == 60) k1_decode_canon_probe<SLOTS, HAS_NMASK, 60, USE_FILTER><<<grid, TILE, 0, st>>>(a, db);
-    else k1_decode_canon_probe<SLOTS, HAS_NMASK, 0, USE_FILTER><<<grid, TILE, 0, st>>>(a, db);
+    if (db.K == 60) {
+        auto kern = k1_decode_canon_probe<SLOTS, HAS_NMASK, 60, USE_FILTER>;
+        static bool once = false;
+        if (!once) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM)); once = true; }
+        kern<<<grid, RT, K1_SMEM, st>>>(a, db);
+    } else {
+        auto kern = k1_decode_canon_probe<SLOTS, HAS_NMASK, 0, USE_FILTER>;
+        static bool once = false;
+        if (!once) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM)); once = true; }
+        kern<<<grid, RT, K1_SMEM, st>>>(a, db);
+    }
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }
 template <int SLOTS>
 int launch_probe_s(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
-    const bool nm = a.nmask != nullptr, fl = db.fbits != 0;
+    const bool nm = a.nmask != nullptr, fl = db.nfw != 0;
     if (nm) return fl ? launch_probe_k<SLOTS, true, true>(db, a, st, grid) : launch_probe_k<SLOTS, true, false>(db, a, st, grid);
     return fl ? launch_probe_k<SLOTS, false, true>(db, a, st, grid) : launch_probe_k<SLOTS, false, false>(db, a, st, grid);
 }
@@ -399,8 +497,8 @@ int launch_probe_s(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsign
 }  // namespace
 
 int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaStream_t st) {
-    if (a.w_end <= a.w_begin) return MLG_OK;
-    const unsigned long long ntiles = (a.w_end - a.w_begin + TILE - 1) / TILE;
+    if (a.r_end <= a.r_begin) return MLG_OK;
+    const unsigned long long ntiles = (a.r_end - a.r_begin + RT - 1) / RT;
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
         ctas_per_sm = 8;   // more CTAs than are resident: the hardware scheduler evens out the tail
@@ -411,20 +509,6 @@ int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaS
     return db.slots == 8 ? launch_probe_s<8>(db, a, st, grid) : launch_probe_s<4>(db, a, st, grid);
 }
 
-int launch_build_smask_fixed(unsigned long long* smask, unsigned long long nwords_alloc, unsigned long long nbases,
-                             uint32_t read_len, cudaStream_t st) {
-    if (!nwords_alloc) return MLG_OK;
-    k_smask_fixed<<<(unsigned)((nwords_alloc + 255) / 256), 256, 0, st>>>(smask, nwords_alloc, nbases, read_len);
-    CUDA_TRY(cudaGetLastError());
-    return MLG_OK;
-}
-int launch_build_smask_offsets(unsigned long long* smask, const unsigned long long* off, unsigned long long nreads,
-                               cudaStream_t st) {
-    if (!nreads) return MLG_OK;
-    k_smask_offsets<<<(unsigned)((nreads + 255) / 256), 256, 0, st>>>(smask, off, nreads);
-    CUDA_TRY(cudaGetLastError());
-    return MLG_OK;
-}
 int launch_pack_ascii(const unsigned char* text, unsigned long long nbases, unsigned char* bases, unsigned char* nmask,
                       cudaStream_t st) {
     unsigned long long ngroups = (nbases + 7) / 8;

@@ -6,8 +6,9 @@ void t_canon(unsigned long long hi, unsigned long long lo, unsigned k, unsigned 
 void t_sub(unsigned long long hi, unsigned long long lo, unsigned K, unsigned off, unsigned k, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_sub(a, K, off, k); out[0] = r.hi; out[1] = r.lo; }
 void t_prefix(unsigned long long hi, unsigned long long lo, unsigned K, unsigned k, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_prefix(a, K, k); out[0] = r.hi; out[1] = r.lo; }
 void t_shl(unsigned long long hi, unsigned long long lo, unsigned s, unsigned long long* out) { key128 a{hi, lo}; key128 r = key_shl(a, s); out[0] = r.hi; out[1] = r.lo; }
-unsigned long long t_hash(unsigned long long hi, unsigned long long lo) { key128 a{hi, lo}; return key_hash(a); }
+unsigned long long t_hash(unsigned long long hi, unsigned long long lo, unsigned K) { key128 a{hi, lo}; return key_hash(a, K); }
 unsigned long long t_bucket(unsigned long long h, unsigned bbits) { return hash_bucket(h, bbits); }
-unsigned long long t_fmask(unsigned long long h) { return filter_mask(h); }
+unsigned t_fword(unsigned long long h, unsigned nfw) { return filter_word(h, nfw); }
+unsigned t_fbit(unsigned long long h) { return filter_bit(h); }
 unsigned t_fp(unsigned long long h) { return hash_fp(h); }
 }

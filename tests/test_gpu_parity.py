@@ -307,7 +307,7 @@ def test_prefilter_variants(ctx, workload, monkeypatch, filter_mb):
     q = db.query()
     q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
     res = q.finish()
-    assert (res["stats"]["filter_log2_words"] == 0) == (filter_mb == "0")
+    assert (res["stats"]["filter_words"] == 0) == (filter_mb == "0")
     _check(res, q.intersection(), *w["refs"]["exact"])
     q.close()
     db.close()

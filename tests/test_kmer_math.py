@@ -24,13 +24,15 @@ def kh(tmp_path_factory):
     L.t_sub.argtypes = [u64, u64, C.c_uint, C.c_uint, C.c_uint, C.POINTER(u64 * 2)]
     L.t_prefix.argtypes = [u64, u64, C.c_uint, C.c_uint, C.POINTER(u64 * 2)]
     L.t_shl.argtypes = [u64, u64, C.c_uint, C.POINTER(u64 * 2)]
-    L.t_hash.argtypes = [u64, u64]
+    L.t_hash.argtypes = [u64, u64, C.c_uint]
     L.t_hash.restype = u64
     L.t_bucket.argtypes = [u64, u64]
     L.t_bucket.restype = u64
     L.t_bucket.argtypes = [u64, C.c_uint]
-    L.t_fmask.argtypes = [u64]
-    L.t_fmask.restype = u64
+    L.t_fword.argtypes = [u64, C.c_uint]
+    L.t_fword.restype = C.c_uint
+    L.t_fbit.argtypes = [u64]
+    L.t_fbit.restype = C.c_uint
     L.t_fp.argtypes = [u64]
     L.t_fp.restype = C.c_uint
     return L
@@ -71,9 +73,15 @@ def test_hash_bucket_monotone_and_fp_nonzero(kh):
     for bbits in (0, 1, 7, 20, 31):
         b = [kh.t_bucket(h, bbits) for h in hs]
         assert b == sorted(b) and max(b) < (1 << bbits)
-    masks = [kh.t_fmask(h) for h in hs]
-    assert all(1 <= bin(m).count("1") <= 2 for m in masks)
+    for nfw in (1, 1000, 10_000_000):
+        assert all(kh.t_fword(h, nfw) < nfw for h in hs)
+    assert all(kh.t_fbit(h) < 32 for h in hs)
     assert kh.t_fp(0) == 1 and kh.t_fp(1 << 31) == 1
     assert all(0 < kh.t_fp(h) < 2**31 for h in hs)
     # different keys hash differently (sanity, not a guarantee)
-    assert len({kh.t_hash(rng.getrandbits(56), rng.getrandbits(64)) for _ in range(5000)}) == 5000
+    assert len({kh.t_hash(rng.getrandbits(56), rng.getrandbits(64), 60) for _ in range(5000)}) == 5000
+    # the hash is strand-symmetric: a k-mer and its reverse complement hash alike
+    for _ in range(200):
+        K = rng.randint(8, 63)
+        s = "".join(rng.choice("ACGT") for _ in range(K))
+        assert kh.t_hash(*codec.kmer_to_key(s), K) == kh.t_hash(*codec.kmer_to_key(oracle_py.rc(s)), K)
