@@ -271,7 +271,7 @@ def run_native(args):
     probe_ms = float(np.mean([s["ms_probe"] for s in st_dev]))
     nbases = reads_per_gpu * READ_LEN
     bucket_bytes = st_dev[-1]["bucket_bytes"]
-    alg_bytes = kmers_step * bucket_bytes + nbases // 4 + nbases // 8 + nbases // 8
+    alg_bytes = kmers_step * bucket_bytes + nbases // 4 + nbases // 8      # one sector per probe + packed bases + N mask, read once
     achieved = alg_bytes / (probe_ms / 1e3) / 1e9
     query_ms = float(np.mean([s["ms_query"] for s in st_dev]))
     launches = int(sum(s["gpu_launches"] for s in st_dev))
