@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmetalign_b200.so")
+LIB_PATH = os.environ.get("MLG_LIB_PATH") or os.path.join(_HERE, "libmetalign_b200.so")   # MLG_LIB_PATH: experiment builds
 _LIB = None
 
 
@@ -37,7 +37,7 @@ def build(force: bool = False) -> str:
     srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".h"))]
     srcs.append(os.path.join(_HERE, "..", "include", "metalign_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs)
-    if force or stale:
+    if (force or stale) and not os.environ.get("MLG_LIB_PATH"):
         subprocess.check_call(["make", "-C", src_dir, "-s"])
     return LIB_PATH
 

@@ -1,6 +1,7 @@
 // C ABI of libmetalign_b200.so (declared in include/metalign_b200.h).  Host-side orchestration only:
 // buffers, streams, chunked host->device copies overlapped with the probe kernel, and the finish stage.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "mlg_internal.h"
@@ -215,6 +216,14 @@ MLG_API int mlg_ctx_create(int device, mlg_ctx** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { mlg_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return MLG_ERR_CUDA; }
+    // Random 32-byte probes: do not let an L2 miss fetch the neighbouring sector as well (the default
+    // fetch granularity is 64 bytes, which doubles DRAM traffic for this access pattern).
+    {
+        size_t gran = 32;
+        if (const char* s = getenv("MLG_L2_FETCH")) gran = (size_t)atoi(s);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     mlg_ctx* ctx = new mlg_ctx();
     ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) != cudaSuccess ||

@@ -112,9 +112,9 @@ __global__ void k_hbucket_hist(const unsigned long long* h, uint32_t nd, uint32_
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nd) atomicAdd(&counts[hash_bucket(h[i], bbits)], 1u);
 }
-__global__ void k_fill_filter(const unsigned long long* h, uint32_t nd, uint32_t nfw, uint32_t* F) {
+__global__ void k_fill_filter(const unsigned long long* h, uint32_t nd, uint32_t nfw, uint32_t fk, uint32_t* F) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nd) atomicOr(&F[filter_word(h[i], nfw)], 1u << filter_bit(h[i]));
+    if (i < nd) atomicOr(&F[filter_word(h[i], nfw)], filter_mask(h[i], fk));
 }
 __global__ void k_fill_t1(const unsigned long long* h, uint32_t nd, uint32_t bbits, const uint32_t* bstart,
                           uint32_t slots, uint32_t* T1) {
@@ -357,9 +357,9 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         CUDA_TRY(cudaMemsetAsync(db->T1.p, 0, (nb * slots_per_bucket + 8) * 4, st));
         if (nd) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p, slots_per_bucket, db->T1.p);
         v.bstart = db->bstart.p; v.T1 = db->T1.p;
-        // One-bit-per-key prefilter sized to stay L2-resident: MLG_FILTER_MB MiB at most (default 48), 16 bits per
+        // One-bit-per-key prefilter sized to stay L2-resident: MLG_FILTER_MB MiB at most (default 64), 16 bits per
         // key at most; below 1.5 bits per key it would pass most probes and is left out.
-        double max_mb = 48.0;
+        double max_mb = 64.0;
         if (const char* s = getenv("MLG_FILTER_MB")) max_mb = atof(s);
         unsigned long long nfw = 0;                       // 32-bit words
         if (nd && max_mb > 0) {
@@ -370,14 +370,18 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             if ((double)nfw * 32.0 < 1.5 * (double)nd) nfw = 0;
         }
         v.nfw = (uint32_t)nfw; v.F = nullptr;
+        v.fk = ((double)nfw * 32.0 >= 3.0 * (double)nd) ? 2u : 1u;     // two probe bits pay off above ~3 bits per key
+        if (const char* s = getenv("MLG_FILTER_K")) { int x = atoi(s); if (x == 1 || x == 2) v.fk = (uint32_t)x; }
         if (nfw) {
             MLG_TRY(db->F.alloc(nfw));
             CUDA_TRY(cudaMemsetAsync(db->F.p, 0, nfw * 4, st));
-            k_fill_filter<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, (uint32_t)nfw, db->F.p);
+            k_fill_filter<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, (uint32_t)nfw, v.fk, db->F.p);
             v.F = db->F.p;
-            // optional: pin the prefilter in L2 (persisting access-policy window on the compute stream)
+            // pin the prefilter in L2: grow the persisting carve-out (default 24 MB of the 79 MB this part allows) and
+            // put a persisting access-policy window over F on the compute stream.  MLG_L2_PERSIST=0 leaves the
+            // device limits alone (the kernel's evict_last / evict_first load policies still apply).
             const char* pe = getenv("MLG_L2_PERSIST");
-            if (pe && atoi(pe) > 0) {
+            if (!pe || atoi(pe) > 0) {
                 cudaDeviceProp prop;
                 if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
                     size_t fbytes = (size_t)nfw * 4;

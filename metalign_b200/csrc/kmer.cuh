@@ -105,6 +105,12 @@ MLG_HD unsigned filter_word(unsigned long long h, unsigned nfw) {
 #endif
 }
 MLG_HD unsigned filter_bit(unsigned long long h) { return ((unsigned)h >> 26) & 31u; }
+// bits of the key inside its filter word: one bit, or two (fk == 2) when the filter has enough bits per key
+MLG_HD unsigned filter_mask(unsigned long long h, unsigned fk) {
+    unsigned m = 1u << (((unsigned)h >> 26) & 31u);
+    if (fk == 2) m |= 1u << (((unsigned)h >> 21) & 31u);
+    return m;
+}
 // 31-bit non-zero fingerprint (bit 31 of a bucket's first word is the overflow flag, 0 = empty slot)
 MLG_HD unsigned hash_fp(unsigned long long h) {
     unsigned f = (unsigned)h & 0x7FFFFFFFu;

@@ -85,6 +85,7 @@ struct DbView {
     // L2-resident prefilter over D: nfw 32-bit words, one bit per key (nfw == 0: disabled)
     const uint32_t* F;
     uint32_t nfw;
+    uint32_t fk;                 // bits per key in the prefilter (1 or 2)
 };
 
 struct mlg_db {

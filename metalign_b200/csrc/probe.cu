@@ -23,6 +23,12 @@
 
 namespace {
 
+#ifndef K1_GROUP
+#define K1_GROUP 4                      // windows whose loads are in flight together, per lane
+#endif
+#ifndef K1_MINCTAS
+#define K1_MINCTAS 2                    // __launch_bounds__ minimum CTAs per SM (caps registers at 65536 / (256 * K1_MINCTAS))
+#endif
 constexpr unsigned RT = 256;            // reads per tile == threads per CTA
 constexpr unsigned WARPS = RT / 32;
 constexpr unsigned WMAX = 96;           // window starts per segment
@@ -169,7 +175,7 @@ struct SharedStage {
 };
 
 template <int SLOTS, bool HAS_NMASK, int KT, bool USE_FILTER>
-__global__ void __launch_bounds__(RT, 2) k1_decode_canon_probe(ProbeArgs a, DbView db) {
+__global__ void __launch_bounds__(RT, K1_MINCTAS) k1_decode_canon_probe(ProbeArgs a, DbView db) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SharedStage& stg = *reinterpret_cast<SharedStage*>(smem_raw);
     WarpQueue& wq = *reinterpret_cast<WarpQueue*>(smem_raw + sizeof(SharedStage));
@@ -350,27 +356,26 @@ __global__ void __launch_bounds__(RT, 2) k1_decode_canon_probe(ProbeArgs a, DbVi
                 const uint32_t vb = v0 & 0xFFFF0000u;            // validity of the 16 windows of this block, MSB first
                 v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
                 if (!__all_sync(0xFFFFFFFFu, vb == 0u)) {
-                    constexpr int GROUP = 4;
+                    constexpr int GROUP = K1_GROUP;
 #pragma unroll
                     for (int g0 = 0; g0 < 16; g0 += GROUP) {
-                        uint32_t f3[GROUP], f2[GROUP], f1[GROUP], f0[GROUP], g3[GROUP], g2[GROUP], g1[GROUP], gz[GROUP];
                         unsigned long long h[GROUP];
                         bool ok[GROUP];
 #pragma unroll
                         for (int j = 0; j < GROUP; ++j) {
                             const int tt = g0 + j;
                             // forward k-mer of window tt: bases [tt, tt+K) of loc[0..4]
-                            f3[j] = fsl(loc[0], loc[1], 2 * tt) & km[3];
-                            f2[j] = fsl(loc[1], loc[2], 2 * tt) & km[2];
-                            f1[j] = fsl(loc[2], loc[3], 2 * tt) & km[1];
-                            f0[j] = fsl(loc[3], loc[4], 2 * tt) & km[0];
+                            const uint32_t f3 = fsl(loc[0], loc[1], 2 * tt) & km[3];
+                            const uint32_t f2 = fsl(loc[1], loc[2], 2 * tt) & km[2];
+                            const uint32_t f1 = fsl(loc[2], loc[3], 2 * tt) & km[1];
+                            const uint32_t f0 = fsl(loc[3], loc[4], 2 * tt) & km[0];
                             // reverse complement: bases [15-tt, 15-tt+K) of rcl[5..9]
-                            g3[j] = fsl(rcl[5], rcl[6], 2 * (15 - tt)) & km[3];
-                            g2[j] = fsl(rcl[6], rcl[7], 2 * (15 - tt)) & km[2];
-                            g1[j] = fsl(rcl[7], rcl[8], 2 * (15 - tt)) & km[1];
-                            gz[j] = fsl(rcl[8], rcl[9], 2 * (15 - tt)) & km[0];
+                            const uint32_t g3 = fsl(rcl[5], rcl[6], 2 * (15 - tt)) & km[3];
+                            const uint32_t g2 = fsl(rcl[6], rcl[7], 2 * (15 - tt)) & km[2];
+                            const uint32_t g1 = fsl(rcl[7], rcl[8], 2 * (15 - tt)) & km[1];
+                            const uint32_t gz = fsl(rcl[8], rcl[9], 2 * (15 - tt)) & km[0];
                             ok[j] = (vb >> (31 - tt)) & 1u;
-                            h[j] = hash_digest(f3[j] + g3[j], f2[j] + g2[j], f1[j] + g1[j], f0[j] + gz[j]);
+                            h[j] = hash_digest(f3 + g3, f2 + g2, f1 + g1, f0 + gz);
                         }
                         if (USE_FILTER) {
                             uint32_t fw[GROUP];
@@ -380,7 +385,10 @@ __global__ void __launch_bounds__(RT, 2) k1_decode_canon_probe(ProbeArgs a, DbVi
                                 if (ok[j]) fw[j] = load_filter(db.F + filter_word(h[j], db.nfw), pol_keep);
                             }
 #pragma unroll
-                            for (int j = 0; j < GROUP; ++j) ok[j] = ok[j] & (bool)((fw[j] >> filter_bit(h[j])) & 1u);
+                            for (int j = 0; j < GROUP; ++j) {
+                                const uint32_t m = filter_mask(h[j], db.fk);
+                                ok[j] = ok[j] & ((fw[j] & m) == m);
+                            }
                         }
                         BucketVec<SLOTS> vec[GROUP];
 #pragma unroll
@@ -398,10 +406,14 @@ __global__ void __launch_bounds__(RT, 2) k1_decode_canon_probe(ProbeArgs a, DbVi
                             for (int j = 0; j < GROUP; ++j) {
                                 const unsigned ballot = __ballot_sync(0xFFFFFFFFu, cand[j]);
                                 if (ballot) {
+                                    // rebuild the two k-mers (not kept alive across the loads);
                                     // canonical = the smaller of the two (top-aligned order == numeric order)
+                                    const int tt = g0 + j;
                                     key128 F, G;
-                                    F.hi = ((unsigned long long)f3[j] << 32) | f2[j]; F.lo = ((unsigned long long)f1[j] << 32) | f0[j];
-                                    G.hi = ((unsigned long long)g3[j] << 32) | g2[j]; G.lo = ((unsigned long long)g1[j] << 32) | gz[j];
+                                    F.hi = ((unsigned long long)(fsl(loc[0], loc[1], 2 * tt) & km[3]) << 32) | (fsl(loc[1], loc[2], 2 * tt) & km[2]);
+                                    F.lo = ((unsigned long long)(fsl(loc[2], loc[3], 2 * tt) & km[1]) << 32) | (fsl(loc[3], loc[4], 2 * tt) & km[0]);
+                                    G.hi = ((unsigned long long)(fsl(rcl[5], rcl[6], 2 * (15 - tt)) & km[3]) << 32) | (fsl(rcl[6], rcl[7], 2 * (15 - tt)) & km[2]);
+                                    G.lo = ((unsigned long long)(fsl(rcl[7], rcl[8], 2 * (15 - tt)) & km[1]) << 32) | (fsl(rcl[8], rcl[9], 2 * (15 - tt)) & km[0]);
                                     const key128 cn = key_shr(key_lt(G, F) ? G : F, 128 - 2 * K);
                                     queue_push(wq, warp, lane, ballot, cand[j], cn.hi, cn.lo, db, a.cnt8);
                                 }

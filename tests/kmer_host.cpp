@@ -10,5 +10,6 @@ unsigned long long t_hash(unsigned long long hi, unsigned long long lo, unsigned
 unsigned long long t_bucket(unsigned long long h, unsigned bbits) { return hash_bucket(h, bbits); }
 unsigned t_fword(unsigned long long h, unsigned nfw) { return filter_word(h, nfw); }
 unsigned t_fbit(unsigned long long h) { return filter_bit(h); }
+unsigned t_fmask(unsigned long long h, unsigned fk) { return filter_mask(h, fk); }
 unsigned t_fp(unsigned long long h) { return hash_fp(h); }
 }

@@ -33,6 +33,8 @@ def kh(tmp_path_factory):
     L.t_fword.restype = C.c_uint
     L.t_fbit.argtypes = [u64]
     L.t_fbit.restype = C.c_uint
+    L.t_fmask.argtypes = [u64, C.c_uint]
+    L.t_fmask.restype = C.c_uint
     L.t_fp.argtypes = [u64]
     L.t_fp.restype = C.c_uint
     return L
@@ -76,6 +78,7 @@ def test_hash_bucket_monotone_and_fp_nonzero(kh):
     for nfw in (1, 1000, 10_000_000):
         assert all(kh.t_fword(h, nfw) < nfw for h in hs)
     assert all(kh.t_fbit(h) < 32 for h in hs)
+    assert all(kh.t_fmask(h, 1) == 1 << kh.t_fbit(h) and bin(kh.t_fmask(h, 2)).count('1') in (1, 2) for h in hs)
     assert kh.t_fp(0) == 1 and kh.t_fp(1 << 31) == 1
     assert all(0 < kh.t_fp(h) < 2**31 for h in hs)
     # different keys hash differently (sanity, not a guarantee)
