@@ -49,53 +49,69 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and clock-event (throttle) reasons sampled through NVML every few ms by a thread, DURING the
+    timed region only (start() / stop() bracket it)."""
+    BAD = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
-    def __init__(self, index):
-        self.index = index
-        self.lines = []
-        self.proc = None
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.stop_flag, self.thread, self.err = [], set(), False, None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except (ValueError, IndexError):
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, str(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, attr in self.BAD:
+                    if r & getattr(nv, attr):
+                        self.reasons.add(name)
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nv:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.nv or not self.thread:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["no samples: %s" % self.err]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "sm_mhz_min": float(min(self.sm))}
+
+
+def measured_traffic():
+    """DRAM bytes per k-mer of the probe kernel from the committed `ncu --set full` capture (profiles/k1_traffic.json,
+    written by scripts/ncu_summary.py): dram__bytes_read.sum + dram__bytes_write.sum over the k-mers of that launch."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def synth_params(G, paired):
@@ -135,7 +151,7 @@ def run_reference(args):
         return
     import synth
     G = env_int("MLG_BENCH_G", 200_000)
-    sample = env_int("MLG_BENCH_CPU_READS", 1_000_000)
+    sample = env_int("MLG_BENCH_CPU_READS", 2_000_000)
     p = synth_params(G, 0)
     keys = synth.sketch_keys(p)
     r = cpu_baseline_run(p, keys, 0, sample, repeats=args.warmup + args.steps)
@@ -200,6 +216,13 @@ def run_native(args):
     h_bases = torch.empty(nbb, dtype=torch.uint8, pin_memory=True)
     h_nmask = torch.empty(nmb, dtype=torch.uint8, pin_memory=True)
     h_bases.copy_(d_bases); h_nmask.copy_(d_nmask)
+    # the end-to-end leg hands N over as (start, length) runs, the compact form of the same information
+    # (mlg_query_push_packed_nruns): 0.1 % of the bases are N, so the mask would be a third of the PCIe bytes
+    from metalign_b200 import codec
+    runs_np = codec.nmask_to_runs(h_nmask.numpy(), reads_per_gpu * READ_LEN)
+    h_runs = torch.empty(max(1, runs_np.size), dtype=torch.int32, pin_memory=True)
+    h_runs[:runs_np.size].copy_(torch.from_numpy(runs_np.reshape(-1).view(np.int32)))
+    n_runs = runs_np.shape[0]
     nk = len(KS)
     h_num = torch.empty(G * nk, dtype=torch.int64, pin_memory=True)
     h_den = torch.empty(G * nk, dtype=torch.int64, pin_memory=True)
@@ -209,7 +232,11 @@ def run_native(args):
     def step(host: bool):
         q = db.query(2, "exact", True)
         if host:
-            q.push_packed_ptr(h_bases.data_ptr(), h_nmask.data_ptr(), None, reads_per_gpu, READ_LEN, device=False)
+            if os.environ.get("MLG_BENCH_E2E_MASK"):
+                q.push_packed_ptr(h_bases.data_ptr(), h_nmask.data_ptr(), None, reads_per_gpu, READ_LEN, device=False)
+            else:
+                q.push_packed_nruns_ptr(h_bases.data_ptr(), h_runs.data_ptr() if n_runs else None, n_runs, None,
+                                        reads_per_gpu, READ_LEN)
         else:
             q.push_packed_ptr(d_bases.data_ptr(), d_nmask.data_ptr(), None, reads_per_gpu, READ_LEN, device=True)
         if world > 1:
@@ -250,7 +277,7 @@ def run_native(args):
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, wall_dev, st_dev, ni, clocks = timed(False, args.steps, args.warmup, sampler)
-    ms_e2e, wall_e2e, st_e2e, ni2, _ = timed(True, args.steps, max(1, args.warmup // 2))
+    ms_e2e, wall_e2e, st_e2e, ni2, _ = timed(True, args.steps, args.warmup)
     assert ni == ni2
 
     kmers_step = st_dev[-1]["n_kmers"]
@@ -271,9 +298,18 @@ def run_native(args):
     probe_ms = float(np.mean([s["ms_probe"] for s in st_dev]))
     nbases = reads_per_gpu * READ_LEN
     bucket_bytes = st_dev[-1]["bucket_bytes"]
-    alg_bytes = kmers_step * bucket_bytes + nbases // 4 + nbases // 8      # one sector per probe + packed bases + N mask, read once
+    # one 32-byte sector per level-1 bucket fetch + the packed bases and N mask read once.  Layout 0
+    # fetches one bucket per k-mer; the super-k-mer layout (1) one per run of windows sharing a minimizer, and
+    # the reduced fetch count is reported next to it.
+    layout = int(st_dev[-1]["layout"])
+    fetches = int(st_dev[-1]["n_bucket_fetches"])
+    alg_bytes = fetches * bucket_bytes + nbases // 4 + nbases // 8
     achieved = alg_bytes / (probe_ms / 1e3) / 1e9
     query_ms = float(np.mean([s["ms_query"] for s in st_dev]))
+    tr = measured_traffic()
+    traffic = tr["dram_bytes_per_kmer"] * kmers_step if tr and G == tr.get("genomes") and tr.get("layout", 0) == int(st_dev[-1]["layout"]) else None
+    traffic_src = ("%s: %.2f DRAM bytes per k-mer (ncu --set full, %s) x k-mers per step" % (tr["source"], tr["dram_bytes_per_kmer"], tr["kernel"])
+                   if traffic is not None else "no ncu capture for this database size")
     launches = int(sum(s["gpu_launches"] for s in st_dev))
 
     if rank == 0:
@@ -296,20 +332,23 @@ def run_native(args):
                     "d2h_bytes_per_step": int(st_e2e[-1]["d2h_bytes"]) * world, "ms_per_step": sec_step_e2e * 1e3,
                     "gbases_per_s": bases_total / sec_step_e2e / 1e9},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k1_decode_canon_probe", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "k1_superkmer_probe" if int(st_dev[-1]["layout"]) == 1 else "k1_decode_canon_probe", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch_set": int(alg_bytes), "kernel_ms_per_step": probe_ms,
-                         "finish_stage_ms_per_step": query_ms, "kmers_per_s_kernel_only": kmers_step / (probe_ms / 1e3)},
+                         "finish_stage_ms_per_step": query_ms, "kmers_per_s_kernel_only": kmers_step / (probe_ms / 1e3),
+                         "layout": layout, "bucket_fetches_per_step": fetches, "kmers_per_bucket_fetch": kmers_step / max(1, fetches),
+                         "algorithmic_bytes_rule": "bucket fetches x %d B + packed bases + N mask (SURVEY.md 8d; layout 1 = minimizer bucketing, one fetch per super-k-mer)" % bucket_bytes,
+                         "sector_per_kmer_equivalent_gbs": (kmers_step * 32 + nbases // 4 + nbases // 8) / (probe_ms / 1e3) / 1e9},
             "clocks": clocks,
             "wall_ms_per_step": wall_dev * 1e3 / args.steps,
         }
         if keys_host is not None:
-            sample = env_int("MLG_BENCH_CPU_READS", 1_000_000)
+            sample = env_int("MLG_BENCH_CPU_READS", reads_per_gpu)      # the whole workload: ~10 s on 16 cores
             sample = min(sample, reads_per_gpu)
             r = cpu_baseline_run(p, keys_host, 0, sample, repeats=1)
             line["cpu_baseline"] = {
                 "value": r["n_kmers"] / r["times"][0], "unit": "k-mers/s", "cores": r["cores"], "kind": "port",
-                "sample": "first %d reads of the same workload (%.1f s of CPU work); CPU restatement of the reference path "
+                "sample": "%d reads of the same workload (%.1f s of CPU work); CPU restatement of the reference path "
                           "(oracle/oracle.c), not KMC/CMash binaries (absent here); its database build (%.1f s) is not timed"
                           % (sample, r["times"][0], r["build_s"])}
         else:

@@ -72,6 +72,9 @@ typedef struct mlg_stats {
     double ms_query;         /* CUDA-event duration of the finish stage (compact, expand, popcount, finalize) */
     uint32_t probe_launches; /* number of probe kernel launches in ms_probe */
     uint32_t filter_words;   /* L2 prefilter: number of 32-bit words, 0 = no prefilter */
+    uint64_t n_bucket_fetches; /* level-1 buckets fetched from HBM: one per k-mer in layout 0, one per super-k-mer in layout 1 */
+    uint32_t layout;         /* 0 = bucket by hash of the whole k-mer (+ L2 prefilter), 1 = bucket by minimizer (super-k-mers) */
+    uint32_t reserved;
 } mlg_stats;
 
 const char* mlg_last_error(void);
@@ -106,7 +109,12 @@ int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode, int cou
 /* host buffers; read_off (n_reads+1 entries, in bases) or NULL with every read read_len long */
 int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint8_t* nmask_or_null,
                           const uint64_t* read_off_or_null, uint64_t n_reads, uint32_t read_len);
-/* same, buffers already on the device (16-byte aligned); they must stay valid until the next sync/finish */
+/* same, with N given as n_runs sorted, non-overlapping (start, length) pairs of uint32 in batch base coordinates
+ * instead of a bit mask (NULL / 0: the batch has no N).  N is rare in real reads, so this format moves 1/3 fewer
+ * bytes over PCIe than the mask does; the mask is rebuilt on the device.  A batch must hold < 2^32 bases. */
+int mlg_query_push_packed_nruns(mlg_query* q, const uint8_t* bases, const uint32_t* nruns_or_null, uint64_t n_runs,
+                                const uint64_t* read_off_or_null, uint64_t n_reads, uint32_t read_len);
+/* same as mlg_query_push_packed, buffers already on the device (16-byte aligned); they must stay valid until the next sync/finish */
 int mlg_query_push_packed_device(mlg_query* q, const uint8_t* d_bases, const uint8_t* d_nmask_or_null,
                                  const uint64_t* d_read_off_or_null, uint64_t n_reads, uint32_t read_len);
 /* host ASCII: read i = text[read_off[i] .. read_off[i+1]); anything outside ACGTacgt is N */

@@ -25,7 +25,8 @@ class Stats(C.Structure):
                 ("n_intersect", C.c_uint64), ("n_db_entries", C.c_uint64), ("n_db_distinct", C.c_uint64),
                 ("n_buckets", C.c_uint64), ("bucket_bytes", C.c_uint32), ("gpu_launches", C.c_uint32),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("ms_probe", C.c_double),
-                ("ms_query", C.c_double), ("probe_launches", C.c_uint32), ("filter_words", C.c_uint32)]
+                ("ms_query", C.c_double), ("probe_launches", C.c_uint32), ("filter_words", C.c_uint32),
+                ("n_bucket_fetches", C.c_uint64), ("layout", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -62,6 +63,7 @@ SIGNATURES = {
     "mlg_db_free": (C.c_int, [_vp]),
     "mlg_query_begin": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _pp]),
     "mlg_query_push_packed": (C.c_int, [_vp, _u8p, _u8p, _u64p, C.c_uint64, C.c_uint32]),
+    "mlg_query_push_packed_nruns": (C.c_int, [_vp, _u8p, _u32p, C.c_uint64, _u64p, C.c_uint64, C.c_uint32]),
     "mlg_query_push_packed_device": (C.c_int, [_vp, _u8p, _u8p, _u64p, C.c_uint64, C.c_uint32]),
     "mlg_query_push_ascii": (C.c_int, [_vp, _vp, _u64p, C.c_uint64]),
     "mlg_query_sync": (C.c_int, [_vp]),

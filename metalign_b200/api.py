@@ -148,6 +148,24 @@ class Query:
         self._keep = self._keep[-3:] + [bases, nmask, off]
         check(_lib.lib().mlg_query_push_packed(self._h, _ptr(bases), _ptr(nmask), _ptr(off), int(n_reads), int(read_len)))
 
+    def push_packed_nruns(self, bases: np.ndarray, nruns: Optional[np.ndarray], off: Optional[np.ndarray],
+                          n_reads: int, read_len: int = 0):
+        """Like push_packed, with N as sorted (start, length) uint32 runs (codec.nmask_to_runs) instead of a mask."""
+        if off is not None:
+            off = np.ascontiguousarray(off, dtype=np.uint64)
+        n_runs = 0
+        if nruns is not None:
+            nruns = np.ascontiguousarray(nruns, dtype=np.uint32).reshape(-1, 2)
+            n_runs = nruns.shape[0]
+        self._keep = self._keep[-3:] + [bases, nruns, off]
+        check(_lib.lib().mlg_query_push_packed_nruns(self._h, _ptr(bases), _ptr(nruns) if n_runs else None, n_runs,
+                                                     _ptr(off), int(n_reads), int(read_len)))
+
+    def push_packed_nruns_ptr(self, bases_ptr: int, nruns_ptr: Optional[int], n_runs: int, off_ptr: Optional[int],
+                              n_reads: int, read_len: int = 0):
+        check(_lib.lib().mlg_query_push_packed_nruns(self._h, bases_ptr, nruns_ptr, int(n_runs), off_ptr, int(n_reads),
+                                                     int(read_len)))
+
     def push_packed_ptr(self, bases_ptr: int, nmask_ptr: Optional[int], off_ptr: Optional[int], n_reads: int,
                         read_len: int = 0, device: bool = False):
         """Raw-pointer variant (pinned host tensors or device tensors from torch)."""

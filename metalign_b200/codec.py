@@ -112,6 +112,32 @@ def unpack_reads(bases: np.ndarray, nmask, off=None, nreads: int = 0, read_len: 
     return [s[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
 
 
+def nmask_to_runs(nmask: np.ndarray, nbases: int) -> np.ndarray:
+    """packed N mask -> sorted (start, length) uint32 runs, shape (m, 2): the input of mlg_query_push_packed_nruns.
+    Works on the non-zero mask bytes only (N is rare), so it is cheap on multi-gigabase streams."""
+    m = np.asarray(nmask, dtype=np.uint8)[: (nbases + 7) // 8]
+    nz = np.flatnonzero(m)
+    if nz.size == 0:
+        return np.zeros((0, 2), dtype=np.uint32)
+    bits = np.unpackbits(m[nz]).reshape(-1, 8)
+    pos = (nz[:, None] * 8 + np.arange(8)[None, :])[bits != 0]
+    pos = pos[pos < nbases]
+    if pos.size == 0:
+        return np.zeros((0, 2), dtype=np.uint32)
+    brk = np.flatnonzero(np.diff(pos) != 1)
+    starts = np.concatenate([pos[:1], pos[brk + 1]])
+    ends = np.concatenate([pos[brk], pos[-1:]]) + 1
+    return np.ascontiguousarray(np.stack([starts, ends - starts], axis=1).astype(np.uint32))
+
+
+def runs_to_nmask(runs: np.ndarray, nbases: int) -> np.ndarray:
+    """inverse of nmask_to_runs (mask padded to 16 bytes)"""
+    isn = np.zeros(nbases, dtype=np.uint8)
+    for a, l in np.asarray(runs, dtype=np.int64).reshape(-1, 2):
+        isn[a:a + l] = 1
+    return _pad16(np.packbits(isn))
+
+
 def _pad16(a: np.ndarray) -> np.ndarray:
     pad = (-a.size) % 16
     if pad or a.size == 0:

@@ -102,6 +102,7 @@ struct Staging {
     DevBuf<unsigned char> bases, nmask;
     DevBuf<unsigned long long> off;
     DevBuf<unsigned char> text;
+    DevBuf<uint32_t> nruns;
     cudaEvent_t done = nullptr;   // last kernel reading this staging set
     bool used = false;
 };
@@ -123,6 +124,7 @@ struct mlg_query {
     cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr;
     mlg_stats st{};
     bool finished = false, reduced = false;
+    unsigned long long chunk_words = CHUNK_WORDS;   // 64-base words per host->device copy chunk
     // results kept for mlg_query_intersection
     DevBuf<uint32_t> present;
     uint32_t n_present = 0;
@@ -134,12 +136,18 @@ int ensure_device(mlg_ctx* ctx) { CUDA_TRY(cudaSetDevice(ctx->device)); return M
 
 // device-side part common to every push: launch the probe over the batch's reads, in ranges; range i may
 // start once copy event i (if any) has completed
-struct ReadRange { unsigned long long r_end; cudaEvent_t ready; };
+struct ReadRange {
+    unsigned long long r_end; cudaEvent_t ready;
+    unsigned long long run0 = 0, run1 = 0;      // N runs [run0, run1) to scatter into the mask before this range is probed
+};
 
 int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsigned char* d_nmask,
               const unsigned long long* d_off, unsigned long long n_reads, uint32_t read_len, unsigned long long nbases,
               const std::vector<ReadRange>* ranges) {
     mlg_ctx* ctx = q->ctx;
+    if (!q->present.p) {                       // first push: room for every database k-mer to become present once
+        MLG_TRY(q->present.alloc((size_t)q->db->v.nd + 1));
+    }
     const unsigned long long nwords64 = (nbases + 63) / 64;       // 64-base words: 16 bytes of bases, 8 bytes of mask
     ProbeArgs a{};
     a.bases = reinterpret_cast<const unsigned long long*>(d_bases);
@@ -148,6 +156,7 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
     a.base_words = nwords64 * 2;                                  // buffers cover whole 16-byte units
     a.nmask_words = round_up(nwords64, 2);
     a.cnt8 = q->cnt8.p; a.n_kmers = q->d_nkmers.p;
+    a.ci_min = (uint32_t)q->ci_min; a.present = q->present.p; a.n_present = q->d_scalar.p;
     auto launch_range = [&](unsigned long long r0, unsigned long long r1) -> int {
         if (r1 <= r0) return MLG_OK;
         cudaEvent_t e0, e1;
@@ -164,6 +173,10 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
         unsigned long long r0 = 0;
         for (auto& rr : *ranges) {
             CUDA_TRY(cudaStreamWaitEvent(ctx->s_comp, rr.ready, 0));
+            if (rr.run1 > rr.run0) {
+                MLG_TRY(launch_scatter_nruns(s.nruns.p + 2 * rr.run0, rr.run1 - rr.run0, nbases, s.nmask.p, ctx->s_comp));
+                q->st.gpu_launches += 1;
+            }
             MLG_TRY(launch_range(r0, rr.r_end));
             if (rr.r_end > r0) r0 = rr.r_end;
         }
@@ -351,12 +364,17 @@ MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode,
     q->ctx = ctx; q->db = db; q->ci_min = ci_min; q->gate = gate_mode; q->count_empty = count_empty_in_den ? 1 : 0;
     size_t cbytes = round_up((size_t)db->v.nd + 4, 16);
     MLG_TRY(q->cnt8.alloc(cbytes));
-    MLG_TRY(q->d_nkmers.alloc(1)); MLG_TRY(q->d_scalar.alloc(2));
+    MLG_TRY(q->d_nkmers.alloc(2)); MLG_TRY(q->d_scalar.alloc(2));
     CUDA_TRY(cudaMemsetAsync(q->cnt8.p, 0, cbytes, ctx->s_comp));
-    CUDA_TRY(cudaMemsetAsync(q->d_nkmers.p, 0, 8, ctx->s_comp));
+    CUDA_TRY(cudaMemsetAsync(q->d_nkmers.p, 0, 16, ctx->s_comp));
+    CUDA_TRY(cudaMemsetAsync(q->d_scalar.p, 0, 16, ctx->s_comp));
     CUDA_TRY(cudaEventCreate(&q->ev_q0)); CUDA_TRY(cudaEventCreate(&q->ev_q1));
+    if (const char* e = getenv("MLG_CHUNK_MB")) {     // experiment knob: MiB of packed bases per copy chunk
+        double mb = atof(e);
+        if (mb >= 0.25 && mb <= 4096) q->chunk_words = std::max<unsigned long long>(1024, (unsigned long long)(mb * 65536.0));
+    }
     q->st.n_db_entries = db->v.np; q->st.n_db_distinct = db->v.nd;
-    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4; q->st.filter_words = db->v.nfw;
+    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4; q->st.filter_words = db->v.nfw; q->st.layout = db->v.layout;
     guard.q = nullptr;
     *out = q;
     return MLG_OK;
@@ -381,22 +399,30 @@ MLG_API int mlg_query_push_packed_device(mlg_query* q, const uint8_t* d_bases, c
     return MLG_OK;
 }
 
-MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint8_t* nmask, const uint64_t* off, uint64_t n_reads,
-                          uint32_t read_len) {
+// host packed stream; N given either as a bit mask (nmask) or as sorted (start, length) runs (nruns), or not at all
+static int push_packed_host(mlg_query* q, const uint8_t* bases, const uint8_t* nmask, const uint32_t* nruns, uint64_t n_runs,
+                            const uint64_t* off, uint64_t n_reads, uint32_t read_len) {
     MLG_TRY(check_push(q));
     if (!n_reads) return MLG_OK;
     if (!bases) { mlg_set_error("null bases"); return MLG_ERR_ARG; }
     unsigned long long nbases = 0;
     MLG_TRY(batch_bases_host(off, n_reads, read_len, &nbases));
     if (!nbases) return MLG_OK;
+    if (n_runs && !nruns) { mlg_set_error("null nruns"); return MLG_ERR_ARG; }
+    if (n_runs && nbases > 0xFFFFFFFFull) { mlg_set_error("a batch pushed with N runs must hold < 2^32 bases"); return MLG_ERR_ARG; }
     mlg_ctx* ctx = q->ctx;
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));          // host buffers of the previous push are free from here on
     Staging& s = q->stg[q->cur];
     if (s.used) CUDA_TRY(cudaEventSynchronize(s.done));   // previous batch that used this set has been consumed
     const unsigned long long nwords = (nbases + 63) / 64;
     const unsigned long long cap_words = round_up(nwords + 2, 2);   // 64-base words
+    const bool have_mask = nmask || n_runs;
     MLG_TRY(s.bases.ensure(cap_words * 16));
-    if (nmask) MLG_TRY(s.nmask.ensure(cap_words * 8));
+    if (have_mask) MLG_TRY(s.nmask.ensure(cap_words * 8));
+    if (n_runs) {
+        MLG_TRY(s.nruns.ensure(2 * n_runs));
+        CUDA_TRY(cudaMemsetAsync(s.nmask.p, 0, cap_words * 8, ctx->s_comp));
+    }
     if (off) {
         MLG_TRY(s.off.ensure(n_reads + 1));
         CUDA_TRY(cudaMemcpyAsync(s.off.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
@@ -408,9 +434,11 @@ MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint
     }
     // chunked copies: the reads that are complete after chunk c are probed while chunk c+1 is still in flight
     const unsigned long long bases_bytes = (nbases + 3) / 4, nmask_bytes = (nbases + 7) / 8;
+    const unsigned long long chunk_words = q->chunk_words;
     std::vector<ReadRange> ready;
-    for (unsigned long long w0 = 0; w0 < nwords; w0 += CHUNK_WORDS) {
-        const unsigned long long w1 = std::min(nwords, w0 + CHUNK_WORDS);
+    unsigned long long run0 = 0;
+    for (unsigned long long w0 = 0; w0 < nwords; w0 += chunk_words) {
+        const unsigned long long w1 = std::min(nwords, w0 + chunk_words);
         const unsigned long long b0 = w0 * 16, b1 = std::min(bases_bytes, w1 * 16);
         CUDA_TRY(cudaMemcpyAsync(s.bases.p + b0, bases + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_copy));
         q->st.h2d_bytes += b1 - b0;
@@ -418,6 +446,21 @@ MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint
             const unsigned long long m0 = w0 * 8, m1 = std::min(nmask_bytes, w1 * 8);
             CUDA_TRY(cudaMemcpyAsync(s.nmask.p + m0, nmask + m0, m1 - m0, cudaMemcpyHostToDevice, ctx->s_copy));
             q->st.h2d_bytes += m1 - m0;
+        }
+        // N runs that START inside this chunk travel with it (a run may extend past the chunk: harmless, the mask
+        // of the whole batch was cleared up front and later reads are probed later)
+        unsigned long long run1 = run0;
+        if (n_runs) {
+            if (w1 == nwords) run1 = n_runs;
+            else {
+                unsigned long long lo = run0, hi = n_runs; const unsigned long long lim = w1 * 64;
+                while (lo < hi) { unsigned long long mid = (lo + hi) / 2; if (nruns[2 * mid] < lim) lo = mid + 1; else hi = mid; }
+                run1 = lo;
+            }
+            if (run1 > run0) {
+                CUDA_TRY(cudaMemcpyAsync(s.nruns.p + 2 * run0, nruns + 2 * run0, (run1 - run0) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+                q->st.h2d_bytes += (run1 - run0) * 8;
+            }
         }
         cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(e, ctx->s_copy));
@@ -427,11 +470,21 @@ MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint
         if (w1 == nwords) r_end = n_reads;
         else if (off) r_end = (unsigned long long)(std::upper_bound(off, off + n_reads + 1, (uint64_t)(w1 * 64)) - off) - 1;
         else r_end = (w1 * 64) / read_len;
-        ready.push_back({r_end, e});
+        ReadRange rr; rr.r_end = r_end; rr.ready = e; rr.run0 = run0; rr.run1 = run1;
+        ready.push_back(rr);
+        run0 = run1;
     }
-    MLG_TRY(run_probe(q, s, s.bases.p, nmask ? s.nmask.p : nullptr, off ? s.off.p : nullptr, n_reads, read_len, nbases, &ready));
+    MLG_TRY(run_probe(q, s, s.bases.p, have_mask ? s.nmask.p : nullptr, off ? s.off.p : nullptr, n_reads, read_len, nbases, &ready));
     q->cur ^= 1;
     return MLG_OK;
+}
+MLG_API int mlg_query_push_packed(mlg_query* q, const uint8_t* bases, const uint8_t* nmask, const uint64_t* off, uint64_t n_reads,
+                          uint32_t read_len) {
+    return push_packed_host(q, bases, nmask, nullptr, 0, off, n_reads, read_len);
+}
+MLG_API int mlg_query_push_packed_nruns(mlg_query* q, const uint8_t* bases, const uint32_t* nruns, uint64_t n_runs,
+                                        const uint64_t* off, uint64_t n_reads, uint32_t read_len) {
+    return push_packed_host(q, bases, nullptr, nruns, n_runs, off, n_reads, read_len);
 }
 
 MLG_API int mlg_query_push_ascii(mlg_query* q, const char* text, const uint64_t* off, uint64_t n_reads) {
@@ -494,38 +547,40 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     MLG_TRY(ensure_device(ctx));
     cudaStream_t st = ctx->s_comp;
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
+    if (!q->present.p) MLG_TRY(q->present.alloc((size_t)v.nd + 1));     // nothing was pushed
     CUDA_TRY(cudaEventRecord(q->ev_q0, st));
-    // I = database k-mers seen >= ci_min times
-    MLG_TRY(launch_count_present(q->cnt8.p, v.nd, (uint32_t)q->ci_min, q->d_scalar.p, st));
-    unsigned long long ni = 0;
-    CUDA_TRY(cudaMemcpyAsync(&ni, q->d_scalar.p, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    q->n_present = (uint32_t)ni;
-    MLG_TRY(q->present.alloc(ni));
-    MLG_TRY(launch_compact_present(q->cnt8.p, v.nd, (uint32_t)q->ci_min, q->present.p, q->d_scalar.p + 1, st));
-    // hit bitmap: nk planes of G*n bits
+    // I = database k-mers seen >= ci_min times.  Single GPU: the probe kernel appended each one when its counter
+    // reached ci_min.  After a cross-rank reduction the list is rebuilt from the summed counters.
+    if (q->reduced) {
+        MLG_TRY(launch_compact_present(q->cnt8.p, v.nd, (uint32_t)q->ci_min, q->present.p, q->d_scalar.p, st));
+        q->st.gpu_launches += 1;
+    }
+    // hit bitmap: nk planes of G*n bits; the kernel that sets a bit first also counts it
     const unsigned long long total = (unsigned long long)v.G * v.n;
     const unsigned long long words_per_k = (total + 31) / 32;
     DevBuf<uint32_t> hitbits; MLG_TRY(hitbits.alloc(words_per_k * v.nk));
     CUDA_TRY(cudaMemsetAsync(hitbits.p, 0, words_per_k * v.nk * 4, st));
-    MLG_TRY(launch_expand_hits(v, q->present.p, q->n_present, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, st));
     const size_t cells = (size_t)v.G * v.nk;
     DevBuf<unsigned long long> d_num; MLG_TRY(d_num.alloc(cells));
     DevBuf<long long> o_num, o_den; DevBuf<double> o_ci;
     MLG_TRY(o_num.alloc(cells)); MLG_TRY(o_den.alloc(cells)); MLG_TRY(o_ci.alloc(cells));
     CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
-    MLG_TRY(launch_popcount_table(hitbits.p, words_per_k, v.G, v.n, v.nk, d_num.p, st));
+    MLG_TRY(launch_expand_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p, st));
     MLG_TRY(launch_finalize(d_num.p, db->den_real.p, db->has_empty.p, v.G, v.nk, q->count_empty, o_num.p, o_den.p, o_ci.p, st));
-    q->st.gpu_launches += 4 + (q->n_present ? 1 : 0);
+    q->st.gpu_launches += 2;
     CUDA_TRY(cudaEventRecord(q->ev_q1, st));
     if (num) { CUDA_TRY(cudaMemcpyAsync(num, o_num.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
     if (den) { CUDA_TRY(cudaMemcpyAsync(den, o_den.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
     if (ci) { CUDA_TRY(cudaMemcpyAsync(ci, o_ci.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
-    unsigned long long nk_host = 0;
-    CUDA_TRY(cudaMemcpyAsync(&nk_host, q->d_nkmers.p, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long nk_host2[2] = {0, 0}, ni = 0;
+    unsigned long long& nk_host = nk_host2[0];
+    CUDA_TRY(cudaMemcpyAsync(nk_host2, q->d_nkmers.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&ni, q->d_scalar.p, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    q->n_present = (uint32_t)ni;
     q->st.n_kmers = nk_host; q->st.n_intersect = ni;
+    q->st.n_bucket_fetches = v.layout == 1 ? nk_host2[1] : nk_host;
     q->st.d2h_bytes += 16;
     // timings
     float ms = 0; double probe_ms = 0;

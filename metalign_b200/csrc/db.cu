@@ -100,9 +100,9 @@ __global__ void k_flag_heads(const key128* a, uint32_t n, unsigned char* flag) {
     if (i >= n) return;
     flag[i] = (i == 0 || !key_eq(a[i], a[i - 1])) ? 1 : 0;
 }
-__global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, unsigned long long* h) {
+__global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, uint32_t layout, unsigned long long* h) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) h[i] = key_hash(a[i], K);
+    if (i < n) h[i] = layout == 1 ? key_hash_sk(a[i], K) : key_hash(a[i], K);
 }
 __global__ void k_gather_key(const key128* src, const uint32_t* idx, uint32_t n, key128* dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,6 +232,10 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
     struct Guard { mlg_db* d; ~Guard() { if (d) delete d; } } guard{db};
     DbView& v = db->v;
     v.G = G; v.n = n; v.K = K; v.nk = nk;
+    // Metalign's K = 60 gets the super-k-mer layout (bucket by minimizer); other K keep the whole-k-mer hash layout.
+    // MLG_LAYOUT=0 forces the latter (A/B measurements).
+    v.layout = (K == 60) ? 1u : 0u;
+    if (const char* s = getenv("MLG_LAYOUT")) { int x = atoi(s); if (x == 0) v.layout = 0; }
     for (uint32_t i = 0; i < MLG_MAX_KS; ++i) v.ks[i] = i < nk ? ks[i] : 0;
 
     // 1. non-empty slots
@@ -329,7 +333,7 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         // order by hash
         DevBuf<unsigned long long> h; DevBuf<uint32_t> iota, perm;
         MLG_TRY(h.alloc(nd)); MLG_TRY(hsorted.alloc(nd)); MLG_TRY(iota.alloc(nd)); MLG_TRY(perm.alloc(nd));
-        k_hash_keys<<<nblk(nd), TPB, 0, st>>>(duniq.p, nd, K, h.p);
+        k_hash_keys<<<nblk(nd), TPB, 0, st>>>(duniq.p, nd, K, v.layout, h.p);
         k_iota<<<nblk(nd), TPB, 0, st>>>(iota.p, nd);
         MLG_TRY(sort_pairs_u64(h.p, hsorted.p, iota.p, perm.p, nd, 0, 64, st));
         MLG_TRY(db->D_key.alloc(nd));
@@ -343,6 +347,11 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         uint32_t slots_per_bucket = 8;
         if (const char* s = getenv("MLG_BUCKET_SLOTS")) { int x = atoi(s); if (x == 4 || x == 8) slots_per_bucket = (uint32_t)x; }
         double load = slots_per_bucket * 0.3125;  // upper bound on the mean entries per bucket (2.5 of 8 slots)
+        if (v.layout == 1) {
+            // k-mers that share a minimizer share a bucket, so bucket occupancy is clumpier than a plain hash's:
+            // at mean load 2.4, 1.6 % of the buckets overflow 8 slots; at <= 1.25, 0.2 %
+            slots_per_bucket = 8; load = 1.25;
+        }
         if (const char* s = getenv("MLG_BUCKET_LOAD")) { double x = atof(s); if (x > 0.01 && x <= slots_per_bucket) load = x; }
         uint32_t bbits = 1;                       // at least two buckets: the probe kernel shifts by 32 - bbits
         while (bbits < 31 && (double)(1ull << bbits) * load < (double)nd) ++bbits;
@@ -362,7 +371,7 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         double max_mb = 64.0;
         if (const char* s = getenv("MLG_FILTER_MB")) max_mb = atof(s);
         unsigned long long nfw = 0;                       // 32-bit words
-        if (nd && max_mb > 0) {
+        if (nd && max_mb > 0 && v.layout == 0) {
             unsigned long long want = ((unsigned long long)nd * 16ull + 31ull) / 32ull;
             unsigned long long cap = (unsigned long long)(max_mb * 1048576.0 / 4.0);
             nfw = want < cap ? want : cap;

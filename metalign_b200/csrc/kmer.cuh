@@ -116,3 +116,57 @@ MLG_HD unsigned hash_fp(unsigned long long h) {
     unsigned f = (unsigned)h & 0x7FFFFFFFu;
     return f ? f : 1u;
 }
+
+// ---- super-k-mer layout (K >= MLG_MIN_M) -----------------------------------------------------------
+// Consecutive K-mers of a read share most of their bases.  In this layout the level-1 bucket of a K-mer is
+// chosen by its MINIMIZER -- the smallest mixed value among its K-M+1 canonical M-mers (M = 16, so an M-mer is one
+// 32-bit word) -- instead of by a hash of the whole K-mer.  A run of consecutive windows with the same
+// minimizer (a "super-k-mer", ~23 windows on average at K = 60) probes ONE 32-byte bucket, fetched once; inside
+// the bucket a K-mer is still recognised by a 31-bit fingerprint of its strand-symmetric digest.  The
+// minimizer is strand-symmetric (canonical M-mers), so a K-mer and its reverse complement agree on the bucket.
+#define MLG_MIN_M 16u
+#define MLG_MIN_MULT 0x9E3779B1u      /* odd: x -> x*MULT + ADD is a bijection of 32-bit words (pseudo-random order,   */
+#define MLG_MIN_ADD 0x7F4A7C15u       /* and poly-A (x = 0) is not the smallest value)                                */
+#define MLG_BKT_MULT 0x85EBCA6Bu      /* odd: spreads the (small) window minima over the bucket index space           */
+
+// reverse the order of the 16 two-bit groups of a 32-bit word
+MLG_HD unsigned rev2_32h(unsigned x) {
+#ifdef __CUDA_ARCH__
+    x = __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+    x = (x >> 16) | (x << 16);
+#endif
+    return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+// mixed value of the canonical form of a 16-mer given both strands
+MLG_HD unsigned mmer_mix(unsigned f, unsigned r) { return (f < r ? f : r) * MLG_MIN_MULT + MLG_MIN_ADD; }
+// minimizer value of a K-mer (bottom-aligned key), K >= 16
+MLG_HD unsigned key_minimizer(const key128& x, unsigned K) {
+    unsigned best = 0xFFFFFFFFu;
+    for (unsigned p = 0; p + MLG_MIN_M <= K; ++p) {
+        const unsigned f = (unsigned)key_shr(x, 2 * (K - MLG_MIN_M - p)).lo;
+        const unsigned h = mmer_mix(f, rev2_32h(~f));
+        best = h < best ? h : best;
+    }
+    return best;
+}
+MLG_HD unsigned minimizer_bucket_hash(unsigned wmin) { return wmin * MLG_BKT_MULT; }
+// 32-bit hash of the strand-symmetric digest (only the fingerprint comes from it in this layout)
+MLG_HD unsigned hash_digest32(unsigned s3, unsigned s2, unsigned s1, unsigned s0) {
+    unsigned x = (s0 * 0x9E3779B1u) ^ (s1 * 0x85EBCA77u) ^ (s2 * 0xC2B2AE3Du) ^ (s3 * 0x27D4EB2Fu);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    return x;
+}
+// 64-bit sort / bucket / fingerprint hash of a K-mer in the super-k-mer layout: top 32 bits place the bucket
+// (hash_bucket takes the top bbits <= 32 bits), the low 31 bits are the fingerprint (hash_fp)
+MLG_HD unsigned long long key_hash_sk(const key128& x, unsigned K) {
+    const key128 f = key_shl(x, 128 - 2 * K), r = key_shl(key_rc(x, K), 128 - 2 * K);
+    const unsigned d = hash_digest32((unsigned)(f.hi >> 32) + (unsigned)(r.hi >> 32), (unsigned)f.hi + (unsigned)r.hi,
+                                     (unsigned)(f.lo >> 32) + (unsigned)(r.lo >> 32), (unsigned)f.lo + (unsigned)r.lo);
+    return ((unsigned long long)minimizer_bucket_hash(key_minimizer(x, K)) << 32) | d;
+}

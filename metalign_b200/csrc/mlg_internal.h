@@ -86,6 +86,8 @@ struct DbView {
     const uint32_t* F;
     uint32_t nfw;
     uint32_t fk;                 // bits per key in the prefilter (1 or 2)
+    // 0: bucket = hash of the whole k-mer (+ L2 prefilter); 1: bucket = minimizer of the k-mer (super-k-mer layout, K = 60)
+    uint32_t layout;
 };
 
 struct mlg_db {
@@ -113,7 +115,10 @@ struct ProbeArgs {
     unsigned long long nmask_words;     // readable 8-byte words of `nmask`
     unsigned long long r_begin, r_end;  // reads of this launch
     unsigned char* cnt8;                // nd saturating occurrence counters
-    unsigned long long* n_kmers;        // device accumulator of valid windows
+    uint32_t ci_min;                    // a counter reaching ci_min appends its index to present[]
+    uint32_t* present;                  // nd entries
+    unsigned long long* n_present;      // device cursor of present[]
+    unsigned long long* n_kmers;        // device accumulators: [0] valid windows, [1] level-1 bucket fetches (layout 1)
 };
 int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaStream_t st);
 int launch_pack_ascii(const unsigned char* text, unsigned long long nbases, unsigned char* bases, unsigned char* nmask,
@@ -121,13 +126,12 @@ int launch_pack_ascii(const unsigned char* text, unsigned long long nbases, unsi
 int launch_ascii_to_keys(const unsigned char* text, unsigned long long nslots, uint32_t K, key128* keys, cudaStream_t st);
 
 int launch_clamp_counts(unsigned char* cnt8, uint32_t nd, uint32_t ci_min, cudaStream_t st);
-int launch_count_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, unsigned long long* d_count, cudaStream_t st);
 int launch_compact_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* d_cursor,
                            cudaStream_t st);
-int launch_expand_hits(const DbView& db, const uint32_t* present, uint32_t n_present, int gate_none, uint32_t* hitbits,
-                       unsigned long long words_per_k, cudaStream_t st);
-int launch_popcount_table(const uint32_t* hitbits, unsigned long long words_per_k, uint32_t G, uint32_t n, uint32_t nk,
-                          unsigned long long* num, cudaStream_t st);
+int launch_expand_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,
+                       uint32_t* hitbits, unsigned long long words_per_k, unsigned long long* num, cudaStream_t st);
+int launch_scatter_nruns(const uint32_t* d_runs, unsigned long long n_runs, unsigned long long nbases, unsigned char* nmask,
+                         cudaStream_t st);
 int launch_finalize(const unsigned long long* num, const long long* den_real, const unsigned char* has_empty, uint32_t G,
                     uint32_t nk, int count_empty, long long* out_num, long long* out_den, double* out_ci, cudaStream_t st);
 int launch_gather_keys(const key128* D_key, const uint32_t* present, uint32_t n_present, key128* out, cudaStream_t st);

@@ -116,25 +116,36 @@ __device__ __forceinline__ bool bucket_candidate(const BucketVec<SLOTS>& v, uint
     return hit;
 }
 
+// where the exact path records an occurrence: the counter table, and the list of database k-mers whose
+// counter has just reached ci_min (the intersection I, appended exactly once per k-mer)
+struct CountSink {
+    unsigned char* cnt8;
+    uint32_t* present;
+    unsigned long long* n_present;
+    uint32_t ci_min;
+};
 // saturating (255) increment of byte counter i via 32-bit CAS
-__device__ __forceinline__ void bump_counter(unsigned char* cnt8, uint32_t i) {
-    uint32_t* wp = reinterpret_cast<uint32_t*>(cnt8) + (i >> 2);
+__device__ __forceinline__ void bump_counter(const CountSink& cs, uint32_t i) {
+    uint32_t* wp = reinterpret_cast<uint32_t*>(cs.cnt8) + (i >> 2);
     const uint32_t sh = (i & 3u) * 8u;
     uint32_t old = *reinterpret_cast<volatile uint32_t*>(wp);
     while (((old >> sh) & 0xFFu) < 0xFFu) {
         uint32_t assumed = old;
         old = atomicCAS(wp, assumed, assumed + (1u << sh));
-        if (old == assumed) break;
+        if (old == assumed) {
+            if (((assumed >> sh) & 0xFFu) + 1u == cs.ci_min) cs.present[atomicAdd(cs.n_present, 1ull)] = i;
+            break;
+        }
     }
 }
 // exact path: compare the full key against the bucket's run of D, bump the counter on a match
-__device__ __forceinline__ void probe_exact(const DbView& db, unsigned char* cnt8, unsigned long long khi, unsigned long long klo) {
+__device__ __forceinline__ void probe_exact(const DbView& db, const CountSink& cs, unsigned long long khi, unsigned long long klo) {
     key128 c; c.hi = khi; c.lo = klo;
     const unsigned long long bucket = hash_bucket(key_hash(c, db.K), db.bbits);
     uint32_t s = db.bstart[bucket], e = db.bstart[bucket + 1];
     for (uint32_t i = s; i < e; ++i) {
         key128 d = db.D_key[i];
-        if (d.hi == khi && d.lo == klo) { bump_counter(cnt8, i); return; }
+        if (d.hi == khi && d.lo == klo) { bump_counter(cs, i); return; }
     }
 }
 
@@ -146,7 +157,7 @@ struct WarpQueue {
     unsigned long long lo[WARPS][QCAP];
     unsigned n[WARPS];
 };
-__device__ __noinline__ void queue_drain(WarpQueue& q, unsigned warp, unsigned lane, const DbView& db, unsigned char* cnt8) {
+__device__ __noinline__ void queue_drain(WarpQueue& q, unsigned warp, unsigned lane, const DbView& db, const CountSink& cnt8) {
     __syncwarp();
     const unsigned n = q.n[warp];
     for (unsigned i = lane; i < n; i += 32) probe_exact(db, cnt8, q.hi[warp][i], q.lo[warp][i]);
@@ -156,7 +167,7 @@ __device__ __noinline__ void queue_drain(WarpQueue& q, unsigned warp, unsigned l
 }
 // all 32 lanes call this with the ballot of candidate lanes (non-zero); candidate lanes append their key
 __device__ __forceinline__ void queue_push(WarpQueue& q, unsigned warp, unsigned lane, unsigned ballot, bool cand,
-                                           unsigned long long khi, unsigned long long klo, const DbView& db, unsigned char* cnt8) {
+                                           unsigned long long khi, unsigned long long klo, const DbView& db, const CountSink& cnt8) {
     const unsigned base = q.n[warp];
     if (cand) {
         const unsigned i = base + __popc(ballot & ((1u << lane) - 1u));
@@ -191,6 +202,7 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_decode_canon_probe(ProbeArg
     const unsigned long long ntiles = (nreads + RT - 1) / RT;
     const unsigned bshift = 32u - db.bbits;      // 1 <= bbits <= 31
     const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    const CountSink sink{a.cnt8, a.present, a.n_present, a.ci_min};
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -415,7 +427,7 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_decode_canon_probe(ProbeArg
                                     G.hi = ((unsigned long long)(fsl(rcl[5], rcl[6], 2 * (15 - tt)) & km[3]) << 32) | (fsl(rcl[6], rcl[7], 2 * (15 - tt)) & km[2]);
                                     G.lo = ((unsigned long long)(fsl(rcl[7], rcl[8], 2 * (15 - tt)) & km[1]) << 32) | (fsl(rcl[8], rcl[9], 2 * (15 - tt)) & km[0]);
                                     const key128 cn = key_shr(key_lt(G, F) ? G : F, 128 - 2 * K);
-                                    queue_push(wq, warp, lane, ballot, cand[j], cn.hi, cn.lo, db, a.cnt8);
+                                    queue_push(wq, warp, lane, ballot, cand[j], cn.hi, cn.lo, db, sink);
                                 }
                             }
                         }
@@ -431,12 +443,399 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_decode_canon_probe(ProbeArg
         __syncthreads();                       // every lane is done with this stage's shared memory
         if (tid == 0 && t + 2ull * gridDim.x < ntiles) issue(stage, t + 2ull * gridDim.x);
     }
-    queue_drain(wq, warp, lane, db, a.cnt8);
+    queue_drain(wq, warp, lane, db, sink);
 
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xFFFFFFFFu, my_valid, o);
     if (lane == 0 && my_valid) atomicAdd(&s_total, my_valid);
     __syncthreads();
     if (tid == 0 && s_total) atomicAdd(a.n_kmers, s_total);
+}
+
+// ======================================================================================================
+// K1, super-k-mer layout (db.layout == 1, K == 60): same lane-per-read walk, but the level-1 bucket of a window
+// is chosen by its MINIMIZER (kmer.cuh) rather than by a hash of the whole k-mer.  Consecutive windows share
+// their minimizer for ~23 windows on average, so a lane fetches ~5 buckets per 150-base read instead of 91 and
+// the kernel stops being bound by random DRAM sectors.  Per block of 16 windows:
+//   phase A  sliding-window minimum of the 45 canonical 16-mers under each window, without divergence:
+//            min(window) = min(suffix of 16-mer block b, whole blocks b+1 [, b+2], prefix of block b+2 / b+3)
+//            (van Herk / Gil-Werman on blocks of 16 positions; 16-mer values are recomputed rather than kept:
+//            2 funnel shifts + min + multiply-add each).  Where the minimum differs from the bucket the lane
+//            holds, the new bucket is fetched global -> shared with cp.async (up to SK_MAXCH per block);
+//   phase B  per window: strand-symmetric digest -> 31-bit fingerprint, compared with the 8 slots of the
+//            bucket held in registers (reloaded from shared memory where phase A marked a change).
+// Candidates (fingerprint match, overflowed bucket, or a window whose bucket did not get a fetch slot) go
+// through the same per-warp queue and exact compare as in the other layout.
+constexpr unsigned SK_K = 60, SK_W = SK_K - MLG_MIN_M + 1;   // 45 minimizer positions per window
+constexpr unsigned SK_MAXCH = 4;
+constexpr uint32_t SK_UNKNOWN = 0xFFFFFFFFu;
+static_assert(SK_W == 45, "the block decomposition below is written for 45 positions");
+
+struct SkSlots {
+    uint4 d[SK_MAXCH][2][RT];        // [slot][half][thread]: 16-byte accesses of a warp are contiguous
+    uint32_t id[SK_MAXCH][RT];       // bucket index of the slot
+};
+struct WarpQueueSk {
+    unsigned long long hi[WARPS][QCAP];
+    unsigned long long lo[WARPS][QCAP];
+    uint32_t b[WARPS][QCAP];
+    unsigned n[WARPS];
+};
+__device__ __forceinline__ void probe_exact_sk(const DbView& db, const CountSink& cs, unsigned long long khi, unsigned long long klo,
+                                               uint32_t bucket) {
+    key128 c; c.hi = khi; c.lo = klo;
+    if (bucket == SK_UNKNOWN) bucket = (uint32_t)hash_bucket(key_hash_sk(c, db.K), db.bbits);
+    uint32_t s = db.bstart[bucket], e = db.bstart[bucket + 1];
+    for (uint32_t i = s; i < e; ++i) {
+        key128 d = db.D_key[i];
+        if (d.hi == khi && d.lo == klo) { bump_counter(cs, i); return; }
+    }
+}
+__device__ __noinline__ void queue_drain_sk(WarpQueueSk& q, unsigned warp, unsigned lane, const DbView& db, const CountSink& cs) {
+    __syncwarp();
+    const unsigned n = q.n[warp];
+    for (unsigned i = lane; i < n; i += 32) probe_exact_sk(db, cs, q.hi[warp][i], q.lo[warp][i], q.b[warp][i]);
+    __syncwarp();
+    if (lane == 0) q.n[warp] = 0;
+    __syncwarp();
+}
+__device__ __forceinline__ void queue_push_sk(WarpQueueSk& q, unsigned warp, unsigned lane, unsigned ballot, bool cand,
+                                              unsigned long long khi, unsigned long long klo, uint32_t bucket, const DbView& db,
+                                              const CountSink& cs) {
+    const unsigned base = q.n[warp];
+    if (cand) {
+        const unsigned i = base + __popc(ballot & ((1u << lane) - 1u));
+        q.hi[warp][i] = khi; q.lo[warp][i] = klo; q.b[warp][i] = bucket;
+    }
+    __syncwarp();
+    const unsigned total = base + __popc(ballot);
+    if (lane == 0) q.n[warp] = total;
+    __syncwarp();
+    if (total >= 32) queue_drain_sk(q, warp, lane, db, cs);
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// mixed value of the canonical 16-mer at position 16*j + i of the current block (0 <= j <= 3): its forward strand is
+// bases [16j+i, 16j+i+16) of loc[], its reverse complement starts at base 139 - (16j+i) of rcl[] (the complement of
+// base x of the block sits at base 154 - x of rcl[], see the alignment of rcl[] in the kernel)
+__device__ __forceinline__ uint32_t sk_mmer(const uint32_t (&loc)[SEGW], const uint32_t (&rcl)[SEGW], int j, int i) {
+    const uint32_t f = fsl(loc[j], loc[j + 1], 2 * i);
+    const int a = i <= 11 ? 8 - j : 7 - j, o = i <= 11 ? 11 - i : 27 - i;
+    const uint32_t r = fsl(rcl[a], rcl[a + 1], 2 * o);
+    return mmer_mix(f, r);
+}
+
+template <bool HAS_NMASK>
+__global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a, DbView db) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SharedStage& stg = *reinterpret_cast<SharedStage*>(smem_raw);
+    SkSlots& slots = *reinterpret_cast<SkSlots*>(smem_raw + sizeof(SharedStage));
+    WarpQueueSk& wq = *reinterpret_cast<WarpQueueSk*>(smem_raw + sizeof(SharedStage) + sizeof(SkSlots));
+    __shared__ __align__(8) unsigned long long mbar[2];
+    __shared__ unsigned long long s_total;
+    __shared__ unsigned long long s_bw0[2], s_mw0[2];
+    __shared__ unsigned s_staged[2];
+
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    constexpr unsigned K = SK_K;
+    const unsigned long long nreads = a.r_end - a.r_begin;
+    const unsigned long long ntiles = (nreads + RT - 1) / RT;
+    const unsigned bshift = 32u - db.bbits;      // 1 <= bbits <= 31
+    const unsigned long long pol_stream = policy_evict_first();
+    const CountSink sink{a.cnt8, a.present, a.n_present, a.ci_min};
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_total = 0;
+    }
+    if (lane == 0) wq.n[warp] = 0;
+    __syncthreads();
+
+    auto issue = [&](unsigned stage, unsigned long long t) {
+        const unsigned long long r0 = a.r_begin + t * RT;
+        const unsigned long long r1 = (r0 + RT < a.r_end) ? r0 + RT : a.r_end;
+        const unsigned long long p0 = a.off ? a.off[r0] : r0 * (unsigned long long)a.read_len;
+        const unsigned long long p1 = a.off ? a.off[r1] : r1 * (unsigned long long)a.read_len;
+        unsigned long long bw0 = (p0 >> 5) & ~1ull;
+        unsigned long long bw1 = ((p1 + 31) >> 5) + 6;
+        if (bw1 > a.base_words) bw1 = a.base_words;
+        bw1 = (bw1 + 1) & ~1ull;
+        unsigned long long mw0 = (p0 >> 6) & ~1ull;
+        unsigned long long mw1 = ((p1 + 63) >> 6) + 4;
+        if (HAS_NMASK) { if (mw1 > a.nmask_words) mw1 = a.nmask_words; mw1 = (mw1 + 1) & ~1ull; }
+        const unsigned long long bytes_b = (bw1 - bw0) * 8ull, bytes_m = HAS_NMASK ? (mw1 - mw0) * 8ull : 0ull;
+        const bool fits = bw1 > bw0 && bytes_b <= STAGE_B && bytes_m <= STAGE_M;
+        s_bw0[stage] = bw0; s_mw0[stage] = mw0; s_staged[stage] = fits ? 1u : 0u;
+        if (fits) {
+            mbar_expect_tx(&mbar[stage], (uint32_t)(bytes_b + bytes_m));
+            bulk_g2s(&stg.b[stage][0], a.bases + bw0, (uint32_t)bytes_b, &mbar[stage], pol_stream);
+            if (HAS_NMASK && bytes_m) bulk_g2s(&stg.m[stage][0], a.nmask + mw0, (uint32_t)bytes_m, &mbar[stage], pol_stream);
+        } else {
+            mbar_arrive(&mbar[stage]);
+        }
+    };
+
+    constexpr uint32_t KM0 = 0xFFFFFFFFu << (128 - 2 * K);     // K = 60: the low word of a top-aligned k-mer keeps 24 bits
+    unsigned long long my_valid = 0;
+    unsigned my_fetch = 0;
+    // the bucket this lane holds (registers), the minimizer value it belongs to, and its index
+    uint32_t cur[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cur[k] = 0;
+    uint32_t cur_wm = 0, cur_bucket = 0;
+    bool have = false;
+
+    unsigned it = 0;
+    for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const unsigned stage = it & 1u, parity = (it >> 1) & 1u;
+        if (it == 0 && tid == 0) {
+            issue(0, t);
+            if (t + gridDim.x < ntiles) issue(1, t + gridDim.x);
+        }
+        __syncthreads();
+        mbar_wait(&mbar[stage], parity);
+
+        const unsigned long long r = a.r_begin + t * RT + tid;
+        const bool active = r < a.r_end;
+        unsigned long long R0 = 0, R1 = 0;
+        if (active) {
+            R0 = a.off ? a.off[r] : r * (unsigned long long)a.read_len;
+            R1 = a.off ? a.off[r + 1] : R0 + a.read_len;
+        }
+        const unsigned long long len = R1 - R0;
+        const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
+        const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
+        const unsigned max_seg = __reduce_max_sync(0xFFFFFFFFu, nseg);
+        const bool staged = s_staged[stage] != 0;
+        const unsigned long long* bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[stage][0]) - s_bw0[stage] : a.bases;
+        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[stage][0]) - s_mw0[stage] : a.nmask;
+
+        for (unsigned seg = 0; seg < max_seg; ++seg) {
+            const unsigned c = seg < nseg ? (unsigned)((nw - (unsigned long long)seg * WMAX) < WMAX ? (nw - (unsigned long long)seg * WMAX) : WMAX) : 0u;
+            const unsigned long long s = R0 + (unsigned long long)seg * WMAX;
+
+            uint32_t loc[SEGW];
+            uint32_t nl[5];
+#pragma unroll
+            for (int k = 0; k < (int)SEGW; ++k) loc[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) nl[k] = 0;
+            if (c) {
+                const unsigned long long q = s >> 5;
+                const unsigned sh = 2u * (unsigned)(s & 31ull);
+                unsigned long long W[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    unsigned long long idx = q + k;
+                    if (idx >= a.base_words) idx = a.base_words - 1;
+                    W[k] = bswap64(bsrc[idx]);
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const unsigned long long v = sh ? ((W[k] << sh) | (W[k + 1] >> (64 - sh))) : W[k];
+                    loc[2 * k] = (uint32_t)(v >> 32); loc[2 * k + 1] = (uint32_t)v;
+                }
+                if (HAS_NMASK) {
+                    const unsigned long long qn = s >> 6;
+                    const unsigned shn = (unsigned)(s & 63ull);
+                    unsigned long long M[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned long long idx = qn + k;
+                        if (idx >= a.nmask_words) idx = a.nmask_words - 1;
+                        M[k] = bswap64(msrc[idx]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const unsigned long long v = shn ? ((M[k] << shn) | (M[k + 1] >> (64 - shn))) : M[k];
+                        if (2 * k < 5) nl[2 * k] = (uint32_t)(v >> 32);
+                        if (2 * k + 1 < 5) nl[2 * k + 1] = (uint32_t)v;
+                    }
+                }
+            }
+            uint32_t v0, v1, v2;
+            {
+                if (HAS_NMASK && __any_sync(0xFFFFFFFFu, (nl[0] | nl[1] | nl[2] | nl[3] | nl[4]) != 0u)) {
+                    unsigned cover = 1;
+                    while (cover * 2 <= K) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], cover);
+                        nl[4] |= nl[4] << cover;
+                        cover *= 2;
+                    }
+                    const unsigned rest = K - cover;
+                    if (rest) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], rest);
+                        nl[4] |= nl[4] << rest;
+                    }
+                }
+                const uint32_t c0 = c >= 32 ? 0xFFFFFFFFu : (c ? ~(0xFFFFFFFFu >> c) : 0u);
+                const uint32_t c1 = c >= 64 ? 0xFFFFFFFFu : (c > 32 ? ~(0xFFFFFFFFu >> (c - 32)) : 0u);
+                const uint32_t c2 = c >= 96 ? 0xFFFFFFFFu : (c > 64 ? ~(0xFFFFFFFFu >> (c - 64)) : 0u);
+                v0 = ~nl[0] & c0; v1 = ~nl[1] & c1; v2 = ~nl[2] & c2;
+            }
+            my_valid += __popc(v0) + __popc(v1) + __popc(v2);
+            if (__all_sync(0xFFFFFFFFu, (v0 | v1 | v2) == 0u)) continue;
+
+            // reverse complement of the segment: the complement of base x sits at base 154 - x of rcl[]
+            uint32_t rcl[SEGW];
+            {
+                uint32_t t160[SEGW + 1];
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) t160[k] = rev2_32(~loc[SEGW - 1 - k]);
+                t160[SEGW] = 0;
+                constexpr unsigned bs = 2u * (160u - (WMAX + K - 1u));       // 10 bits dropped at the front
+                static_assert(bs < 32, "alignment shift must stay inside one word");
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) rcl[k] = fsl(t160[k], t160[k + 1], bs);
+            }
+
+            // minimizer state carried from block to block: A1 = min of 16-mer block b+1, P = prefix of block b+2 up to index 11
+            uint32_t A1 = 0xFFFFFFFFu, P = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) A1 = min(A1, sk_mmer(loc, rcl, 1, i));
+#pragma unroll
+            for (int i = 0; i < 12; ++i) P = min(P, sk_mmer(loc, rcl, 2, i));
+
+#pragma unroll 1
+            for (int blk = 0; blk < (int)(WMAX / 16); ++blk) {
+                if (__all_sync(0xFFFFFFFFu, (v0 | v1 | v2) == 0u)) break;       // nothing valid from here to the end of the segment
+                const uint32_t vb = v0 & 0xFFFF0000u;
+                v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
+
+                // ---- phase A: window minima, change points, bucket fetches
+                uint32_t chg = 0, ovf = 0;
+                {
+                    uint32_t Suf[16];
+                    {
+                        uint32_t sm = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = 15; i >= 0; --i) { sm = min(sm, sk_mmer(loc, rcl, 0, i)); Suf[i] = sm; }
+                    }
+                    unsigned ns = 0;
+                    bool ovfmode = false;
+                    uint32_t base12 = A1, A2 = 0;
+#pragma unroll
+                    for (int tt = 0; tt < 16; ++tt) {
+                        uint32_t wm;
+                        if (tt < 4) {
+                            P = min(P, sk_mmer(loc, rcl, 2, 12 + tt));
+                            wm = min(min(Suf[tt], A1), P);
+                            if (tt == 3) { A2 = P; base12 = min(A1, A2); P = 0xFFFFFFFFu; }
+                        } else {
+                            P = min(P, sk_mmer(loc, rcl, 3, tt - 4));
+                            wm = min(min(Suf[tt], base12), P);
+                        }
+                        const bool valid = (vb >> (31 - tt)) & 1u;
+                        const bool need = valid && (!have || wm != cur_wm);
+                        if (need) {
+                            if (ns < SK_MAXCH) {
+                                const uint32_t bucket = (wm * MLG_BKT_MULT) >> bshift;
+                                const uint32_t* src = db.T1 + (unsigned long long)bucket * 8ull;
+                                cp_async16(&slots.d[ns][0][tid], src);
+                                cp_async16(&slots.d[ns][1][tid], src + 4);
+                                slots.id[ns][tid] = bucket;
+                                ++ns; cur_wm = wm; have = true; chg |= 1u << tt;
+                            } else {
+                                ovfmode = true;
+                            }
+                        }
+                        if (ovfmode && valid) ovf |= 1u << tt;
+                    }
+                    A1 = A2;
+                    my_fetch += ns;
+                }
+                cp_async_wait_all();
+
+                // ---- phase B: fingerprints against the held bucket
+                if (!__all_sync(0xFFFFFFFFu, vb == 0u)) {
+                    unsigned sp = 0;
+                    constexpr int GROUP = 4;
+#pragma unroll
+                    for (int g0 = 0; g0 < 16; g0 += GROUP) {
+                        bool cand[GROUP];
+                        uint32_t cb[GROUP];
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < GROUP; ++j) {
+                            const int tt = g0 + j;
+                            if ((chg >> tt) & 1u) {
+                                const uint4 x = slots.d[sp][0][tid], y = slots.d[sp][1][tid];
+                                cur[0] = x.x; cur[1] = x.y; cur[2] = x.z; cur[3] = x.w;
+                                cur[4] = y.x; cur[5] = y.y; cur[6] = y.z; cur[7] = y.w;
+                                cur_bucket = slots.id[sp][tid];
+                                ++sp;
+                            }
+                            const uint32_t f3 = fsl(loc[0], loc[1], 2 * tt);
+                            const uint32_t f2 = fsl(loc[1], loc[2], 2 * tt);
+                            const uint32_t f1 = fsl(loc[2], loc[3], 2 * tt);
+                            const uint32_t f0 = fsl(loc[3], loc[4], 2 * tt) & KM0;
+                            const uint32_t g3 = fsl(rcl[5], rcl[6], 2 * (15 - tt));
+                            const uint32_t g2 = fsl(rcl[6], rcl[7], 2 * (15 - tt));
+                            const uint32_t g1 = fsl(rcl[7], rcl[8], 2 * (15 - tt));
+                            const uint32_t gz = fsl(rcl[8], rcl[9], 2 * (15 - tt)) & KM0;
+                            const uint32_t d = hash_digest32(f3 + g3, f2 + g2, f1 + g1, f0 + gz);
+                            const uint32_t fp = (d & 0x7FFFFFFFu) ? (d & 0x7FFFFFFFu) : 1u;
+                            bool hit = ((cur[0] & 0x7FFFFFFFu) == fp) | ((int)cur[0] < 0);
+#pragma unroll
+                            for (int sl = 1; sl < 8; ++sl) hit |= (cur[sl] == fp);
+                            const bool isovf = (ovf >> tt) & 1u;
+                            cand[j] = ((vb >> (31 - tt)) & 1u) && (hit | isovf);
+                            cb[j] = isovf ? SK_UNKNOWN : cur_bucket;
+                            any |= cand[j];
+                        }
+                        if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+                            for (int j = 0; j < GROUP; ++j) {
+                                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, cand[j]);
+                                if (ballot) {
+                                    const int tt = g0 + j;
+                                    key128 F, G;
+                                    F.hi = ((unsigned long long)fsl(loc[0], loc[1], 2 * tt) << 32) | fsl(loc[1], loc[2], 2 * tt);
+                                    F.lo = ((unsigned long long)fsl(loc[2], loc[3], 2 * tt) << 32) | (fsl(loc[3], loc[4], 2 * tt) & KM0);
+                                    G.hi = ((unsigned long long)fsl(rcl[5], rcl[6], 2 * (15 - tt)) << 32) | fsl(rcl[6], rcl[7], 2 * (15 - tt));
+                                    G.lo = ((unsigned long long)fsl(rcl[7], rcl[8], 2 * (15 - tt)) << 32) | (fsl(rcl[8], rcl[9], 2 * (15 - tt)) & KM0);
+                                    const key128 cn = key_shr(key_lt(G, F) ? G : F, 128 - 2 * K);
+                                    queue_push_sk(wq, warp, lane, ballot, cand[j], cn.hi, cn.lo, cb[j], db, sink);
+                                }
+                            }
+                        }
+                    }
+                }
+                // slide the register windows by one word
+#pragma unroll
+                for (int k = 0; k < (int)SEGW - 1; ++k) loc[k] = loc[k + 1];
+#pragma unroll
+                for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + 2ull * gridDim.x < ntiles) issue(stage, t + 2ull * gridDim.x);
+    }
+    queue_drain_sk(wq, warp, lane, db, sink);
+
+    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xFFFFFFFFu, my_valid, o);
+    my_fetch = __reduce_add_sync(0xFFFFFFFFu, my_fetch);
+    if (lane == 0 && my_valid) atomicAdd(&s_total, my_valid);
+    if (lane == 0 && my_fetch) atomicAdd(a.n_kmers + 1, (unsigned long long)my_fetch);
+    __syncthreads();
+    if (tid == 0 && s_total) atomicAdd(a.n_kmers, s_total);
+}
+constexpr size_t K1SK_SMEM = sizeof(SharedStage) + sizeof(SkSlots) + sizeof(WarpQueueSk);
+
+template <bool HAS_NMASK>
+int launch_probe_sk(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
+    auto kern = k1_superkmer_probe<HAS_NMASK>;
+    static bool once = false;
+    if (!once) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1SK_SMEM)); once = true; }
+    kern<<<grid, RT, K1SK_SMEM, st>>>(a, db);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
 }
 
 // ---------------------------------------------------------------- prep kernels
@@ -518,6 +917,10 @@ int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaS
     }
     unsigned long long want = (unsigned long long)ctx->sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(ntiles < want ? ntiles : want);
+    if (db.layout == 1) {
+        if (db.K != SK_K || db.slots != 8) { mlg_set_error("super-k-mer layout needs K=60 and 8-slot buckets"); return MLG_ERR_STATE; }
+        return a.nmask ? launch_probe_sk<true>(db, a, st, grid) : launch_probe_sk<false>(db, a, st, grid);
+    }
     return db.slots == 8 ? launch_probe_s<8>(db, a, st, grid) : launch_probe_s<4>(db, a, st, grid);
 }
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_stats_struct_matches_header():
     from metalign_b200._lib import Stats
-    assert C.sizeof(Stats) == 8 * 7 + 4 * 2 + 8 * 2 + 8 * 2 + 4 * 2
+    assert C.sizeof(Stats) == 8 * 7 + 4 * 2 + 8 * 2 + 8 * 2 + 4 * 2 + 8 + 4 * 2
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")

@@ -87,7 +87,7 @@ def test_synthetic_packed_host_fixed_len(workload):
         q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
         res = q.finish()
         _check(res, q.intersection(), *w["refs"][gate], tag=gate)
-        assert res["stats"]["gpu_launches"] >= 5 and res["stats"]["ms_probe"] > 0
+        assert res["stats"]["gpu_launches"] >= 3 and res["stats"]["ms_probe"] > 0
         q.close()
 
 
@@ -206,6 +206,7 @@ def test_mlgdb_roundtrip(ctx, workload, tmp_path):
 def test_sixteen_byte_buckets(ctx, workload, monkeypatch):
     w = workload
     monkeypatch.setenv("MLG_BUCKET_SLOTS", "4")
+    monkeypatch.setenv("MLG_LAYOUT", "0")          # 16-byte buckets exist in the whole-k-mer hash layout only
     monkeypatch.setenv("MLG_BUCKET_LOAD", "3.0")   # forces many overflowing buckets through the exact path
     db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
     q = db.query()
@@ -303,11 +304,12 @@ def test_prefilter_variants(ctx, workload, monkeypatch, filter_mb):
     """no prefilter, a starved prefilter (~2 bits per key, most probes pass) and the default one"""
     w = workload
     monkeypatch.setenv("MLG_FILTER_MB", filter_mb)
+    monkeypatch.setenv("MLG_LAYOUT", "0")       # the prefilter belongs to the whole-k-mer-hash layout
     db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
     q = db.query()
     q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
     res = q.finish()
-    assert (res["stats"]["filter_words"] == 0) == (filter_mb == "0")
+    assert (res["stats"]["filter_words"] == 0) == (filter_mb == "0") and res["stats"]["layout"] == 0
     _check(res, q.intersection(), *w["refs"]["exact"])
     q.close()
     db.close()
@@ -329,4 +331,136 @@ def test_deep_coverage_many_hits(ctx):
     _check(res, q.intersection(), ref, I_ref)
     assert res["n_intersect"] >= 300
     q.close()
+    db.close()
+
+
+def test_nruns_push_equals_mask_push(ctx, workload):
+    """N given as (start, length) runs (mlg_query_push_packed_nruns) == N given as a bit mask, in several
+    batches and with offsets; a batch without any N takes the mask-free kernel."""
+    w = workload
+    p, nreads = w["p"], w["nreads"]
+    nb = nreads * p.read_len
+    runs = codec.nmask_to_runs(w["nmask"], nb)
+    assert runs.shape[0] > 10 and np.array_equal(codec.runs_to_nmask(runs, nb)[: (nb + 7) // 8], w["nmask"][: (nb + 7) // 8])
+    q = w["db"].query()
+    q.push_packed_nruns(w["bases"], runs, None, nreads, p.read_len)
+    res = q.finish()
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+    # small copy chunks: runs are sliced per chunk, some straddle chunk boundaries
+    import os
+    os.environ["MLG_CHUNK_MB"] = "0.25"
+    try:
+        q = w["db"].query()
+        off = np.arange(nreads + 1, dtype=np.uint64) * np.uint64(p.read_len)
+        q.push_packed_nruns(w["bases"], runs, off, nreads, 0)
+        res = q.finish()
+        _check(res, q.intersection(), *w["refs"]["exact"])
+        q.close()
+    finally:
+        del os.environ["MLG_CHUNK_MB"]
+
+
+def test_nruns_long_runs_and_no_n(ctx):
+    """runs longer than a read, runs touching batch start / end, and nruns=None"""
+    rng = random.Random(77)
+    K = 60
+    genome = "".join(rng.choice("ACGT") for _ in range(3000))
+    sketches = [[genome[i:i + K] for i in range(0, 2400, 100)]]
+    reads = []
+    for i in range(400):
+        a = rng.randint(0, len(genome) - 200)
+        r = list(genome[a:a + 200])
+        if i % 3 == 0:
+            s = rng.randint(0, 199); l = rng.randint(1, 260)
+            for j in range(s, min(200, s + l)):
+                r[j] = "N"
+        reads.append("".join(r))
+    reads[0] = "N" * 200
+    reads[-1] = reads[-1][:150] + "N" * 50
+    keys = codec.sketches_to_keys(sketches, K)
+    ref, I_ref = oracle_c_run(keys, 1, len(sketches[0]), K, KS, lambda q: q.push_reads(reads + reads))
+    bases, nmask, off = codec.pack_reads(reads)
+    runs = codec.nmask_to_runs(nmask, int(off[-1]))
+    assert runs[:, 1].max() > 150
+    db = Database.from_keys(ctx, keys, 1, len(sketches[0]), K, KS)
+    q = db.query()
+    q.push_packed_nruns(bases, runs, off, len(reads))
+    q.push_packed(bases, nmask, off, len(reads))
+    res = q.finish()
+    _check(res, q.intersection(), ref, I_ref)
+    q.close()
+    clean = [r.replace("N", "A") for r in reads]
+    ref2, I2 = oracle_c_run(keys, 1, len(sketches[0]), K, KS, lambda q: q.push_reads(clean))
+    b2, m2, off2 = codec.pack_reads(clean)
+    q = db.query(1)
+    ref2, I2 = oracle_c_run(keys, 1, len(sketches[0]), K, KS, lambda q: q.push_reads(clean), 1)
+    q.push_packed_nruns(b2, None, off2, len(clean))
+    res = q.finish()
+    _check(res, q.intersection(), ref2, I2)
+    q.close()
+    db.close()
+
+
+def test_both_layouts_k60(ctx, workload, monkeypatch):
+    """K = 60 defaults to the super-k-mer layout (bucket by minimizer, ~5 bucket fetches per 150-base read);
+    MLG_LAYOUT=0 keeps the whole-k-mer hash layout.  Same results, and the fetch counts tell them apart."""
+    w = workload
+    q = w["db"].query()
+    q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+    res = q.finish()
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    st = res["stats"]
+    q.close()
+    assert st["layout"] == 1 and st["filter_words"] == 0
+    assert 0.03 * st["n_kmers"] < st["n_bucket_fetches"] < 0.09 * st["n_kmers"]
+    monkeypatch.setenv("MLG_LAYOUT", "0")
+    db0 = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
+    for gate in ("exact", "none"):
+        q = db0.query(2, gate, True)
+        q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+        res = q.finish()
+        _check(res, q.intersection(), *w["refs"][gate])
+        assert res["stats"]["layout"] == 0 and res["stats"]["n_bucket_fetches"] == res["stats"]["n_kmers"]
+        q.close()
+    db0.close()
+
+
+def test_superkmer_adversarial_minimizers(ctx):
+    """reads built to stress the super-k-mer path: low-complexity sequence (every window shares one minimizer),
+    tandem repeats (the minimizer recurs), strictly decreasing minimizers are approximated by random sequence with
+    many N (segments restart), reads of 60..400 bases (several 96-window segments per lane), and a database whose
+    sketch k-mers overlap heavily (many keys per minimizer -> overflowing buckets -> exact path)."""
+    rng = random.Random(2024)
+    K = 60
+    genome = "".join(rng.choice("ACGT") for _ in range(4000))
+    lowc = ("A" * 70 + "ACACACACAC" * 8 + "T" * 70 + genome[:300]) * 2
+    sketches = [[genome[i:i + K] for i in range(0, 600)],                         # 600 overlapping k-mers: shared minimizers
+                [lowc[i:i + K] for i in range(0, 600)],
+                [oracle_py.rc(genome[i:i + K]) for i in range(1000, 1600)]]
+    reads = []
+    for src in (genome, lowc):
+        for _ in range(300):
+            L = rng.choice([60, 61, 75, 150, 155, 156, 157, 251, 400])
+            a = rng.randint(0, len(src) - L)
+            r = src[a:a + L]
+            if rng.random() < 0.5:
+                r = oracle_py.rc(r)
+            r = list(r)
+            if rng.random() < 0.3:
+                for _ in range(rng.randint(1, 4)):
+                    r[rng.randint(0, L - 1)] = "N"
+            reads.append("".join(r))
+    reads += ["A" * 200, "ACGT" * 60, "T" * 59, "", "N" * 100, genome[:60]]
+    keys = codec.sketches_to_keys(sketches, K)
+    db = Database.from_keys(ctx, keys, 3, 600, K, KS)
+    for ci_min, gate in ((1, "exact"), (2, "none"), (3, "exact")):
+        ref, I_ref = oracle_c_run(keys, 3, 600, K, KS, lambda q: q.push_reads(reads), ci_min, gate, True)
+        q = db.query(ci_min, gate, True)
+        q.push_reads(reads)
+        res = q.finish()
+        _check(res, q.intersection(), ref, I_ref, (ci_min, gate))
+        assert res["stats"]["layout"] == 1
+        q.close()
+    assert ref["n_intersect"] > 500
     db.close()

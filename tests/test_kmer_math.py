@@ -37,6 +37,14 @@ def kh(tmp_path_factory):
     L.t_fmask.restype = C.c_uint
     L.t_fp.argtypes = [u64]
     L.t_fp.restype = C.c_uint
+    L.t_minimizer.argtypes = [u64, u64, C.c_uint]
+    L.t_minimizer.restype = C.c_uint
+    L.t_hash_sk.argtypes = [u64, u64, C.c_uint]
+    L.t_hash_sk.restype = u64
+    L.t_mmer_mix.argtypes = [C.c_uint, C.c_uint]
+    L.t_mmer_mix.restype = C.c_uint
+    L.t_rev2_32.argtypes = [C.c_uint]
+    L.t_rev2_32.restype = C.c_uint
     return L
 
 
@@ -88,3 +96,39 @@ def test_hash_bucket_monotone_and_fp_nonzero(kh):
         K = rng.randint(8, 63)
         s = "".join(rng.choice("ACGT") for _ in range(K))
         assert kh.t_hash(*codec.kmer_to_key(s), K) == kh.t_hash(*codec.kmer_to_key(oracle_py.rc(s)), K)
+
+
+def _kmer_int(s):
+    v = 0
+    for ch in s:
+        v = (v << 2) | "ACGT".index(ch)
+    return v
+
+
+def test_minimizer_is_strand_symmetric_and_matches_strings(kh):
+    """super-k-mer layout: the minimizer of a K-mer is the smallest mixed value over its canonical 16-mers, the
+    same for both strands; overlapping K-mers that share it agree on the top 32 bits of key_hash_sk (the bucket)."""
+    rng = random.Random(5)
+    for K in (60, 31, 16, 45):
+        for _ in range(200):
+            s = "".join(rng.choice("ACGT") for _ in range(K))
+            r = oracle_py.rc(s)
+            want = min(kh.t_mmer_mix(_kmer_int(s[p:p + 16]), _kmer_int(oracle_py.rc(s[p:p + 16]))) for p in range(K - 15))
+            hi, lo = codec.kmer_to_key(s)
+            rhi, rlo = codec.kmer_to_key(r)
+            assert kh.t_minimizer(hi, lo, K) == want == kh.t_minimizer(rhi, rlo, K)
+            assert kh.t_hash_sk(hi, lo, K) == kh.t_hash_sk(rhi, rlo, K)
+    # canonical 16-mer mix: both argument orders agree, and rev2_32 reverses base order
+    for _ in range(200):
+        m = "".join(rng.choice("ACGT") for _ in range(16))
+        f, r = _kmer_int(m), _kmer_int(oracle_py.rc(m))
+        assert kh.t_mmer_mix(f, r) == kh.t_mmer_mix(r, f)
+        assert kh.t_rev2_32(~f & 0xFFFFFFFF) == r
+    # a long sequence: consecutive windows share minimizers in runs (super-k-mers), ~2/(w+1) changes per window
+    seq = "".join(rng.choice("ACGT") for _ in range(5000))
+    mins = []
+    for i in range(len(seq) - 59):
+        hi, lo = codec.kmer_to_key(seq[i:i + 60])
+        mins.append(kh.t_minimizer(hi, lo, 60))
+    changes = sum(1 for a, b in zip(mins, mins[1:]) if a != b)
+    assert 0.02 < changes / len(mins) < 0.07
