@@ -100,9 +100,9 @@ __global__ void k_flag_heads(const key128* a, uint32_t n, unsigned char* flag) {
     if (i >= n) return;
     flag[i] = (i == 0 || !key_eq(a[i], a[i - 1])) ? 1 : 0;
 }
-__global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, uint32_t layout, unsigned long long* h) {
+__global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, uint32_t layout, uint32_t bbits, unsigned long long* h) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) h[i] = layout == 1 ? key_hash_sk(a[i], K) : key_hash(a[i], K);
+    if (i < n) h[i] = layout == 1 ? key_hash_sk(a[i], K, bbits) : key_hash(a[i], K);
 }
 __global__ void k_gather_key(const key128* src, const uint32_t* idx, uint32_t n, key128* dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +208,23 @@ int sort_keys128(unsigned long long* hi, unsigned long long* lo, const uint32_t*
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
+}
+
+// level-1 table geometry from the number of distinct keys: slots per bucket and number of buckets (a power of two)
+void choose_buckets(DbView& v, uint32_t nd) {
+    uint32_t slots_per_bucket = 8;
+    if (const char* s = getenv("MLG_BUCKET_SLOTS")) { int x = atoi(s); if (x == 4 || x == 8) slots_per_bucket = (uint32_t)x; }
+    double load = slots_per_bucket * 0.3125;  // upper bound on the mean entries per bucket (2.5 of 8 slots)
+    if (const char* s = getenv("MLG_BUCKET_LOAD")) { double x = atof(s); if (x > 0.01 && x <= slots_per_bucket) load = x; }
+    uint32_t bbits = 1;                       // at least two buckets: the probe kernel shifts by 32 - bbits
+    if (v.layout == 1) {
+        // k-mers that share a minimizer share a bucket PAIR (kmer.cuh), so occupancy is clumpier than a plain hash's;
+        // mean load <= 1.25 per 8-slot half keeps the overflowing halves rare
+        slots_per_bucket = 8; load = 1.25; bbits = 2;
+        if (const char* s = getenv("MLG_SK_LOAD")) { double x = atof(s); if (x > 0.01 && x <= 8) load = x; }
+    }
+    while (bbits < 31 && (double)(1ull << bbits) * load < (double)nd) ++bbits;
+    v.nbuckets = 1ull << bbits; v.bbits = bbits; v.slots = slots_per_bucket;
 }
 
 }  // namespace
@@ -333,7 +350,8 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         // order by hash
         DevBuf<unsigned long long> h; DevBuf<uint32_t> iota, perm;
         MLG_TRY(h.alloc(nd)); MLG_TRY(hsorted.alloc(nd)); MLG_TRY(iota.alloc(nd)); MLG_TRY(perm.alloc(nd));
-        k_hash_keys<<<nblk(nd), TPB, 0, st>>>(duniq.p, nd, K, v.layout, h.p);
+        choose_buckets(v, nd);
+        k_hash_keys<<<nblk(nd), TPB, 0, st>>>(duniq.p, nd, K, v.layout, v.bbits, h.p);
         k_iota<<<nblk(nd), TPB, 0, st>>>(iota.p, nd);
         MLG_TRY(sort_pairs_u64(h.p, hsorted.p, iota.p, perm.p, nd, 0, 64, st));
         MLG_TRY(db->D_key.alloc(nd));
@@ -344,20 +362,9 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
     }
     v.nd = nd; v.D_key = db->D_key.p;
     {
-        uint32_t slots_per_bucket = 8;
-        if (const char* s = getenv("MLG_BUCKET_SLOTS")) { int x = atoi(s); if (x == 4 || x == 8) slots_per_bucket = (uint32_t)x; }
-        double load = slots_per_bucket * 0.3125;  // upper bound on the mean entries per bucket (2.5 of 8 slots)
-        if (v.layout == 1) {
-            // k-mers that share a minimizer share a bucket, so bucket occupancy is clumpier than a plain hash's:
-            // at mean load 2.4, 1.6 % of the buckets overflow 8 slots; at <= 1.25, 0.2 %
-            slots_per_bucket = 8; load = 1.25;
-        }
-        if (const char* s = getenv("MLG_BUCKET_LOAD")) { double x = atof(s); if (x > 0.01 && x <= slots_per_bucket) load = x; }
-        uint32_t bbits = 1;                       // at least two buckets: the probe kernel shifts by 32 - bbits
-        while (bbits < 31 && (double)(1ull << bbits) * load < (double)nd) ++bbits;
-        if ((double)(1ull << bbits) * load < (double)nd) { mlg_set_error("too many buckets"); return MLG_ERR_ARG; }
-        unsigned long long nb = 1ull << bbits;
-        v.nbuckets = nb; v.bbits = bbits; v.slots = slots_per_bucket;
+        if (!nd) choose_buckets(v, nd);
+        const uint32_t slots_per_bucket = v.slots, bbits = v.bbits;
+        const unsigned long long nb = v.nbuckets;
         MLG_TRY(db->bstart.alloc(nb + 1));
         CUDA_TRY(cudaMemsetAsync(db->bstart.p, 0, (nb + 1) * 4, st));
         if (nd) k_hbucket_hist<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p);

@@ -155,18 +155,31 @@ MLG_HD unsigned key_minimizer(const key128& x, unsigned K) {
     return best;
 }
 MLG_HD unsigned minimizer_bucket_hash(unsigned wmin) { return wmin * MLG_BKT_MULT; }
-// 32-bit hash of the strand-symmetric digest (only the fingerprint comes from it in this layout)
-MLG_HD unsigned hash_digest32(unsigned s3, unsigned s2, unsigned s1, unsigned s0) {
-    unsigned x = (s0 * 0x9E3779B1u) ^ (s1 * 0x85EBCA77u) ^ (s2 * 0xC2B2AE3Du) ^ (s3 * 0x27D4EB2Fu);
-    x ^= x >> 16; x *= 0x7FEB352Du;
+// Fingerprint of a K-mer in this layout: a mix of the values of its FIRST and LAST canonical M-mers (the probe
+// kernel has both at hand from the minimizer scan).  Swapping strands swaps the two, and the sum does not care.
+// It tells a window from its shifted neighbours -- all a fingerprint has to do; the exact path compares full keys.
+MLG_HD unsigned sk_fp(unsigned h_first, unsigned h_last) {
+    unsigned x = (h_first + h_last) * 0x7FEB352Du;
     x ^= x >> 15;
-    return x;
+    return (x & 0x7FFFFFFFu) | 1u;       // 31 bits, never 0 (0 = empty slot; bit 31 of a bucket's first word = overflow flag)
 }
-// 64-bit sort / bucket / fingerprint hash of a K-mer in the super-k-mer layout: top 32 bits place the bucket
-// (hash_bucket takes the top bbits <= 32 bits), the low 31 bits are the fingerprint (hash_fp)
-MLG_HD unsigned long long key_hash_sk(const key128& x, unsigned K) {
-    const key128 f = key_shl(x, 128 - 2 * K), r = key_shl(key_rc(x, K), 128 - 2 * K);
-    const unsigned d = hash_digest32((unsigned)(f.hi >> 32) + (unsigned)(r.hi >> 32), (unsigned)f.hi + (unsigned)r.hi,
-                                     (unsigned)(f.lo >> 32) + (unsigned)(r.lo >> 32), (unsigned)f.lo + (unsigned)r.lo);
-    return ((unsigned long long)minimizer_bucket_hash(key_minimizer(x, K)) << 32) | d;
+// Level-1 buckets come in PAIRS in this layout: the minimizer picks the pair (one 64-byte fetch per super-k-mer),
+// bit 30 of the K-mer's own fingerprint picks the half it lives in.  K-mers that share a minimizer -- by descent
+// or, with 16-base minimizers and >1e8 keys, by chance -- are thereby spread over 16 slots instead of 8.
+MLG_HD unsigned sk_pair_index(unsigned wmin, unsigned bbits) { return minimizer_bucket_hash(wmin) >> (33u - bbits); }   // 2 <= bbits <= 31
+MLG_HD unsigned sk_half(unsigned fp) { return (fp >> 30) & 1u; }
+// 64-bit sort / bucket / fingerprint hash of a K-mer in the super-k-mer layout: the top bbits bits are the bucket
+// (2 * pair + half; hash_bucket reads them), the low 31 bits are the fingerprint (hash_fp)
+MLG_HD unsigned long long key_hash_sk(const key128& x, unsigned K, unsigned bbits) {
+    unsigned best = 0xFFFFFFFFu, h_first = 0, h_last = 0;
+    for (unsigned p = 0; p + MLG_MIN_M <= K; ++p) {
+        const unsigned f = (unsigned)key_shr(x, 2 * (K - MLG_MIN_M - p)).lo;
+        const unsigned h = mmer_mix(f, rev2_32h(~f));
+        best = h < best ? h : best;
+        if (p == 0) h_first = h;
+        h_last = h;
+    }
+    const unsigned fp = sk_fp(h_first, h_last);
+    const unsigned long long bucket = 2ull * sk_pair_index(best, bbits) + sk_half(fp);
+    return (bucket << (64u - bbits)) | fp;
 }

@@ -452,39 +452,52 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_decode_canon_probe(ProbeArg
 }
 
 // ======================================================================================================
-// K1, super-k-mer layout (db.layout == 1, K == 60): same lane-per-read walk, but the level-1 bucket of a window
-// is chosen by its MINIMIZER (kmer.cuh) rather than by a hash of the whole k-mer.  Consecutive windows share
-// their minimizer for ~23 windows on average, so a lane fetches ~5 buckets per 150-base read instead of 91 and
-// the kernel stops being bound by random DRAM sectors.  Per block of 16 windows:
-//   phase A  sliding-window minimum of the 45 canonical 16-mers under each window, without divergence:
+// K1, super-k-mer layout (db.layout == 1, K == 60): same lane-per-read walk, but the level-1 bucket PAIR of a
+// window is chosen by its MINIMIZER (kmer.cuh) rather than by a hash of the whole k-mer.  Consecutive windows share
+// their minimizer for ~18 windows on average, so a lane fetches ~5 bucket pairs (64 bytes each) per 150-base read
+// instead of 91 buckets, and the kernel stops being bound by random DRAM sectors.  Every warp is its own pipeline:
+// it owns two staging buffers (TMA bulk copies of the packed bases / N mask of its next 32 reads,
+// mbarrier-signalled) and never meets the other warps of the CTA at a barrier.  Per block of 16 windows, all of
+// it branch-free:
+//   phase A  sliding-window minimum of the 45 canonical 16-mers under each window:
 //            min(window) = min(suffix of 16-mer block b, whole blocks b+1 [, b+2], prefix of block b+2 / b+3)
 //            (van Herk / Gil-Werman on blocks of 16 positions; 16-mer values are recomputed rather than kept:
-//            2 funnel shifts + min + multiply-add each).  Where the minimum differs from the bucket the lane
-//            holds, the new bucket is fetched global -> shared with cp.async (up to SK_MAXCH per block);
-//   phase B  per window: strand-symmetric digest -> 31-bit fingerprint, compared with the 8 slots of the
-//            bucket held in registers (reloaded from shared memory where phase A marked a change).
-// Candidates (fingerprint match, overflowed bucket, or a window whose bucket did not get a fetch slot) go
-// through the same per-warp queue and exact compare as in the other layout.
+//            2 funnel shifts + min + multiply-add each).  The window's fingerprint is a mix of its first and last
+//            16-mer values, both of which this scan produces anyway.  Where the minimum differs from the one
+//            whose pair the lane holds, the new pair is fetched global -> shared by predicated cp.async
+//            (up to SK_MAXCH per block; slot 0 is the pair carried in from the previous block);
+//   phase B  per window: the half of the held pair that bit 30 of the fingerprint selects is read from shared
+//            memory (2 x LDS.128) and its 8 slots are compared with the fingerprint.
+// Candidates (fingerprint match, overflowed half, or -- rarely -- a window whose pair found no fetch slot) are
+// rebuilt as canonical keys in a rolled loop and go through a per-warp queue to the exact compare.
 constexpr unsigned SK_K = 60, SK_W = SK_K - MLG_MIN_M + 1;   // 45 minimizer positions per window
-constexpr unsigned SK_MAXCH = 4;
+constexpr unsigned SK_MAXCH = 3;                             // new pairs fetched asynchronously per block of 16 windows
+constexpr unsigned SK_NSLOT = SK_MAXCH + 1;                  // + the carried one
 constexpr uint32_t SK_UNKNOWN = 0xFFFFFFFFu;
 static_assert(SK_W == 45, "the block decomposition below is written for 45 positions");
+constexpr unsigned WSTAGE_B = 1280 + 64;                     // per-warp staging: 32 reads x 160 bases fit; longer reads are gathered from global
+constexpr unsigned WSTAGE_M = 640 + 64;
 
-struct SkSlots {
-    uint4 d[SK_MAXCH][2][RT];        // [slot][half][thread]: 16-byte accesses of a warp are contiguous
-    uint32_t id[SK_MAXCH][RT];       // bucket index of the slot
+struct SkStage {
+    __align__(16) unsigned char b[WARPS][2][WSTAGE_B];
+    __align__(16) unsigned char m[WARPS][2][WSTAGE_M];
 };
+struct SkSlots {
+    uint4 d[SK_NSLOT][4][RT];        // [slot][quarter][thread]: a 64-byte pair per lane; 16-byte accesses of a warp are contiguous
+    uint32_t id[SK_NSLOT][RT];       // pair index of the slot
+};
+constexpr uint32_t SK_SLOT_STRIDE = 4 * RT * 16, SK_Q_STRIDE = RT * 16, SK_ID_STRIDE = RT * 4;
 struct WarpQueueSk {
     unsigned long long hi[WARPS][QCAP];
     unsigned long long lo[WARPS][QCAP];
     uint32_t b[WARPS][QCAP];
     unsigned n[WARPS];
 };
+// exact compare against the keys of BOTH halves of the pair (their runs of D are adjacent)
 __device__ __forceinline__ void probe_exact_sk(const DbView& db, const CountSink& cs, unsigned long long khi, unsigned long long klo,
-                                               uint32_t bucket) {
-    key128 c; c.hi = khi; c.lo = klo;
-    if (bucket == SK_UNKNOWN) bucket = (uint32_t)hash_bucket(key_hash_sk(c, db.K), db.bbits);
-    uint32_t s = db.bstart[bucket], e = db.bstart[bucket + 1];
+                                               uint32_t pair) {
+    if (pair == SK_UNKNOWN) { key128 c; c.hi = khi; c.lo = klo; pair = (uint32_t)hash_bucket(key_hash_sk(c, db.K, db.bbits), db.bbits) >> 1; }
+    uint32_t s = db.bstart[2ull * pair], e = db.bstart[2ull * pair + 2];
     for (uint32_t i = s; i < e; ++i) {
         key128 d = db.D_key[i];
         if (d.hi == khi && d.lo == klo) { bump_counter(cs, i); return; }
@@ -499,12 +512,12 @@ __device__ __noinline__ void queue_drain_sk(WarpQueueSk& q, unsigned warp, unsig
     __syncwarp();
 }
 __device__ __forceinline__ void queue_push_sk(WarpQueueSk& q, unsigned warp, unsigned lane, unsigned ballot, bool cand,
-                                              unsigned long long khi, unsigned long long klo, uint32_t bucket, const DbView& db,
+                                              unsigned long long khi, unsigned long long klo, uint32_t pair, const DbView& db,
                                               const CountSink& cs) {
     const unsigned base = q.n[warp];
     if (cand) {
         const unsigned i = base + __popc(ballot & ((1u << lane) - 1u));
-        q.hi[warp][i] = khi; q.lo[warp][i] = klo; q.b[warp][i] = bucket;
+        q.hi[warp][i] = khi; q.lo[warp][i] = klo; q.b[warp][i] = pair;
     }
     __syncwarp();
     const unsigned total = base + __popc(ballot);
@@ -512,8 +525,28 @@ __device__ __forceinline__ void queue_push_sk(WarpQueueSk& q, unsigned warp, uns
     __syncwarp();
     if (total >= 32) queue_drain_sk(q, warp, lane, db, cs);
 }
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+// if (p): fetch the 64-byte bucket pair at src into the lane's slot (four 16-byte cp.async) and note its index
+__device__ __forceinline__ void sk_fetch_if(uint32_t p, uint32_t slot_addr, uint32_t id_addr, const uint32_t* src, uint32_t pair) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.u32 q, %0, 0;\n"
+        "@q cp.async.cg.shared.global [%1], [%2], 16;\n"
+        "@q cp.async.cg.shared.global [%1+4096], [%2+16], 16;\n"
+        "@q cp.async.cg.shared.global [%1+8192], [%2+32], 16;\n"
+        "@q cp.async.cg.shared.global [%1+12288], [%2+48], 16;\n"
+        "@q st.shared.u32 [%3], %4;\n"
+        "}\n" ::"r"(p), "r"(slot_addr), "l"(src), "r"(id_addr), "r"(pair)
+        : "memory");
+}
+static_assert(SK_Q_STRIDE == 4096, "sk_fetch_if hard-codes the quarter stride");
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -530,34 +563,38 @@ __device__ __forceinline__ uint32_t sk_mmer(const uint32_t (&loc)[SEGW], const u
 template <bool HAS_NMASK>
 __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a, DbView db) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SharedStage& stg = *reinterpret_cast<SharedStage*>(smem_raw);
-    SkSlots& slots = *reinterpret_cast<SkSlots*>(smem_raw + sizeof(SharedStage));
-    WarpQueueSk& wq = *reinterpret_cast<WarpQueueSk*>(smem_raw + sizeof(SharedStage) + sizeof(SkSlots));
-    __shared__ __align__(8) unsigned long long mbar[2];
+    SkStage& stg = *reinterpret_cast<SkStage*>(smem_raw);
+    SkSlots& slots = *reinterpret_cast<SkSlots*>(smem_raw + sizeof(SkStage));
+    WarpQueueSk& wq = *reinterpret_cast<WarpQueueSk*>(smem_raw + sizeof(SkStage) + sizeof(SkSlots));
+    __shared__ __align__(8) unsigned long long mbar[WARPS][2];
     __shared__ unsigned long long s_total;
-    __shared__ unsigned long long s_bw0[2], s_mw0[2];
-    __shared__ unsigned s_staged[2];
+    __shared__ unsigned long long s_bw0[WARPS][2], s_mw0[WARPS][2];
+    __shared__ unsigned s_staged[WARPS][2];
 
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     constexpr unsigned K = SK_K;
     const unsigned long long nreads = a.r_end - a.r_begin;
-    const unsigned long long ntiles = (nreads + RT - 1) / RT;
-    const unsigned bshift = 32u - db.bbits;      // 1 <= bbits <= 31
+    const unsigned long long ntiles = (nreads + 31) / 32;                 // a tile = the 32 reads of one warp pass
+    const unsigned long long gw = (unsigned long long)blockIdx.x * WARPS + warp, gstride = (unsigned long long)gridDim.x * WARPS;
+    const unsigned qshift = 33u - db.bbits;      // pair index = top bbits-1 bits of the minimizer's bucket hash; 2 <= bbits <= 31
     const unsigned long long pol_stream = policy_evict_first();
     const CountSink sink{a.cnt8, a.present, a.n_present, a.ci_min};
+    const uint32_t slot_base = smem_u32(&slots.d[0][0][tid]), id_base = smem_u32(&slots.id[0][tid]);
+    const uint32_t slot_end = slot_base + SK_NSLOT * SK_SLOT_STRIDE;
 
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+    if (tid == 0) s_total = 0;
+    if (lane == 0) {
+        mbar_init(&mbar[warp][0], 1);
+        mbar_init(&mbar[warp][1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_total = 0;
+        wq.n[warp] = 0;
     }
-    if (lane == 0) wq.n[warp] = 0;
     __syncthreads();
 
+    // producer side (lane 0 of each warp): stage the stream range of one warp tile, if it fits
     auto issue = [&](unsigned stage, unsigned long long t) {
-        const unsigned long long r0 = a.r_begin + t * RT;
-        const unsigned long long r1 = (r0 + RT < a.r_end) ? r0 + RT : a.r_end;
+        const unsigned long long r0 = a.r_begin + t * 32ull;
+        const unsigned long long r1 = (r0 + 32 < a.r_end) ? r0 + 32 : a.r_end;
         const unsigned long long p0 = a.off ? a.off[r0] : r0 * (unsigned long long)a.read_len;
         const unsigned long long p1 = a.off ? a.off[r1] : r1 * (unsigned long long)a.read_len;
         unsigned long long bw0 = (p0 >> 5) & ~1ull;
@@ -568,38 +605,34 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
         unsigned long long mw1 = ((p1 + 63) >> 6) + 4;
         if (HAS_NMASK) { if (mw1 > a.nmask_words) mw1 = a.nmask_words; mw1 = (mw1 + 1) & ~1ull; }
         const unsigned long long bytes_b = (bw1 - bw0) * 8ull, bytes_m = HAS_NMASK ? (mw1 - mw0) * 8ull : 0ull;
-        const bool fits = bw1 > bw0 && bytes_b <= STAGE_B && bytes_m <= STAGE_M;
-        s_bw0[stage] = bw0; s_mw0[stage] = mw0; s_staged[stage] = fits ? 1u : 0u;
+        const bool fits = bw1 > bw0 && bytes_b <= WSTAGE_B && bytes_m <= WSTAGE_M;
+        s_bw0[warp][stage] = bw0; s_mw0[warp][stage] = mw0; s_staged[warp][stage] = fits ? 1u : 0u;
         if (fits) {
-            mbar_expect_tx(&mbar[stage], (uint32_t)(bytes_b + bytes_m));
-            bulk_g2s(&stg.b[stage][0], a.bases + bw0, (uint32_t)bytes_b, &mbar[stage], pol_stream);
-            if (HAS_NMASK && bytes_m) bulk_g2s(&stg.m[stage][0], a.nmask + mw0, (uint32_t)bytes_m, &mbar[stage], pol_stream);
+            mbar_expect_tx(&mbar[warp][stage], (uint32_t)(bytes_b + bytes_m));
+            bulk_g2s(&stg.b[warp][stage][0], a.bases + bw0, (uint32_t)bytes_b, &mbar[warp][stage], pol_stream);
+            if (HAS_NMASK && bytes_m) bulk_g2s(&stg.m[warp][stage][0], a.nmask + mw0, (uint32_t)bytes_m, &mbar[warp][stage], pol_stream);
         } else {
-            mbar_arrive(&mbar[stage]);
+            mbar_arrive(&mbar[warp][stage]);
         }
     };
 
     constexpr uint32_t KM0 = 0xFFFFFFFFu << (128 - 2 * K);     // K = 60: the low word of a top-aligned k-mer keeps 24 bits
     unsigned long long my_valid = 0;
     unsigned my_fetch = 0;
-    // the bucket this lane holds (registers), the minimizer value it belongs to, and its index
-    uint32_t cur[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) cur[k] = 0;
-    uint32_t cur_wm = 0, cur_bucket = 0;
-    bool have = false;
+    // the minimizer value whose pair this lane holds in slot 0 (nhave: nothing held yet)
+    uint32_t cur_wm = 0, nhave = 0xFFFFFFFFu;
 
     unsigned it = 0;
-    for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    for (unsigned long long t = gw; t < ntiles; t += gstride, ++it) {
         const unsigned stage = it & 1u, parity = (it >> 1) & 1u;
-        if (it == 0 && tid == 0) {
+        if (it == 0 && lane == 0) {
             issue(0, t);
-            if (t + gridDim.x < ntiles) issue(1, t + gridDim.x);
+            if (t + gstride < ntiles) issue(1, t + gstride);
         }
-        __syncthreads();
-        mbar_wait(&mbar[stage], parity);
+        __syncwarp();
+        mbar_wait(&mbar[warp][stage], parity);
 
-        const unsigned long long r = a.r_begin + t * RT + tid;
+        const unsigned long long r = a.r_begin + t * 32ull + lane;
         const bool active = r < a.r_end;
         unsigned long long R0 = 0, R1 = 0;
         if (active) {
@@ -610,9 +643,9 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
         const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
         const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
         const unsigned max_seg = __reduce_max_sync(0xFFFFFFFFu, nseg);
-        const bool staged = s_staged[stage] != 0;
-        const unsigned long long* bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[stage][0]) - s_bw0[stage] : a.bases;
-        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[stage][0]) - s_mw0[stage] : a.nmask;
+        const bool staged = s_staged[warp][stage] != 0;
+        const unsigned long long* bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[warp][stage][0]) - s_bw0[warp][stage] : a.bases;
+        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[warp][stage][0]) - s_mw0[warp][stage] : a.nmask;
 
         for (unsigned seg = 0; seg < max_seg; ++seg) {
             const unsigned c = seg < nseg ? (unsigned)((nw - (unsigned long long)seg * WMAX) < WMAX ? (nw - (unsigned long long)seg * WMAX) : WMAX) : 0u;
@@ -708,104 +741,91 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                 const uint32_t vb = v0 & 0xFFFF0000u;
                 v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
 
-                // ---- phase A: window minima, change points, bucket fetches
+                // ---- phase A: window minima, fingerprints, change points, bucket fetches
+                uint32_t fpv[16];                 // value of the window's first 16-mer, then the window's fingerprint
                 uint32_t chg = 0, ovf = 0;
                 {
                     uint32_t Suf[16];
                     {
                         uint32_t sm = 0xFFFFFFFFu;
 #pragma unroll
-                        for (int i = 15; i >= 0; --i) { sm = min(sm, sk_mmer(loc, rcl, 0, i)); Suf[i] = sm; }
+                        for (int i = 15; i >= 0; --i) { fpv[i] = sk_mmer(loc, rcl, 0, i); sm = min(sm, fpv[i]); Suf[i] = sm; }
                     }
-                    unsigned ns = 0;
-                    bool ovfmode = false;
                     uint32_t base12 = A1, A2 = 0;
+                    uint32_t wr = slot_base + SK_SLOT_STRIDE, wid = id_base + SK_ID_STRIDE;      // slot 0 = the pair carried in
 #pragma unroll
                     for (int tt = 0; tt < 16; ++tt) {
-                        uint32_t wm;
+                        uint32_t wm, he;
                         if (tt < 4) {
-                            P = min(P, sk_mmer(loc, rcl, 2, 12 + tt));
+                            he = sk_mmer(loc, rcl, 2, 12 + tt);
+                            P = min(P, he);
                             wm = min(min(Suf[tt], A1), P);
                             if (tt == 3) { A2 = P; base12 = min(A1, A2); P = 0xFFFFFFFFu; }
                         } else {
-                            P = min(P, sk_mmer(loc, rcl, 3, tt - 4));
+                            he = sk_mmer(loc, rcl, 3, tt - 4);
+                            P = min(P, he);
                             wm = min(min(Suf[tt], base12), P);
                         }
-                        const bool valid = (vb >> (31 - tt)) & 1u;
-                        const bool need = valid && (!have || wm != cur_wm);
-                        if (need) {
-                            if (ns < SK_MAXCH) {
-                                const uint32_t bucket = (wm * MLG_BKT_MULT) >> bshift;
-                                const uint32_t* src = db.T1 + (unsigned long long)bucket * 8ull;
-                                cp_async16(&slots.d[ns][0][tid], src);
-                                cp_async16(&slots.d[ns][1][tid], src + 4);
-                                slots.id[ns][tid] = bucket;
-                                ++ns; cur_wm = wm; have = true; chg |= 1u << tt;
-                            } else {
-                                ovfmode = true;
-                            }
-                        }
-                        if (ovfmode && valid) ovf |= 1u << tt;
+                        fpv[tt] = sk_fp(fpv[tt], he);
+                        const uint32_t vbit = (vb >> (31 - tt)) & 1u;
+                        const uint32_t need = vbit & ((((wm ^ cur_wm) | nhave) != 0u) ? 1u : 0u);
+                        const uint32_t pf = need & (wr != slot_end ? 1u : 0u);
+                        const uint32_t pair = (wm * MLG_BKT_MULT) >> qshift;
+                        sk_fetch_if(pf, wr, wid, db.T1 + (unsigned long long)pair * 16ull, pair);
+                        wr += pf * SK_SLOT_STRIDE; wid += pf * SK_ID_STRIDE;
+                        cur_wm = pf ? wm : cur_wm;
+                        nhave = pf ? 0u : nhave;
+                        chg |= pf << tt;
+                        ovf |= (need ^ pf) << tt;           // a new minimizer, but no fetch slot left in this block
                     }
                     A1 = A2;
-                    my_fetch += ns;
                 }
+                my_fetch += __popc(chg);
                 cp_async_wait_all();
 
-                // ---- phase B: fingerprints against the held bucket
+                // ---- phase B: fingerprints against the half of the held pair that the fingerprint selects
                 if (!__all_sync(0xFFFFFFFFu, vb == 0u)) {
-                    unsigned sp = 0;
-                    constexpr int GROUP = 4;
+                    uint32_t rd = slot_base;
+                    uint32_t candm = ovf;             // windows that must take the exact path
 #pragma unroll
-                    for (int g0 = 0; g0 < 16; g0 += GROUP) {
-                        bool cand[GROUP];
-                        uint32_t cb[GROUP];
-                        bool any = false;
-#pragma unroll
-                        for (int j = 0; j < GROUP; ++j) {
-                            const int tt = g0 + j;
-                            if ((chg >> tt) & 1u) {
-                                const uint4 x = slots.d[sp][0][tid], y = slots.d[sp][1][tid];
-                                cur[0] = x.x; cur[1] = x.y; cur[2] = x.z; cur[3] = x.w;
-                                cur[4] = y.x; cur[5] = y.y; cur[6] = y.z; cur[7] = y.w;
-                                cur_bucket = slots.id[sp][tid];
-                                ++sp;
-                            }
-                            const uint32_t f3 = fsl(loc[0], loc[1], 2 * tt);
-                            const uint32_t f2 = fsl(loc[1], loc[2], 2 * tt);
-                            const uint32_t f1 = fsl(loc[2], loc[3], 2 * tt);
-                            const uint32_t f0 = fsl(loc[3], loc[4], 2 * tt) & KM0;
-                            const uint32_t g3 = fsl(rcl[5], rcl[6], 2 * (15 - tt));
-                            const uint32_t g2 = fsl(rcl[6], rcl[7], 2 * (15 - tt));
-                            const uint32_t g1 = fsl(rcl[7], rcl[8], 2 * (15 - tt));
-                            const uint32_t gz = fsl(rcl[8], rcl[9], 2 * (15 - tt)) & KM0;
-                            const uint32_t d = hash_digest32(f3 + g3, f2 + g2, f1 + g1, f0 + gz);
-                            const uint32_t fp = (d & 0x7FFFFFFFu) ? (d & 0x7FFFFFFFu) : 1u;
-                            bool hit = ((cur[0] & 0x7FFFFFFFu) == fp) | ((int)cur[0] < 0);
-#pragma unroll
-                            for (int sl = 1; sl < 8; ++sl) hit |= (cur[sl] == fp);
-                            const bool isovf = (ovf >> tt) & 1u;
-                            cand[j] = ((vb >> (31 - tt)) & 1u) && (hit | isovf);
-                            cb[j] = isovf ? SK_UNKNOWN : cur_bucket;
-                            any |= cand[j];
-                        }
-                        if (__any_sync(0xFFFFFFFFu, any)) {
-#pragma unroll
-                            for (int j = 0; j < GROUP; ++j) {
-                                const unsigned ballot = __ballot_sync(0xFFFFFFFFu, cand[j]);
-                                if (ballot) {
-                                    const int tt = g0 + j;
-                                    key128 F, G;
-                                    F.hi = ((unsigned long long)fsl(loc[0], loc[1], 2 * tt) << 32) | fsl(loc[1], loc[2], 2 * tt);
-                                    F.lo = ((unsigned long long)fsl(loc[2], loc[3], 2 * tt) << 32) | (fsl(loc[3], loc[4], 2 * tt) & KM0);
-                                    G.hi = ((unsigned long long)fsl(rcl[5], rcl[6], 2 * (15 - tt)) << 32) | fsl(rcl[6], rcl[7], 2 * (15 - tt));
-                                    G.lo = ((unsigned long long)fsl(rcl[7], rcl[8], 2 * (15 - tt)) << 32) | (fsl(rcl[8], rcl[9], 2 * (15 - tt)) & KM0);
-                                    const key128 cn = key_shr(key_lt(G, F) ? G : F, 128 - 2 * K);
-                                    queue_push_sk(wq, warp, lane, ballot, cand[j], cn.hi, cn.lo, cb[j], db, sink);
-                                }
-                            }
+                    for (int tt = 0; tt < 16; ++tt) {
+                        rd += ((chg >> tt) & 1u) * SK_SLOT_STRIDE;
+                        const uint32_t fp = fpv[tt];
+                        const uint32_t ha = rd + ((fp >> 17) & (2u * SK_Q_STRIDE));      // bit 30 of the fingerprint: which half
+                        const uint4 x = lds128(ha), y = lds128(ha + SK_Q_STRIDE);
+                        bool hit = ((x.x & 0x7FFFFFFFu) == fp) | ((int)x.x < 0);
+                        hit |= (x.y == fp) | (x.z == fp) | (x.w == fp) | (y.x == fp) | (y.y == fp) | (y.z == fp) | (y.w == fp);
+                        candm |= (hit ? 1u : 0u) << tt;
+                    }
+                    candm &= __brev(vb);              // bit tt of brev(vb) = validity of window tt
+                    if (__any_sync(0xFFFFFFFFu, candm != 0u)) {
+                        // rare path, rolled: rebuild the canonical key of every candidate window and queue it
+#pragma unroll 1
+                        for (unsigned tt = 0; tt < 16; ++tt) {
+                            const bool cnd = (candm >> tt) & 1u;
+                            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, cnd);
+                            if (!ballot) continue;
+                            const unsigned sf = 2u * tt, sr = 30u - sf;
+                            key128 F, G;
+                            F.hi = ((unsigned long long)fsl(loc[0], loc[1], sf) << 32) | fsl(loc[1], loc[2], sf);
+                            F.lo = ((unsigned long long)fsl(loc[2], loc[3], sf) << 32) | (fsl(loc[3], loc[4], sf) & KM0);
+                            G.hi = ((unsigned long long)fsl(rcl[5], rcl[6], sr) << 32) | fsl(rcl[6], rcl[7], sr);
+                            G.lo = ((unsigned long long)fsl(rcl[7], rcl[8], sr) << 32) | (fsl(rcl[8], rcl[9], sr) & KM0);
+                            const key128 cn = key_shr(key_lt(G, F) ? G : F, 128 - 2 * K);
+                            // the pair the lane held at window tt: slot = number of changes at or before tt
+                            uint32_t pr = SK_UNKNOWN;
+                            if (cnd && !((ovf >> tt) & 1u)) pr = slots.id[__popc(chg & ((2u << tt) - 1u))][tid];
+                            queue_push_sk(wq, warp, lane, ballot, cnd, cn.hi, cn.lo, pr, db, sink);
                         }
                     }
+                }
+                // the pair held at the end of the block moves to slot 0 for the next block
+                if (chg) {
+                    const unsigned last = __popc(chg);
+                    const uint32_t from = slot_base + last * SK_SLOT_STRIDE;
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) sts128(slot_base + qd * SK_Q_STRIDE, lds128(from + qd * SK_Q_STRIDE));
+                    slots.id[0][tid] = slots.id[last][tid];
                 }
                 // slide the register windows by one word
 #pragma unroll
@@ -814,8 +834,8 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                 for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
             }
         }
-        __syncthreads();
-        if (tid == 0 && t + 2ull * gridDim.x < ntiles) issue(stage, t + 2ull * gridDim.x);
+        __syncwarp();
+        if (lane == 0 && t + 2ull * gstride < ntiles) issue(stage, t + 2ull * gstride);
     }
     queue_drain_sk(wq, warp, lane, db, sink);
 
@@ -826,7 +846,7 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
     __syncthreads();
     if (tid == 0 && s_total) atomicAdd(a.n_kmers, s_total);
 }
-constexpr size_t K1SK_SMEM = sizeof(SharedStage) + sizeof(SkSlots) + sizeof(WarpQueueSk);
+constexpr size_t K1SK_SMEM = sizeof(SkStage) + sizeof(SkSlots) + sizeof(WarpQueueSk);
 
 template <bool HAS_NMASK>
 int launch_probe_sk(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {

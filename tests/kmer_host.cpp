@@ -13,7 +13,7 @@ unsigned t_fbit(unsigned long long h) { return filter_bit(h); }
 unsigned t_fmask(unsigned long long h, unsigned fk) { return filter_mask(h, fk); }
 unsigned t_fp(unsigned long long h) { return hash_fp(h); }
 unsigned t_minimizer(unsigned long long hi, unsigned long long lo, unsigned K) { key128 a{hi, lo}; return key_minimizer(a, K); }
-unsigned long long t_hash_sk(unsigned long long hi, unsigned long long lo, unsigned K) { key128 a{hi, lo}; return key_hash_sk(a, K); }
+unsigned long long t_hash_sk(unsigned long long hi, unsigned long long lo, unsigned K, unsigned bbits) { key128 a{hi, lo}; return key_hash_sk(a, K, bbits); }
 unsigned t_mmer_mix(unsigned f, unsigned r) { return mmer_mix(f, r); }
 unsigned t_rev2_32(unsigned x) { return rev2_32h(x); }
 }

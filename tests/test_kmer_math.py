@@ -39,7 +39,7 @@ def kh(tmp_path_factory):
     L.t_fp.restype = C.c_uint
     L.t_minimizer.argtypes = [u64, u64, C.c_uint]
     L.t_minimizer.restype = C.c_uint
-    L.t_hash_sk.argtypes = [u64, u64, C.c_uint]
+    L.t_hash_sk.argtypes = [u64, u64, C.c_uint, C.c_uint]
     L.t_hash_sk.restype = u64
     L.t_mmer_mix.argtypes = [C.c_uint, C.c_uint]
     L.t_mmer_mix.restype = C.c_uint
@@ -117,7 +117,13 @@ def test_minimizer_is_strand_symmetric_and_matches_strings(kh):
             hi, lo = codec.kmer_to_key(s)
             rhi, rlo = codec.kmer_to_key(r)
             assert kh.t_minimizer(hi, lo, K) == want == kh.t_minimizer(rhi, rlo, K)
-            assert kh.t_hash_sk(hi, lo, K) == kh.t_hash_sk(rhi, rlo, K)
+            for bbits in (2, 11, 27, 31):
+                h = kh.t_hash_sk(hi, lo, K, bbits)
+                assert h == kh.t_hash_sk(rhi, rlo, K, bbits)
+                fp = kh.t_fp(h)
+                assert fp == (h & 0x7FFFFFFF) and fp & 1
+                # bucket = 2 * pair + half; the half is bit 30 of the fingerprint, the pair depends on the minimizer only
+                assert kh.t_bucket(h, bbits) & 1 == (fp >> 30) & 1
     # canonical 16-mer mix: both argument orders agree, and rev2_32 reverses base order
     for _ in range(200):
         m = "".join(rng.choice("ACGT") for _ in range(16))
