@@ -64,7 +64,7 @@ typedef struct mlg_stats {
     uint64_t n_db_entries;   /* non-empty sketch slots */
     uint64_t n_db_distinct;  /* |D|: distinct canonical sketch k-mers */
     uint64_t n_buckets;      /* level-1 fingerprint buckets */
-    uint32_t bucket_bytes;   /* bytes fetched per membership probe */
+    uint32_t bucket_bytes;   /* bytes per level-1 fetch: one 16/32-byte bucket (layout 0) or one 64-byte bucket pair (layout 1) */
     uint32_t gpu_launches;   /* kernels of this library launched for this query so far */
     uint64_t h2d_bytes;      /* host->device bytes copied for this query */
     uint64_t d2h_bytes;      /* device->host bytes copied for this query */

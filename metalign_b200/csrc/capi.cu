@@ -96,7 +96,7 @@ void mlg_pool_trim(int device) {
 
 namespace {
 
-constexpr unsigned long long CHUNK_WORDS = 64ull * MLG_TILE_WORDS * 32ull;   // 524288 words = 8 MiB of packed bases per copy chunk
+constexpr unsigned long long CHUNK_WORDS = 2ull * 64ull * MLG_TILE_WORDS * 32ull;   // 1048576 words = 16 MiB of packed bases per copy chunk
 
 struct Staging {
     DevBuf<unsigned char> bases, nmask;
@@ -374,7 +374,8 @@ MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode,
         if (mb >= 0.25 && mb <= 4096) q->chunk_words = std::max<unsigned long long>(1024, (unsigned long long)(mb * 65536.0));
     }
     q->st.n_db_entries = db->v.np; q->st.n_db_distinct = db->v.nd;
-    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.slots * 4; q->st.filter_words = db->v.nfw; q->st.layout = db->v.layout;
+    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.layout == 1 ? 64u : db->v.slots * 4;   // layout 1 fetches bucket PAIRS
+    q->st.filter_words = db->v.nfw; q->st.layout = db->v.layout;
     guard.q = nullptr;
     *out = q;
     return MLG_OK;

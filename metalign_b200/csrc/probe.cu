@@ -484,9 +484,9 @@ struct SkStage {
 };
 struct SkSlots {
     uint4 d[SK_NSLOT][4][RT];        // [slot][quarter][thread]: a 64-byte pair per lane; 16-byte accesses of a warp are contiguous
-    uint32_t id[SK_NSLOT][RT];       // pair index of the slot
+    uint32_t wm[SK_NSLOT + 1][RT];   // minimizer value of the run in each slot (+ one dump entry for runs beyond the last slot)
 };
-constexpr uint32_t SK_SLOT_STRIDE = 4 * RT * 16, SK_Q_STRIDE = RT * 16, SK_ID_STRIDE = RT * 4;
+constexpr uint32_t SK_SLOT_STRIDE = 4 * RT * 16, SK_Q_STRIDE = RT * 16, SK_WM_STRIDE = RT * 4;
 struct WarpQueueSk {
     unsigned long long hi[WARPS][QCAP];
     unsigned long long lo[WARPS][QCAP];
@@ -525,8 +525,8 @@ __device__ __forceinline__ void queue_push_sk(WarpQueueSk& q, unsigned warp, uns
     __syncwarp();
     if (total >= 32) queue_drain_sk(q, warp, lane, db, cs);
 }
-// if (p): fetch the 64-byte bucket pair at src into the lane's slot (four 16-byte cp.async) and note its index
-__device__ __forceinline__ void sk_fetch_if(uint32_t p, uint32_t slot_addr, uint32_t id_addr, const uint32_t* src, uint32_t pair) {
+// if (p): fetch the 64-byte bucket pair at src into the lane's slot (four 16-byte cp.async)
+__device__ __forceinline__ void sk_fetch_if(bool p, uint32_t slot_addr, const uint32_t* src) {
     asm volatile(
         "{\n"
         ".reg .pred q;\n"
@@ -535,9 +535,14 @@ __device__ __forceinline__ void sk_fetch_if(uint32_t p, uint32_t slot_addr, uint
         "@q cp.async.cg.shared.global [%1+4096], [%2+16], 16;\n"
         "@q cp.async.cg.shared.global [%1+8192], [%2+32], 16;\n"
         "@q cp.async.cg.shared.global [%1+12288], [%2+48], 16;\n"
-        "@q st.shared.u32 [%3], %4;\n"
-        "}\n" ::"r"(p), "r"(slot_addr), "l"(src), "r"(id_addr), "r"(pair)
+        "}\n" ::"r"((uint32_t)p), "r"(slot_addr), "l"(src)
         : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
 }
 static_assert(SK_Q_STRIDE == 4096, "sk_fetch_if hard-codes the quarter stride");
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -579,8 +584,8 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
     const unsigned qshift = 33u - db.bbits;      // pair index = top bbits-1 bits of the minimizer's bucket hash; 2 <= bbits <= 31
     const unsigned long long pol_stream = policy_evict_first();
     const CountSink sink{a.cnt8, a.present, a.n_present, a.ci_min};
-    const uint32_t slot_base = smem_u32(&slots.d[0][0][tid]), id_base = smem_u32(&slots.id[0][tid]);
-    const uint32_t slot_end = slot_base + SK_NSLOT * SK_SLOT_STRIDE;
+    const uint32_t slot_base = smem_u32(&slots.d[0][0][tid]), wm_base = smem_u32(&slots.wm[0][tid]);
+    const uint32_t wm_dump = wm_base + SK_NSLOT * SK_WM_STRIDE;
 
     if (tid == 0) s_total = 0;
     if (lane == 0) {
@@ -619,8 +624,9 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
     constexpr uint32_t KM0 = 0xFFFFFFFFu << (128 - 2 * K);     // K = 60: the low word of a top-aligned k-mer keeps 24 bits
     unsigned long long my_valid = 0;
     unsigned my_fetch = 0;
-    // the minimizer value whose pair this lane holds in slot 0 (nhave: nothing held yet)
-    uint32_t cur_wm = 0, nhave = 0xFFFFFFFFu;
+    // the minimizer value whose pair this lane holds in slot 0 (have: false until the first block has been processed)
+    uint32_t held_wm = 0;
+    bool have = false;
 
     unsigned it = 0;
     for (unsigned long long t = gw; t < ntiles; t += gstride, ++it) {
@@ -741,9 +747,10 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                 const uint32_t vb = v0 & 0xFFFF0000u;
                 v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
 
-                // ---- phase A: window minima, fingerprints, change points, bucket fetches
+                // ---- phase A: window minima, fingerprints, runs of equal minimizer (validity is ignored here: a window
+                //      that is not valid costs at most a wasted fetch; it is masked out of the candidates below)
                 uint32_t fpv[16];                 // value of the window's first 16-mer, then the window's fingerprint
-                uint32_t chg = 0, ovf = 0;
+                uint32_t chgraw = 0, wm_first = 0;
                 {
                     uint32_t Suf[16];
                     {
@@ -751,8 +758,8 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
 #pragma unroll
                         for (int i = 15; i >= 0; --i) { fpv[i] = sk_mmer(loc, rcl, 0, i); sm = min(sm, fpv[i]); Suf[i] = sm; }
                     }
-                    uint32_t base12 = A1, A2 = 0;
-                    uint32_t wr = slot_base + SK_SLOT_STRIDE, wid = id_base + SK_ID_STRIDE;      // slot 0 = the pair carried in
+                    uint32_t base12 = A1, A2 = 0, pw = 0;
+                    uint32_t lst = wm_base + SK_WM_STRIDE;          // where the next run's minimizer goes
 #pragma unroll
                     for (int tt = 0; tt < 16; ++tt) {
                         uint32_t wm, he;
@@ -767,20 +774,37 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                             wm = min(min(Suf[tt], base12), P);
                         }
                         fpv[tt] = sk_fp(fpv[tt], he);
-                        const uint32_t vbit = (vb >> (31 - tt)) & 1u;
-                        const uint32_t need = vbit & ((((wm ^ cur_wm) | nhave) != 0u) ? 1u : 0u);
-                        const uint32_t pf = need & (wr != slot_end ? 1u : 0u);
-                        const uint32_t pair = (wm * MLG_BKT_MULT) >> qshift;
-                        sk_fetch_if(pf, wr, wid, db.T1 + (unsigned long long)pair * 16ull, pair);
-                        wr += pf * SK_SLOT_STRIDE; wid += pf * SK_ID_STRIDE;
-                        cur_wm = pf ? wm : cur_wm;
-                        nhave = pf ? 0u : nhave;
-                        chg |= pf << tt;
-                        ovf |= (need ^ pf) << tt;           // a new minimizer, but no fetch slot left in this block
+                        if (tt == 0) { wm_first = wm; sts32(wm_base, wm); }
+                        else if (wm != pw) {                       // a new run starts at window tt
+                            sts32(min(lst, wm_dump), wm);
+                            lst += SK_WM_STRIDE;
+                            chgraw |= 1u << tt;
+                        }
+                        pw = wm;
                     }
                     A1 = A2;
                 }
-                my_fetch += __popc(chg);
+                // runs 0..3 of the block live in slots 0..3; windows of later runs (rare) take the exact path with an unknown pair
+                uint32_t chg, ovf;
+                {
+                    uint32_t t3 = chgraw;
+                    t3 &= t3 - 1u; t3 &= t3 - 1u; t3 &= t3 - 1u;      // changes beyond the third
+                    chg = chgraw ^ t3;
+                    ovf = t3 ? ~((t3 & (0u - t3)) - 1u) & 0xFFFFu : 0u;   // every window from the fourth change on
+                }
+                const unsigned nrun = 1u + __popc(chg);
+                // run 0 continues the pair carried in slot 0 unless its minimizer differs; runs 1.. are always new
+                {
+                    const bool need0 = !have || wm_first != held_wm;
+                    sk_fetch_if(need0, slot_base, db.T1 + (unsigned long long)((wm_first * MLG_BKT_MULT) >> qshift) * 16ull);
+                    my_fetch += need0 ? 1u : 0u;
+#pragma unroll
+                    for (unsigned rr = 1; rr < SK_NSLOT; ++rr) {
+                        const uint32_t w = lds32(wm_base + rr * SK_WM_STRIDE);
+                        sk_fetch_if(rr < nrun, slot_base + rr * SK_SLOT_STRIDE, db.T1 + (unsigned long long)((w * MLG_BKT_MULT) >> qshift) * 16ull);
+                    }
+                    my_fetch += nrun - 1u;
+                }
                 cp_async_wait_all();
 
                 // ---- phase B: fingerprints against the half of the held pair that the fingerprint selects
@@ -814,18 +838,18 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                             const key128 cn = key_shr(key_lt(G, F) ? G : F, 128 - 2 * K);
                             // the pair the lane held at window tt: slot = number of changes at or before tt
                             uint32_t pr = SK_UNKNOWN;
-                            if (cnd && !((ovf >> tt) & 1u)) pr = slots.id[__popc(chg & ((2u << tt) - 1u))][tid];
+                            if (cnd && !((ovf >> tt) & 1u)) pr = (slots.wm[__popc(chg & ((2u << tt) - 1u))][tid] * MLG_BKT_MULT) >> qshift;
                             queue_push_sk(wq, warp, lane, ballot, cnd, cn.hi, cn.lo, pr, db, sink);
                         }
                     }
                 }
-                // the pair held at the end of the block moves to slot 0 for the next block
-                if (chg) {
-                    const unsigned last = __popc(chg);
-                    const uint32_t from = slot_base + last * SK_SLOT_STRIDE;
+                // the pair of the last run in a slot moves to slot 0 for the next block
+                have = true;
+                held_wm = lds32(wm_base + (nrun - 1u) * SK_WM_STRIDE);
+                if (nrun > 1u) {
+                    const uint32_t from = slot_base + (nrun - 1u) * SK_SLOT_STRIDE;
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd) sts128(slot_base + qd * SK_Q_STRIDE, lds128(from + qd * SK_Q_STRIDE));
-                    slots.id[0][tid] = slots.id[last][tid];
                 }
                 // slide the register windows by one word
 #pragma unroll
