@@ -126,7 +126,7 @@ struct mlg_query {
     bool finished = false, reduced = false;
     unsigned long long chunk_words = CHUNK_WORDS;   // 64-base words per host->device copy chunk
     // results kept for mlg_query_intersection
-    DevBuf<uint32_t> present;
+    DevBuf<uint32_t> present, touched;
     uint32_t n_present = 0;
 };
 
@@ -147,6 +147,7 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
     mlg_ctx* ctx = q->ctx;
     if (!q->present.p) {                       // first push: room for every database k-mer to become present once
         MLG_TRY(q->present.alloc((size_t)q->db->v.nd + 1));
+        MLG_TRY(q->touched.alloc((size_t)q->db->v.nd + 1));
     }
     const unsigned long long nwords64 = (nbases + 63) / 64;       // 64-base words: 16 bytes of bases, 8 bytes of mask
     ProbeArgs a{};
@@ -156,7 +157,7 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
     a.base_words = nwords64 * 2;                                  // buffers cover whole 16-byte units
     a.nmask_words = round_up(nwords64, 2);
     a.cnt8 = q->cnt8.p; a.n_kmers = q->d_nkmers.p;
-    a.ci_min = (uint32_t)q->ci_min; a.present = q->present.p; a.n_present = q->d_scalar.p;
+    a.ci_min = (uint32_t)q->ci_min; a.present = q->present.p; a.n_present = q->d_scalar.p; a.touched = q->touched.p;
     auto launch_range = [&](unsigned long long r0, unsigned long long r1) -> int {
         if (r1 <= r0) return MLG_OK;
         cudaEvent_t e0, e1;
@@ -364,10 +365,10 @@ MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode,
     q->ctx = ctx; q->db = db; q->ci_min = ci_min; q->gate = gate_mode; q->count_empty = count_empty_in_den ? 1 : 0;
     size_t cbytes = round_up((size_t)db->v.nd + 4, 16);
     MLG_TRY(q->cnt8.alloc(cbytes));
-    MLG_TRY(q->d_nkmers.alloc(2)); MLG_TRY(q->d_scalar.alloc(2));
+    MLG_TRY(q->d_nkmers.alloc(2)); MLG_TRY(q->d_scalar.alloc(4));
     CUDA_TRY(cudaMemsetAsync(q->cnt8.p, 0, cbytes, ctx->s_comp));
     CUDA_TRY(cudaMemsetAsync(q->d_nkmers.p, 0, 16, ctx->s_comp));
-    CUDA_TRY(cudaMemsetAsync(q->d_scalar.p, 0, 16, ctx->s_comp));
+    CUDA_TRY(cudaMemsetAsync(q->d_scalar.p, 0, 32, ctx->s_comp));
     CUDA_TRY(cudaEventCreate(&q->ev_q0)); CUDA_TRY(cudaEventCreate(&q->ev_q1));
     if (const char* e = getenv("MLG_CHUNK_MB")) {     // experiment knob: MiB of packed bases per copy chunk
         double mb = atof(e);
@@ -529,8 +530,10 @@ MLG_API int mlg_query_counts_export(mlg_query* q, uint8_t** d_counts, uint64_t* 
     if (!q || !d_counts || !n_counts) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
     if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
     MLG_TRY(ensure_device(q->ctx));
-    MLG_TRY(launch_clamp_counts(q->cnt8.p, q->db->v.nd, (uint32_t)q->ci_min, q->ctx->s_comp));
-    q->st.gpu_launches += 1;
+    if (q->touched.p) {     // nothing pushed: every counter is still zero
+        MLG_TRY(launch_clamp_counts(q->cnt8.p, q->touched.p, q->d_scalar.p + 1, (uint32_t)q->ci_min, q->ctx->s_comp));
+        q->st.gpu_launches += 1;
+    }
     MLG_TRY(mlg_query_sync(q));
     *d_counts = q->cnt8.p; *n_counts = q->db->v.nd;
     return MLG_OK;
@@ -548,7 +551,7 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     MLG_TRY(ensure_device(ctx));
     cudaStream_t st = ctx->s_comp;
     CUDA_TRY(cudaStreamSynchronize(ctx->s_copy));
-    if (!q->present.p) MLG_TRY(q->present.alloc((size_t)v.nd + 1));     // nothing was pushed
+    if (!q->present.p) { MLG_TRY(q->present.alloc((size_t)v.nd + 1)); MLG_TRY(q->touched.alloc((size_t)v.nd + 1)); }   // nothing was pushed
     CUDA_TRY(cudaEventRecord(q->ev_q0, st));
     // I = database k-mers seen >= ci_min times.  Single GPU: the probe kernel appended each one when its counter
     // reached ci_min.  After a cross-rank reduction the list is rebuilt from the summed counters.
@@ -566,7 +569,14 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     DevBuf<long long> o_num, o_den; DevBuf<double> o_ci;
     MLG_TRY(o_num.alloc(cells)); MLG_TRY(o_den.alloc(cells)); MLG_TRY(o_ci.alloc(cells));
     CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
-    MLG_TRY(launch_expand_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p, st));
+    if (db->hoff.p) {
+        // replay the precomputed hit lists; touched[] is dead by now and serves as the list of k-mers without one
+        MLG_TRY(launch_apply_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p,
+                                  db->hoff.p, db->hits.p, q->touched.p, q->d_scalar.p + 2, st));
+        q->st.gpu_launches += 1;
+    } else {
+        MLG_TRY(launch_expand_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p, st));
+    }
     MLG_TRY(launch_finalize(d_num.p, db->den_real.p, db->has_empty.p, v.G, v.nk, q->count_empty, o_num.p, o_den.p, o_ci.p, st));
     q->st.gpu_launches += 2;
     CUDA_TRY(cudaEventRecord(q->ev_q1, st));

@@ -415,6 +415,42 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             }
         }
     }
+    // 6. hit lists: what a present k-mer of D contributes to the per-genome table is a static function of the
+    //    database, so it is expanded once here (same code as the on-the-fly kernel) and replayed per query.
+    //    MLG_PRECOMPUTE_HITS=0 skips this; k-mers that do not fit (buffer or list too small) stay on the fly.
+    {
+        const char* pe = getenv("MLG_PRECOMPUTE_HITS");
+        if (nd && (!pe || atoi(pe) != 0)) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            unsigned long long cap = (unsigned long long)nd * 12ull;                 // words; ~5-7 are used per k-mer
+            const unsigned long long lim = (unsigned long long)(free_b * 0.4) / 4ull;
+            if (cap > lim) cap = lim;
+            if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+            if (const char* s = getenv("MLG_HIT_CAP_WORDS")) { unsigned long long x = strtoull(s, nullptr, 10); if (x >= 16 && x < cap) cap = x; }   // tests: force the fallback
+            if (cap >= 16 && db->hoff.alloc(nd) == MLG_OK) {
+                DevBuf<uint32_t> big;
+                if (big.alloc(cap) == MLG_OK) {
+                    MLG_TRY(launch_collect_hits(v, db->hoff.p, big.p, cap, d_cnt.p, st));
+                    unsigned long long used = 0;
+                    CUDA_TRY(cudaMemcpyAsync(&used, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    CUDA_TRY(cudaGetLastError());
+                    if (used > cap) used = cap;
+                    if (used == 0) used = 1;
+                    MLG_TRY(db->hits.alloc(used));
+                    CUDA_TRY(cudaMemcpyAsync(db->hits.p, big.p, used * 4ull, cudaMemcpyDeviceToDevice, st));
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    db->hit_words = used;
+                } else {
+                    db->hoff.release();
+                }
+            } else {
+                db->hoff.release();
+            }
+        }
+    }
     CUDA_TRY(cudaEventRecord(e1, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());

@@ -97,6 +97,8 @@ struct mlg_db {
     DevBuf<uint32_t> P_slot, pidx, rep, bstart, T1;
     DevBuf<uint32_t> F;
     DevBuf<key128> D_key;
+    DevBuf<uint32_t> hoff, hits;     // precomputed hit lists per k-mer of D (hoff.p == nullptr: not built)
+    unsigned long long hit_words = 0;
     DevBuf<long long> den_real;      // G*nk
     DevBuf<unsigned char> has_empty; // G
     double build_ms = 0;
@@ -117,7 +119,8 @@ struct ProbeArgs {
     unsigned char* cnt8;                // nd saturating occurrence counters
     uint32_t ci_min;                    // a counter reaching ci_min appends its index to present[]
     uint32_t* present;                  // nd entries
-    unsigned long long* n_present;      // device cursor of present[]
+    unsigned long long* n_present;      // device cursors: [0] of present[], [1] of touched[]
+    uint32_t* touched;                  // nd entries: counters that left zero
     unsigned long long* n_kmers;        // device accumulators: [0] valid windows, [1] level-1 bucket fetches (layout 1)
 };
 int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaStream_t st);
@@ -125,11 +128,18 @@ int launch_pack_ascii(const unsigned char* text, unsigned long long nbases, unsi
                       cudaStream_t st);
 int launch_ascii_to_keys(const unsigned char* text, unsigned long long nslots, uint32_t K, key128* keys, cudaStream_t st);
 
-int launch_clamp_counts(unsigned char* cnt8, uint32_t nd, uint32_t ci_min, cudaStream_t st);
+int launch_clamp_counts(unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min, cudaStream_t st);
 int launch_compact_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* d_cursor,
                            cudaStream_t st);
 int launch_expand_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,
                        uint32_t* hitbits, unsigned long long words_per_k, unsigned long long* num, cudaStream_t st);
+// precomputed hit lists (built once per database, replayed per query); HOFF_NONE = no list, expand on the fly
+#define HOFF_NONE 0xFFFFFFFFu
+int launch_apply_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,
+                      uint32_t* hitbits, unsigned long long words_per_k, unsigned long long* num, const uint32_t* hoff,
+                      const uint32_t* hits, uint32_t* fallback, unsigned long long* d_n_fallback, cudaStream_t st);
+int launch_collect_hits(const DbView& db, uint32_t* hoff, uint32_t* hits, unsigned long long cap_words, unsigned long long* d_cursor,
+                        cudaStream_t st);
 int launch_scatter_nruns(const uint32_t* d_runs, unsigned long long n_runs, unsigned long long nbases, unsigned char* nmask,
                          cudaStream_t st);
 int launch_finalize(const unsigned long long* num, const long long* den_real, const unsigned char* has_empty, uint32_t G,

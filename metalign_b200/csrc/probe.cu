@@ -121,7 +121,8 @@ __device__ __forceinline__ bool bucket_candidate(const BucketVec<SLOTS>& v, uint
 struct CountSink {
     unsigned char* cnt8;
     uint32_t* present;
-    unsigned long long* n_present;
+    unsigned long long* n_present;      // [0] cursor of present[], [1] cursor of touched[]
+    uint32_t* touched;                  // database k-mers seen at least once (the non-zero counters: what a cross-rank exchange needs)
     uint32_t ci_min;
 };
 // saturating (255) increment of byte counter i via 32-bit CAS
@@ -133,7 +134,9 @@ __device__ __forceinline__ void bump_counter(const CountSink& cs, uint32_t i) {
         uint32_t assumed = old;
         old = atomicCAS(wp, assumed, assumed + (1u << sh));
         if (old == assumed) {
-            if (((assumed >> sh) & 0xFFu) + 1u == cs.ci_min) cs.present[atomicAdd(cs.n_present, 1ull)] = i;
+            const uint32_t before = (assumed >> sh) & 0xFFu;
+            if (before == 0u) cs.touched[atomicAdd(cs.n_present + 1, 1ull)] = i;
+            if (before + 1u == cs.ci_min) cs.present[atomicAdd(cs.n_present, 1ull)] = i;
             break;
         }
     }
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_decode_canon_probe(ProbeArg
     const unsigned long long ntiles = (nreads + RT - 1) / RT;
     const unsigned bshift = 32u - db.bbits;      // 1 <= bbits <= 31
     const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
-    const CountSink sink{a.cnt8, a.present, a.n_present, a.ci_min};
+    const CountSink sink{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
     const unsigned long long gw = (unsigned long long)blockIdx.x * WARPS + warp, gstride = (unsigned long long)gridDim.x * WARPS;
     const unsigned qshift = 33u - db.bbits;      // pair index = top bbits-1 bits of the minimizer's bucket hash; 2 <= bbits <= 31
     const unsigned long long pol_stream = policy_evict_first();
-    const CountSink sink{a.cnt8, a.present, a.n_present, a.ci_min};
+    const CountSink sink{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
     const uint32_t slot_base = smem_u32(&slots.d[0][0][tid]), wm_base = smem_u32(&slots.wm[0][tid]);
     const uint32_t wm_dump = wm_base + SK_NSLOT * SK_WM_STRIDE;
 

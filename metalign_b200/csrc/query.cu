@@ -35,66 +35,155 @@ __device__ __forceinline__ void prefix_range(const DbView& db, const key128& v, 
     lo_out = lo; cnt_out = e - lo;
 }
 
+// ---- where a hit goes -----------------------------------------------------------------------------------------
+// (a) query time, on the fly: straight into the hit bitmap (set semantics) and, on the first set, the count table
 struct HitSink {
     uint32_t* hitbits;
     unsigned long long words_per_k;
     unsigned long long* num;      // G * nk
+    __device__ __forceinline__ void set(const DbView& db, uint32_t ki, uint32_t r) const {
+        const uint32_t bit = 1u << (r & 31u);
+        const uint32_t old = atomicOr(&hitbits[(unsigned long long)ki * words_per_k + (r >> 5)], bit);
+        if (!(old & bit)) atomicAdd(&num[(unsigned long long)(r / db.n) * db.nk + ki], 1ull);
+    }
+    __device__ __forceinline__ void mark(const DbView& db, uint32_t ki, uint32_t e, bool /*also_under_exact_gate*/) const {
+        const unsigned long long total = (unsigned long long)db.G * db.n;
+        set(db, ki, db.rep[(unsigned long long)ki * total + db.P_slot[e]]);
+    }
 };
-__device__ __forceinline__ void mark_hit(const DbView& db, const HitSink& hs, uint32_t ki, uint32_t e) {
-    const unsigned long long total = (unsigned long long)db.G * db.n;
-    const uint32_t slot = db.P_slot[e];
-    const uint32_t r = db.rep[(unsigned long long)ki * total + slot];
-    const uint32_t bit = 1u << (r & 31u);
-    const uint32_t old = atomicOr(&hs.hitbits[(unsigned long long)ki * hs.words_per_k + (r >> 5)], bit);
-    if (!(old & bit)) atomicAdd(&hs.num[(unsigned long long)(r / db.n) * db.nk + ki], 1ull);
+// (b) database build: the hits of a database k-mer are a static function of the database, so they are expanded
+//     ONCE for every k-mer of D (gate = none, each hit flagged with whether the exact gate would also let it
+//     through) and kept as a list per k-mer; a query then only replays the lists of the k-mers it found.
+constexpr unsigned HCAP = 96;          // hits collected per k-mer before the list is given up (-> on-the-fly expansion)
+constexpr uint32_t HIT_EXACT = 0x80000000u;
+struct CollectSink {
+    uint32_t* val;                // [HCAP] per warp, shared memory: representative slot | HIT_EXACT
+    unsigned char* kis;           // [HCAP]
+    unsigned* n;                  // per warp
+    __device__ __forceinline__ void mark(const DbView& db, uint32_t ki, uint32_t e, bool also_under_exact_gate) const {
+        const unsigned long long total = (unsigned long long)db.G * db.n;
+        const uint32_t r = db.rep[(unsigned long long)ki * total + db.P_slot[e]];
+        const unsigned i = atomicAdd(n, 1u);
+        if (i < HCAP) { val[i] = r | (also_under_exact_gate ? HIT_EXACT : 0u); kis[i] = (unsigned char)ki; }
+    }
+};
+
+// all lanes of a warp: expand database k-mer x.  gate_none = 0 applies the exact smallest-k gate.
+template <class Sink>
+__device__ __forceinline__ void expand_one(const DbView& db, const key128& x, int gate_none, const Sink& sink, unsigned lane,
+                                           uint32_t* s_flo, uint32_t* s_fcnt, uint32_t* s_rlo, uint32_t* s_rcnt) {
+    const unsigned K = db.K, k0 = db.ks[0], noff = K - k0 + 1;
+    for (unsigned o = lane; o < noff; o += 32) {
+        const key128 w = key_sub(x, K, o, k0);
+        uint32_t lo, cnt;
+        prefix_range(db, w, k0, lo, cnt);
+        s_flo[o] = lo; s_fcnt[o] = cnt;
+        prefix_range(db, key_rc(w, k0), k0, lo, cnt);
+        s_rlo[o] = lo; s_rcnt[o] = cnt;
+    }
+    __syncwarp();
+    for (unsigned o = lane; o < noff; o += 32) {
+        const uint32_t fl = s_flo[o], fc = s_fcnt[o];
+        const uint32_t rl = s_rlo[o], rc = s_rcnt[o];
+        // smallest k: forward first, reverse complement only if forward is empty (no gate on this lookup)
+        if (fc) { for (uint32_t e = fl; e < fl + fc; ++e) sink.mark(db, 0, e, true); }
+        else    { for (uint32_t e = rl; e < rl + rc; ++e) sink.mark(db, 0, e, true); }
+        const bool exact_ok = fc || rc;
+        if (!(gate_none || exact_ok)) continue;
+        for (uint32_t ki = 1; ki < db.nk; ++ki) {
+            const unsigned k = db.ks[ki];
+            if (o + k > K) continue;
+            const key128 wk = key_sub(x, K, o, k);
+            bool any = false;
+            for (uint32_t e = fl; e < fl + fc; ++e)
+                if (key_eq(key_prefix(db.P_key[e], K, k), wk)) { sink.mark(db, ki, e, exact_ok); any = true; }
+            if (!any) {
+                // rc(wk) starts with the reverse complement of the LAST k0 bases of wk: offset o + k - k0
+                const unsigned o2 = o + k - k0;
+                const uint32_t rl2 = s_rlo[o2], rc2 = s_rcnt[o2];
+                const key128 rk = key_rc(wk, k);
+                for (uint32_t e = rl2; e < rl2 + rc2; ++e)
+                    if (key_eq(key_prefix(db.P_key[e], K, k), rk)) sink.mark(db, ki, e, exact_ok);
+            }
+        }
+    }
+    __syncwarp();
 }
 
+// on-the-fly expansion of the listed k-mers (all present ones, or those without a precomputed list)
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_expand_hits(DbView db, const uint32_t* __restrict__ present,
                                                                     const unsigned long long* __restrict__ d_n_present,
                                                                     int gate_none, HitSink hs) {
     __shared__ uint32_t s_flo[WARPS_PER_CTA][MAX_OFF], s_fcnt[WARPS_PER_CTA][MAX_OFF];
     __shared__ uint32_t s_rlo[WARPS_PER_CTA][MAX_OFF], s_rcnt[WARPS_PER_CTA][MAX_OFF];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const unsigned K = db.K, k0 = db.ks[0], noff = K - k0 + 1;
     const unsigned long long n_present = *d_n_present;
     for (unsigned long long xi = (unsigned long long)blockIdx.x * WARPS_PER_CTA + warp; xi < n_present;
-         xi += (unsigned long long)gridDim.x * WARPS_PER_CTA) {
-        const key128 x = db.D_key[present[xi]];
-        for (unsigned o = lane; o < noff; o += 32) {
-            const key128 w = key_sub(x, K, o, k0);
-            uint32_t lo, cnt;
-            prefix_range(db, w, k0, lo, cnt);
-            s_flo[warp][o] = lo; s_fcnt[warp][o] = cnt;
-            prefix_range(db, key_rc(w, k0), k0, lo, cnt);
-            s_rlo[warp][o] = lo; s_rcnt[warp][o] = cnt;
-        }
+         xi += (unsigned long long)gridDim.x * WARPS_PER_CTA)
+        expand_one(db, db.D_key[present[xi]], gate_none, hs, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
+}
+
+// database build: hit list of every k-mer of D.  Record layout in hits[]: header word (count per k, 4 bits each),
+// then the hits grouped by k, each = representative slot | HIT_EXACT.  hoff[e] = word offset of the record, or
+// HOFF_NONE when the k-mer has too many hits / the buffer is full (such k-mers are expanded on the fly).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_collect_hits(DbView db, uint32_t* hoff, uint32_t* hits,
+                                                                     unsigned long long cap_words, unsigned long long* cursor) {
+    __shared__ uint32_t s_flo[WARPS_PER_CTA][MAX_OFF], s_fcnt[WARPS_PER_CTA][MAX_OFF];
+    __shared__ uint32_t s_rlo[WARPS_PER_CTA][MAX_OFF], s_rcnt[WARPS_PER_CTA][MAX_OFF];
+    __shared__ uint32_t s_val[WARPS_PER_CTA][HCAP];
+    __shared__ unsigned char s_ki[WARPS_PER_CTA][HCAP];
+    __shared__ unsigned s_n[WARPS_PER_CTA];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS_PER_CTA + warp; e < db.nd;
+         e += (unsigned long long)gridDim.x * WARPS_PER_CTA) {
+        if (lane == 0) s_n[warp] = 0;
         __syncwarp();
-        for (unsigned o = lane; o < noff; o += 32) {
-            const uint32_t fl = s_flo[warp][o], fc = s_fcnt[warp][o];
-            const uint32_t rl = s_rlo[warp][o], rc = s_rcnt[warp][o];
-            // smallest k: forward first, reverse complement only if forward is empty
-            if (fc) { for (uint32_t e = fl; e < fl + fc; ++e) mark_hit(db, hs, 0, e); }
-            else    { for (uint32_t e = rl; e < rl + rc; ++e) mark_hit(db, hs, 0, e); }
-            const bool possible = gate_none || fc || rc;
-            if (!possible) continue;
-            for (uint32_t ki = 1; ki < db.nk; ++ki) {
-                const unsigned k = db.ks[ki];
-                if (o + k > K) continue;
-                const key128 wk = key_sub(x, K, o, k);
-                bool any = false;
-                for (uint32_t e = fl; e < fl + fc; ++e)
-                    if (key_eq(key_prefix(db.P_key[e], K, k), wk)) { mark_hit(db, hs, ki, e); any = true; }
-                if (!any) {
-                    // rc(wk) starts with the reverse complement of the LAST k0 bases of wk: offset o + k - k0
-                    const unsigned o2 = o + k - k0;
-                    const uint32_t rl2 = s_rlo[warp][o2], rc2 = s_rcnt[warp][o2];
-                    const key128 rk = key_rc(wk, k);
-                    for (uint32_t e = rl2; e < rl2 + rc2; ++e)
-                        if (key_eq(key_prefix(db.P_key[e], K, k), rk)) mark_hit(db, hs, ki, e);
+        CollectSink sink{s_val[warp], s_ki[warp], &s_n[warp]};
+        expand_one(db, db.D_key[e], 1, sink, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
+        if (lane == 0) {
+            const unsigned n = s_n[warp];
+            uint32_t off = HOFF_NONE;
+            unsigned cnt[MLG_MAX_KS];
+            for (unsigned k = 0; k < MLG_MAX_KS; ++k) cnt[k] = 0;
+            bool ok = n <= HCAP;
+            if (ok) {
+                for (unsigned i = 0; i < n; ++i) cnt[s_ki[warp][i]]++;
+                for (unsigned k = 0; k < MLG_MAX_KS; ++k) ok = ok && cnt[k] <= 15u;
+            }
+            if (ok) {
+                const unsigned long long base = atomicAdd(cursor, (unsigned long long)n + 1ull);
+                if (base + n + 1ull <= cap_words && base + n + 1ull < (unsigned long long)HOFF_NONE) {
+                    uint32_t hdr = 0; unsigned start[MLG_MAX_KS]; unsigned acc = 0;
+                    for (unsigned k = 0; k < MLG_MAX_KS; ++k) { hdr |= cnt[k] << (4 * k); start[k] = acc; acc += cnt[k]; }
+                    hits[base] = hdr;
+                    for (unsigned i = 0; i < n; ++i) hits[base + 1 + start[s_ki[warp][i]]++] = s_val[warp][i];
+                    off = (uint32_t)base;
                 }
             }
+            hoff[e] = off;
         }
         __syncwarp();
+    }
+}
+
+// query time: replay the precomputed hit lists of the present k-mers; k-mers without a list are queued for
+// the on-the-fly kernel
+__global__ void k_apply_hits(DbView db, const uint32_t* __restrict__ present, const unsigned long long* __restrict__ d_n_present,
+                             int gate_none, HitSink hs, const uint32_t* __restrict__ hoff, const uint32_t* __restrict__ hits,
+                             uint32_t* fallback, unsigned long long* n_fallback) {
+    const unsigned long long n_present = *d_n_present;
+    for (unsigned long long xi = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; xi < n_present;
+         xi += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t e = present[xi];
+        const uint32_t off = hoff[e];
+        if (off == HOFF_NONE) { fallback[atomicAdd(n_fallback, 1ull)] = e; continue; }
+        uint32_t hdr = hits[off];
+        const uint32_t* hp = hits + off + 1;
+        for (uint32_t ki = 0; ki < db.nk; ++ki, hdr >>= 4)
+            for (uint32_t c = hdr & 15u; c; --c) {
+                const uint32_t v = *hp++;
+                if (gate_none || (v & HIT_EXACT)) hs.set(db, ki, v & ~HIT_EXACT);
+            }
     }
 }
 
@@ -109,29 +198,34 @@ __global__ void k_finalize(const unsigned long long* num, const long long* den_r
     out_ci[c] = nu > 0 ? (double)nu / (double)de : 0.0;
 }
 
-__global__ void k_clamp_counts(uint32_t* cnt_words, unsigned long long nwords, uint32_t ci_min) {
-    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    uint32_t w = cnt_words[i], r = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        uint32_t c = (w >> (8 * b)) & 0xFFu;
-        r |= (c > ci_min ? ci_min : c) << (8 * b);
+// clamp the counters that are non-zero (listed in touched[]) to ci_min: what a rank contributes to the cross-rank sum
+__global__ void k_clamp_counts(unsigned char* cnt8, const uint32_t* __restrict__ touched, const unsigned long long* __restrict__ d_n,
+                               uint32_t ci_min) {
+    const unsigned long long n = *d_n;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t e = touched[i];
+        if (cnt8[e] > ci_min) cnt8[e] = (unsigned char)ci_min;
     }
-    cnt_words[i] = r;
 }
-__global__ void k_compact_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* cursor) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long nd_round = ((unsigned long long)nd + 31ull) & ~31ull;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nd_round; i += stride) {
-        const bool p = i < nd && cnt8[i] >= ci_min;
-        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, p);
-        if (ballot == 0) continue;
-        const unsigned lane = threadIdx.x & 31u;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(ballot));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (p) out[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)i;
+// present[] = indices of the counters >= ci_min; 16 counters per thread and step (the table is almost all zeros)
+__global__ void k_compact_present(const uint4* __restrict__ cnt16, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* cursor) {
+    const unsigned long long nvec = ((unsigned long long)nd + 15ull) / 16ull;       // the table is padded to 16 bytes with zeros
+    for (unsigned long long v = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; v < nvec; v += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 q = cnt16[v];
+        if ((q.x | q.y | q.z | q.w) == 0u) continue;
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t hits[16]; unsigned nh = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const unsigned long long idx = v * 16ull + 4 * k + b;
+                if (((w[k] >> (8 * b)) & 0xFFu) >= ci_min && idx < nd) hits[nh++] = (uint32_t)idx;
+            }
+        if (nh) {
+            const unsigned long long base = atomicAdd(cursor, (unsigned long long)nh);
+            for (unsigned h = 0; h < nh; ++h) out[base + h] = hits[h];
+        }
     }
 }
 // N runs -> N mask.  One thread per (start, length) run; bit i of the mask lives in byte i/8, bit 7-(i%8).
@@ -159,10 +253,8 @@ __global__ void k_gather_present_keys(const key128* D_key, const uint32_t* prese
 
 }  // namespace
 
-int launch_clamp_counts(unsigned char* cnt8, uint32_t nd, uint32_t ci_min, cudaStream_t st) {
-    unsigned long long nwords = ((unsigned long long)nd + 3) / 4;
-    if (!nwords) return MLG_OK;
-    k_clamp_counts<<<(unsigned)((nwords + 255) / 256), 256, 0, st>>>(reinterpret_cast<uint32_t*>(cnt8), nwords, ci_min);
+int launch_clamp_counts(unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min, cudaStream_t st) {
+    k_clamp_counts<<<148u * 4u, 256, 0, st>>>(cnt8, touched, d_n_touched, ci_min);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }
@@ -170,9 +262,7 @@ int launch_compact_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_m
                            cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 8, st));
     if (!nd) return MLG_OK;
-    unsigned grid = (unsigned)(((unsigned long long)nd + 256ull * 16 - 1) / (256ull * 16));
-    if (grid > 148u * 8u) grid = 148u * 8u;
-    k_compact_present<<<grid, 256, 0, st>>>(cnt8, nd, ci_min, out, d_cursor);
+    k_compact_present<<<148u * 8u, 256, 0, st>>>(reinterpret_cast<const uint4*>(cnt8), nd, ci_min, out, d_cursor);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }
@@ -181,6 +271,26 @@ int launch_expand_hits(const DbView& db, const uint32_t* present, const unsigned
     // persistent grid: |I| is only known on the device (no host round trip between the probe and this kernel)
     HitSink hs{hitbits, words_per_k, num};
     k_expand_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, present, d_n_present, gate_none, hs);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_apply_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,
+                      uint32_t* hitbits, unsigned long long words_per_k, unsigned long long* num, const uint32_t* hoff,
+                      const uint32_t* hits, uint32_t* fallback, unsigned long long* d_n_fallback, cudaStream_t st) {
+    HitSink hs{hitbits, words_per_k, num};
+    CUDA_TRY(cudaMemsetAsync(d_n_fallback, 0, 8, st));
+    k_apply_hits<<<148u * 4u, 256, 0, st>>>(db, present, d_n_present, gate_none, hs, hoff, hits, fallback, d_n_fallback);
+    CUDA_TRY(cudaGetLastError());
+    // whatever had no list (none, usually) is expanded on the fly
+    k_expand_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, fallback, d_n_fallback, gate_none, hs);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_collect_hits(const DbView& db, uint32_t* hoff, uint32_t* hits, unsigned long long cap_words, unsigned long long* d_cursor,
+                        cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 8, st));
+    if (!db.nd) return MLG_OK;
+    k_collect_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, hoff, hits, cap_words, d_cursor);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }

@@ -464,3 +464,22 @@ def test_superkmer_adversarial_minimizers(ctx):
         q.close()
     assert ref["n_intersect"] > 500
     db.close()
+
+
+@pytest.mark.parametrize("mode", ["off", "tiny_buffer"])
+def test_hit_list_fallbacks(ctx, workload, monkeypatch, mode):
+    """the per-k-mer hit lists are precomputed at database build; without them (MLG_PRECOMPUTE_HITS=0), or for the
+    k-mers that did not fit the buffer, the same expansion runs on the fly at query time"""
+    w = workload
+    if mode == "off":
+        monkeypatch.setenv("MLG_PRECOMPUTE_HITS", "0")
+    else:
+        monkeypatch.setenv("MLG_HIT_CAP_WORDS", "4000")      # room for a few hundred of the ~60000 k-mers
+    db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
+    for gate in ("exact", "none"):
+        q = db.query(2, gate, True)
+        q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+        res = q.finish()
+        _check(res, q.intersection(), *w["refs"][gate], tag=(mode, gate))
+        q.close()
+    db.close()
