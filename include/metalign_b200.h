@@ -125,6 +125,12 @@ int mlg_query_sync(mlg_query* q);
  * derive presence from the summed table. */
 int mlg_query_counts_export(mlg_query* q, uint8_t** d_counts, uint64_t* n_counts);
 int mlg_query_counts_import(mlg_query* q);
+/* the same seam in sparse form (the counter table is >99.9 % zeros): *d_entries = device array of one 64-bit entry per
+ * non-zero counter, index | min(count, ci_min) << 32, work joined; the caller all-gathers the ranks' arrays and hands
+ * every OTHER rank's array to mlg_query_counts_merge_sparse(), which adds it into this rank's counters.  Entries with
+ * count 0 (padding) are ignored.  After the first merge no more reads can be pushed. */
+int mlg_query_counts_export_sparse(mlg_query* q, uint64_t** d_entries, uint64_t* n_entries);
+int mlg_query_counts_merge_sparse(mlg_query* q, const uint64_t* d_entries, uint64_t n_entries);
 /* num/den: int64 [G*nk]; ci: double [G*nk] (num/den where num > 0, else 0.0); any pointer may be NULL */
 int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect);
 /* after finish: I as (hi,lo) canonical keys in increasing order; writes at most cap pairs, *n = |I| */

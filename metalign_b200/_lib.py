@@ -69,6 +69,8 @@ SIGNATURES = {
     "mlg_query_sync": (C.c_int, [_vp]),
     "mlg_query_counts_export": (C.c_int, [_vp, _pp, C.POINTER(C.c_uint64)]),
     "mlg_query_counts_import": (C.c_int, [_vp]),
+    "mlg_query_counts_export_sparse": (C.c_int, [_vp, _pp, C.POINTER(C.c_uint64)]),
+    "mlg_query_counts_merge_sparse": (C.c_int, [_vp, _u64p, C.c_uint64]),
     "mlg_query_finish": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.POINTER(C.c_uint64)]),
     "mlg_query_intersection": (C.c_int, [_vp, _u64p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mlg_query_stats": (C.c_int, [_vp, C.POINTER(Stats)]),

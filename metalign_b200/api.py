@@ -196,6 +196,15 @@ class Query:
         check(_lib.lib().mlg_query_counts_export(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def counts_export_sparse(self):
+        """(device pointer, n) of this rank's non-zero counters as uint64 entries: index | min(count, ci_min) << 32."""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().mlg_query_counts_export_sparse(self._h, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def counts_merge_sparse(self, d_entries_ptr: int, n: int):
+        check(_lib.lib().mlg_query_counts_merge_sparse(self._h, d_entries_ptr, int(n)))
+
     def counts_import(self):
         check(_lib.lib().mlg_query_counts_import(self._h))
 

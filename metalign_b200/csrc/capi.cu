@@ -123,7 +123,8 @@ struct mlg_query {
     std::vector<cudaEvent_t> chunk_events;
     cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr;
     mlg_stats st{};
-    bool finished = false, reduced = false;
+    bool finished = false, reduced = false, merged = false;
+    DevBuf<unsigned long long> sparse;             // this rank's non-zero counters as index | count << 32
     unsigned long long chunk_words = CHUNK_WORDS;   // 64-base words per host->device copy chunk
     // results kept for mlg_query_intersection
     DevBuf<uint32_t> present, touched;
@@ -194,7 +195,7 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
 int check_push(mlg_query* q) {
     if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
     if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
-    if (q->reduced) { mlg_set_error("counters were already reduced; no more reads can be pushed"); return MLG_ERR_STATE; }
+    if (q->reduced || q->merged) { mlg_set_error("counters were already combined across ranks; no more reads can be pushed"); return MLG_ERR_STATE; }
     return ensure_device(q->ctx);
 }
 
@@ -536,6 +537,39 @@ MLG_API int mlg_query_counts_export(mlg_query* q, uint8_t** d_counts, uint64_t* 
     }
     MLG_TRY(mlg_query_sync(q));
     *d_counts = q->cnt8.p; *n_counts = q->db->v.nd;
+    return MLG_OK;
+}
+MLG_API int mlg_query_counts_export_sparse(mlg_query* q, uint64_t** d_entries, uint64_t* n_entries) {
+    if (!q || !d_entries || !n_entries) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
+    if (q->merged || q->reduced) { mlg_set_error("counters were already combined across ranks"); return MLG_ERR_STATE; }
+    MLG_TRY(ensure_device(q->ctx));
+    *d_entries = nullptr; *n_entries = 0;
+    if (!q->touched.p) return MLG_OK;                      // nothing pushed: no non-zero counter
+    cudaStream_t st = q->ctx->s_comp;
+    CUDA_TRY(cudaStreamSynchronize(q->ctx->s_copy));
+    unsigned long long nt = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nt, q->d_scalar.p + 1, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));                   // joins the probe kernels
+    MLG_TRY(q->sparse.ensure(nt));
+    MLG_TRY(launch_pack_touched(q->cnt8.p, q->touched.p, q->d_scalar.p + 1, (uint32_t)q->ci_min, q->sparse.p, st));
+    q->st.gpu_launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *d_entries = reinterpret_cast<uint64_t*>(q->sparse.p); *n_entries = nt;
+    return MLG_OK;
+}
+MLG_API int mlg_query_counts_merge_sparse(mlg_query* q, const uint64_t* d_entries, uint64_t n_entries) {
+    if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
+    if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
+    if (q->reduced) { mlg_set_error("counters were already reduced densely"); return MLG_ERR_STATE; }
+    MLG_TRY(ensure_device(q->ctx));
+    q->merged = true;
+    if (!n_entries) return MLG_OK;
+    if (!d_entries) { mlg_set_error("null entries"); return MLG_ERR_ARG; }
+    if (!q->present.p) { MLG_TRY(q->present.alloc((size_t)q->db->v.nd + 1)); MLG_TRY(q->touched.alloc((size_t)q->db->v.nd + 1)); }
+    MLG_TRY(launch_merge_sparse(q->cnt8.p, reinterpret_cast<const unsigned long long*>(d_entries), n_entries, q->db->v.nd,
+                                (uint32_t)q->ci_min, q->present.p, q->touched.p, q->d_scalar.p, q->ctx->s_comp));
+    q->st.gpu_launches += 1;
     return MLG_OK;
 }
 MLG_API int mlg_query_counts_import(mlg_query* q) {

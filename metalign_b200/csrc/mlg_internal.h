@@ -129,6 +129,10 @@ int launch_pack_ascii(const unsigned char* text, unsigned long long nbases, unsi
 int launch_ascii_to_keys(const unsigned char* text, unsigned long long nslots, uint32_t K, key128* keys, cudaStream_t st);
 
 int launch_clamp_counts(unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min, cudaStream_t st);
+int launch_pack_touched(const unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min,
+                        unsigned long long* out, cudaStream_t st);
+int launch_merge_sparse(unsigned char* cnt8, const unsigned long long* entries, unsigned long long n, uint32_t nd, uint32_t ci_min,
+                        uint32_t* present, uint32_t* touched, unsigned long long* d_cursors, cudaStream_t st);
 int launch_compact_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* d_cursor,
                            cudaStream_t st);
 int launch_expand_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,

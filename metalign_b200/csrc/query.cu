@@ -207,6 +207,40 @@ __global__ void k_clamp_counts(unsigned char* cnt8, const uint32_t* __restrict__
         if (cnt8[e] > ci_min) cnt8[e] = (unsigned char)ci_min;
     }
 }
+// sparse form of a rank's contribution: one 64-bit entry per non-zero counter = index | min(count, ci_min) << 32
+__global__ void k_pack_touched(const unsigned char* __restrict__ cnt8, const uint32_t* __restrict__ touched,
+                               const unsigned long long* __restrict__ d_n, uint32_t ci_min, unsigned long long* out) {
+    const unsigned long long n = *d_n;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t e = touched[i];
+        const uint32_t c = cnt8[e];
+        out[i] = (unsigned long long)e | ((unsigned long long)(c > ci_min ? ci_min : c) << 32);
+    }
+}
+// add another rank's sparse entries into this rank's counters (saturating); a counter that crosses ci_min joins present[]
+__global__ void k_merge_sparse(unsigned char* cnt8, const unsigned long long* __restrict__ entries, unsigned long long n, uint32_t nd,
+                               uint32_t ci_min, uint32_t* present, uint32_t* touched, unsigned long long* cursors) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long en = entries[i];
+        const uint32_t e = (uint32_t)en, c = (uint32_t)(en >> 32);
+        if (c == 0u || e >= nd) continue;
+        uint32_t* wp = reinterpret_cast<uint32_t*>(cnt8) + (e >> 2);
+        const uint32_t sh = (e & 3u) * 8u;
+        uint32_t old = *reinterpret_cast<volatile uint32_t*>(wp);
+        for (;;) {
+            const uint32_t before = (old >> sh) & 0xFFu;
+            const uint32_t after = before + c > 255u ? 255u : before + c;
+            if (after == before) break;
+            const uint32_t assumed = old;
+            old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (after << sh));
+            if (old == assumed) {
+                if (before == 0u) touched[atomicAdd(cursors + 1, 1ull)] = e;
+                if (before < ci_min && after >= ci_min) present[atomicAdd(cursors, 1ull)] = e;
+                break;
+            }
+        }
+    }
+}
 // present[] = indices of the counters >= ci_min; 16 counters per thread and step (the table is almost all zeros)
 __global__ void k_compact_present(const uint4* __restrict__ cnt16, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* cursor) {
     const unsigned long long nvec = ((unsigned long long)nd + 15ull) / 16ull;       // the table is padded to 16 bytes with zeros
@@ -255,6 +289,20 @@ __global__ void k_gather_present_keys(const key128* D_key, const uint32_t* prese
 
 int launch_clamp_counts(unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min, cudaStream_t st) {
     k_clamp_counts<<<148u * 4u, 256, 0, st>>>(cnt8, touched, d_n_touched, ci_min);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_pack_touched(const unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min,
+                        unsigned long long* out, cudaStream_t st) {
+    k_pack_touched<<<148u * 4u, 256, 0, st>>>(cnt8, touched, d_n_touched, ci_min, out);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_merge_sparse(unsigned char* cnt8, const unsigned long long* entries, unsigned long long n, uint32_t nd, uint32_t ci_min,
+                        uint32_t* present, uint32_t* touched, unsigned long long* d_cursors, cudaStream_t st) {
+    if (!n) return MLG_OK;
+    unsigned long long want = (n + 255) / 256;
+    k_merge_sparse<<<(unsigned)(want < 148ull * 8ull ? want : 148ull * 8ull), 256, 0, st>>>(cnt8, entries, n, nd, ci_min, present, touched, d_cursors);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }

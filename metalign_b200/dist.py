@@ -1,8 +1,15 @@
 """Read-sharded multi-GPU run: one process per GPU, database replicated, each rank probes
-its own contiguous share of the reads, then ONE exchange -- a uint8 sum all-reduce (NCCL over NVLink) of
-the per-database-k-mer occurrence counters, each rank's counters clamped to ci_min first -- and the
-per-genome table is derived from the summed counters.  Per-genome tables of shards are never summed:
-the >= ci_min threshold is global and hits have set semantics.
+its own contiguous share of the reads, then ONE exchange step -- the sum over ranks of the per-database-k-mer
+occurrence counters, each rank's counters clamped to ci_min first -- and the per-genome table is derived from
+the summed counters.  Per-genome tables of shards are never summed: the >= ci_min threshold is global and
+hits have set semantics.
+
+The sum comes in two equivalent forms (NCCL over NVLink on GPUs, gloo on CPU):
+  "sparse" (default)  the counter table is >99.9 % zeros, so every rank all-gathers its non-zero counters
+                      (64-bit entries: index | count << 32, a few MB) and adds the other ranks' entries into
+                      its own table;
+  "dense"             one uint8 sum all-reduce of the whole table (|D| bytes, 0.16 GB for the default-scale
+                      database) -- MLG_EXCHANGE=dense.
 
 The reference has nothing to compare with (it is a single process around subprocesses,
 scripts/select_db.py:50-76); this module is the new host-side plumbing, on torch.distributed.
@@ -51,18 +58,64 @@ def allreduce_counts(counts, group=None):
     return counts
 
 
-def reduce_query(query, device: int = 0, group=None) -> None:
-    """The exchange step for a live GPU Query: export -> all-reduce in place -> import."""
+def device_view_i64(ptr: int, n: int, device: int = 0):
+    """torch int64 tensor aliasing n 8-byte words of device memory at ptr (no copy)."""
+    import torch
+
+    class _M:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(_M(), device="cuda:%d" % device)
+
+
+def allgather_sparse(entries, group=None):
+    """entries: 1-D int64 tensor (CPU for gloo, CUDA for NCCL) of this rank's sparse counters.  Returns the list
+    of every rank's entries (zero-padded to the longest; padding has count 0 and is ignored by the merge)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_loc = torch.tensor([entries.numel()], dtype=torch.int64, device=entries.device)
+    sizes = [torch.zeros_like(n_loc) for _ in range(world)]
+    dist.all_gather(sizes, n_loc, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    m = max(max(sizes), 1)
+    send = torch.zeros(m, dtype=torch.int64, device=entries.device)
+    send[:entries.numel()] = entries
+    recv = [torch.empty(m, dtype=torch.int64, device=entries.device) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    return recv, sizes
+
+
+def exchange_mode() -> str:
+    m = os.environ.get("MLG_EXCHANGE", "sparse")
+    if m not in ("sparse", "dense"):
+        raise ValueError("MLG_EXCHANGE must be 'sparse' or 'dense'")
+    return m
+
+
+def reduce_query(query, device: int = 0, group=None, mode: str = None) -> None:
+    """The exchange step for a live GPU Query (see the module docstring for the two forms)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):
         return
-    check_reducible(query_ci_min(query), dist.get_world_size(group))
-    ptr, n = query.counts_export()          # joins the library's streams
-    t = device_view_u8(ptr, n, device)
-    allreduce_counts(t, group)
-    torch.cuda.synchronize(device)          # NCCL ran on torch's stream; the library uses its own
-    query.counts_import()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    check_reducible(query_ci_min(query), world)
+    mode = mode or exchange_mode()
+    if mode == "dense":
+        ptr, n = query.counts_export()          # joins the library's streams
+        t = device_view_u8(ptr, n, device)
+        allreduce_counts(t, group)
+        torch.cuda.synchronize(device)          # NCCL ran on torch's stream; the library uses its own
+        query.counts_import()
+        return
+    ptr, n = query.counts_export_sparse()       # joins the library's streams
+    mine = device_view_i64(ptr, n, device) if n else torch.zeros(0, dtype=torch.int64, device="cuda:%d" % device)
+    recv, sizes = allgather_sparse(mine, group)
+    torch.cuda.synchronize(device)
+    for r in range(world):
+        if r != rank:
+            query.counts_merge_sparse(recv[r].data_ptr(), sizes[r])
+    query.sync()                                # recv buffers may be released after this
 
 
 def query_ci_min(query) -> int:

@@ -123,6 +123,21 @@ class OracleQuery:
         assert counts.size == self.db.num_distinct
         lib().orc_query_import_counts(self._h, _p(counts, C.c_uint8))
 
+    def export_sparse(self) -> np.ndarray:
+        """the sparse form of export_counts(): int64 entries index | count << 32 for the non-zero clamped counters"""
+        c = self.export_counts()
+        idx = np.flatnonzero(c)
+        return (idx.astype(np.int64) | (c[idx].astype(np.int64) << 32))
+
+    def merge_sparse(self, own_dense: np.ndarray, others) -> None:
+        """sum this rank's clamped counters and the other ranks' sparse entries, then import the sum"""
+        tot = own_dense.astype(np.int64)
+        for e in others:
+            e = np.asarray(e, dtype=np.int64)
+            e = e[(e >> 32) != 0]
+            np.add.at(tot, e & 0xFFFFFFFF, e >> 32)
+        self.import_counts(np.minimum(tot, 255).astype(np.uint8))
+
     def finish(self):
         G, nk = self.db.G, len(self.db.ks)
         num = np.zeros((G, nk), dtype=np.int64)

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 from conftest import ROOT
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode="dense"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -32,22 +32,27 @@ def _worker(rank, world, port, out_dir):
     q = OracleQuery(db, ci_min=2)
     q.push_packed(bases, nmask, None, b - a, p.read_len)
     mdist.check_reducible(2, world)
-    counts = torch.from_numpy(q.export_counts())                   # clamped to ci_min
-    assert int(counts.max()) <= 2
-    mdist.allreduce_counts(counts)
-    q.import_counts(counts.numpy())
+    if mode == "dense":
+        counts = torch.from_numpy(q.export_counts())                   # clamped to ci_min
+        assert int(counts.max()) <= 2
+        mdist.allreduce_counts(counts)
+        q.import_counts(counts.numpy())
+    else:
+        own = q.export_counts()
+        recv, sizes = mdist.allgather_sparse(torch.from_numpy(q.export_sparse()))
+        q.merge_sparse(own, [recv[r][:sizes[r]].numpy() for r in range(world) if r != rank])
     res = q.finish()
     np.save(os.path.join(out_dir, "num_%d.npy" % rank), res["num"])
     np.save(os.path.join(out_dir, "ni_%d.npy" % rank), np.array([res["n_intersect"]]))
     tdist.destroy_process_group()
 
 
-def test_two_rank_counter_allreduce_equals_single_run(tmp_path):
+@pytest.mark.parametrize("mode,world", [("dense", 2), ("sparse", 2), ("sparse", 3)])
+def test_two_rank_counter_allreduce_equals_single_run(tmp_path, mode, world):
     import synth
     from oracle.oracle_c import OracleDB, OracleQuery
-    world = 2
-    port = 29500 + (os.getpid() % 400)
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 400) + {"dense": 0, "sparse": 1}[mode] + 2 * world
+    mp.spawn(_worker, args=(world, port, str(tmp_path), mode), nprocs=world, join=True)
     p = synth.params(G=30, n=60, seed=3, len_min=5000, len_max=9000, n_present=6)
     keys = synth.sketch_keys(p)
     bases, nmask = synth.reads_packed(p, 0, 9001)

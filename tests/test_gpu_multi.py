@@ -18,7 +18,7 @@ def _params():
     return synth.params(G=400, n=250, seed=13, len_min=20000, len_max=60000, n_present=50, paired=1)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as tdist
@@ -34,7 +34,7 @@ def _worker(rank, world, port, out_dir):
     db = Database.from_keys(ctx, keys, p.G, p.n, 60, KS)
     q = db.query()
     q.push_packed(bases, nmask, None, b - a, p.read_len)
-    mdist.reduce_query(q, local)
+    mdist.reduce_query(q, local, mode=mode)
     res = q.finish()
     np.save(os.path.join(out_dir, "num_%d.npy" % rank), res["num"])
     np.save(os.path.join(out_dir, "I_%d.npy" % rank), q.intersection())
@@ -42,7 +42,8 @@ def _worker(rank, world, port, out_dir):
     tdist.destroy_process_group()
 
 
-def test_two_gpu_read_sharding_matches_oracle(tmp_path):
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+def test_two_gpu_read_sharding_matches_oracle(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -50,7 +51,7 @@ def test_two_gpu_read_sharding_matches_oracle(tmp_path):
     import synth
     from helpers import oracle_c_run
     world = 2
-    mp.spawn(_worker, args=(world, 29400 + os.getpid() % 500, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29400 + os.getpid() % 500 + (7 if mode == "dense" else 0), str(tmp_path), mode), nprocs=world, join=True)
     p = _params()
     keys = synth.sketch_keys(p)
     bases, nmask = synth.reads_packed(p, 0, NREADS)
