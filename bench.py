@@ -187,6 +187,7 @@ def run_native(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     import torch.distributed as tdist
+    numa = mdist.bind_to_gpu_numa(local) if not os.environ.get("MLG_BENCH_NO_NUMA_BIND") else {"disabled": True}
 
     G = env_int("MLG_BENCH_G", 200_000)
     reads_per_gpu = env_int("MLG_BENCH_READS", 10_000_000)
@@ -350,6 +351,7 @@ def run_native(args):
                          "algorithmic_bytes_rule": "level-1 fetches x %d B + packed bases + N mask (SURVEY.md 8d; layout 1 = minimizer bucketing: one 64-byte bucket-pair fetch per super-k-mer instead of one sector per k-mer)" % bucket_bytes,
                          "sector_per_kmer_equivalent_gbs": (kmers_step * 32 + nbases // 4 + nbases // 8) / (probe_ms / 1e3) / 1e9},
             "clocks": clocks,
+            "host_numa_binding_rank0": numa,
             "wall_ms_per_step": wall_dev * 1e3 / args.steps,
             "exchange_wall_ms_per_step_incl_probe_join": (float(np.mean(exch[args.warmup:args.warmup + args.steps])) * 1e3 if exch else None),
         }

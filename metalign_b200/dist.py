@@ -69,19 +69,31 @@ def device_view_i64(ptr: int, n: int, device: int = 0):
 
 def allgather_sparse(entries, group=None):
     """entries: 1-D int64 tensor (CPU for gloo, CUDA for NCCL) of this rank's sparse counters.  Returns the list
-    of every rank's entries (zero-padded to the longest; padding has count 0 and is ignored by the merge)."""
+    of every rank's entries (zero-padded to the longest; padding has count 0 and is ignored by the merge) and the
+    true lengths."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     n_loc = torch.tensor([entries.numel()], dtype=torch.int64, device=entries.device)
-    sizes = [torch.zeros_like(n_loc) for _ in range(world)]
-    dist.all_gather(sizes, n_loc, group=group)
-    sizes = [int(x.item()) for x in sizes]
+    flat = entries.is_cuda          # NCCL: one flat output buffer per collective; gloo: the list form
+    if flat:
+        sz = torch.empty(world, dtype=torch.int64, device=entries.device)
+        dist.all_gather_into_tensor(sz, n_loc, group=group)
+        sizes = sz.tolist()
+    else:
+        szl = [torch.zeros_like(n_loc) for _ in range(world)]
+        dist.all_gather(szl, n_loc, group=group)
+        sizes = [int(x.item()) for x in szl]
     m = max(max(sizes), 1)
     send = torch.zeros(m, dtype=torch.int64, device=entries.device)
     send[:entries.numel()] = entries
-    recv = [torch.empty(m, dtype=torch.int64, device=entries.device) for _ in range(world)]
-    dist.all_gather(recv, send, group=group)
+    if flat:
+        out = torch.empty(world * m, dtype=torch.int64, device=entries.device)
+        dist.all_gather_into_tensor(out, send, group=group)
+        recv = [out[r * m:(r + 1) * m] for r in range(world)]
+    else:
+        recv = [torch.empty(m, dtype=torch.int64, device=entries.device) for _ in range(world)]
+        dist.all_gather(recv, send, group=group)
     return recv, sizes
 
 
@@ -120,6 +132,48 @@ def reduce_query(query, device: int = 0, group=None, mode: str = None) -> None:
 
 def query_ci_min(query) -> int:
     return getattr(query, "ci_min", 2)
+
+
+def bind_to_gpu_numa(local_gpu: int) -> dict:
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off, so that the pinned host buffers it
+    allocates afterwards (first touch) and its copy-issuing threads are local to that GPU's PCIe root.  With 8
+    ranks streaming reads from host memory, remote-node buffers halve the aggregate host->device rate.
+    Best effort: returns what it did, never raises."""
+    info = {"gpu": local_gpu, "numa_node": None, "cpus": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = local_gpu
+        if vis:
+            try:
+                phys = int(vis.split(",")[local_gpu])
+            except (ValueError, IndexError):
+                phys = local_gpu
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML pads the PCI domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            info.update(numa_node=node, cpus=len(use))
+    except Exception as e:  # noqa: BLE001
+        info["error"] = str(e)
+    return info
 
 
 def init_from_env(backend: str = "nccl"):
