@@ -19,6 +19,17 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data
 
 
+def pinned_array(nbytes: int) -> np.ndarray:
+    """uint8 numpy view of page-locked host memory (mlg_host_alloc); freed when the array is collected"""
+    import weakref
+    p = C.c_void_p()
+    check(_lib.lib().mlg_host_alloc(C.byref(p), int(nbytes)))
+    buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    weakref.finalize(buf, _lib.lib().mlg_host_free, p.value)
+    return arr
+
+
 class Context:
     """One GPU.  One process (host thread) per context."""
 

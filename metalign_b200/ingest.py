@@ -4,7 +4,12 @@ Query.push_ascii.  In the reference this job belongs to KMC (`kmc -fq|-fa`, scri
   -fa  FASTA with one sequence line per record; here every non-header line is taken as its own record, which
        is the same thing for single-line FASTA
 Symbols outside ACGTacgt are left in place: the device treats them as N (they break the k-mer run).
-Vectorised with numpy; a multi-threaded native parser is the next step.
+Two implementations of the same record rules:
+  * `PackedBatches` -- the native multi-threaded reader (csrc/ingest.cpp, include/metalign_b200_ingest.h): inflates /
+    reads, finds the sequence lines and packs them 2 bits per base with N as (start, length) runs, straight into
+    (pinned) host buffers for `Query.push_packed_nruns`.  This is what the drop-in select_db.py uses.
+  * `batches` -- the numpy version (whole file in memory, ASCII batches for `Query.push_ascii`); kept as the
+    independent restatement the native reader is tested against.
 """
 from __future__ import annotations
 
@@ -12,6 +17,92 @@ import gzip
 from typing import Iterator, Tuple
 
 import numpy as np
+
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_INGEST = None
+FASTQ, FASTA = 0, 1
+
+
+def ingest_lib():
+    """libmlg_ingest.so (host-only C++), built on demand"""
+    global _INGEST
+    if _INGEST is None:
+        path = os.path.join(_HERE, "libmlg_ingest.so")
+        src = os.path.join(_HERE, "csrc", "ingest.cpp")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s", "../libmlg_ingest.so"])
+        L = C.CDLL(path)
+        L.mlgi_last_error.restype = C.c_char_p
+        L.mlgi_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.mlgi_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.mlgi_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
+        L.mlgi_close.argtypes = [C.c_void_p]
+        L.mlgi_close.restype = None
+        _INGEST = L
+    return _INGEST
+
+
+class PackedBatches:
+    """Iterate a reads file as packed batches: yields (bases uint8[], nruns uint32[m,2], off uint64[n+1], n_reads).
+    The arrays are views of two alternating buffer sets (so one batch can still be in flight to the GPU while the
+    next is being filled); `alloc(nbytes) -> uint8 ndarray` supplies them (pinned memory from api.pinned_array on a
+    GPU box, numpy otherwise)."""
+
+    def __init__(self, path: str, input_type: str, reads_per_batch: int = 4_000_000, bases_per_batch: int = 0,
+                 threads: int = 0, alloc=None, max_runs: int = 0):
+        self.L = ingest_lib()
+        self.h = C.c_void_p()
+        t = {"fastq": FASTQ, "fasta": FASTA}[input_type]
+        if self.L.mlgi_open(path.encode(), t, int(threads), C.byref(self.h)) != 0:
+            raise IOError(self.L.mlgi_last_error().decode())
+        self.max_reads = int(reads_per_batch)
+        self.max_bases = int(bases_per_batch) or min(self.max_reads * 160, 0xFFFFFF00)
+        self.max_runs = int(max_runs) or max(1024, self.max_bases // 64)
+        alloc = alloc or (lambda nbytes: np.zeros(nbytes, dtype=np.uint8))
+        self.sets = []
+        for _ in range(2):
+            b = alloc(self.max_bases // 4 + 64)
+            r = alloc(self.max_runs * 8).view(np.uint32)
+            o = alloc((self.max_reads + 1) * 8).view(np.uint64)
+            self.sets.append((b, r, o))
+        self.cur = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        b, r, o = self.sets[self.cur]
+        self.cur ^= 1
+        nr, nn = C.c_uint64(), C.c_uint64()
+        rc = self.L.mlgi_next(self.h, b.ctypes.data, b.size, r.ctypes.data, self.max_runs, o.ctypes.data, self.max_reads,
+                              self.max_bases, C.byref(nr), C.byref(nn))
+        if rc < 0:
+            raise IOError(self.L.mlgi_last_error().decode())
+        if rc == 0:
+            raise StopIteration
+        return b, r[:2 * nn.value].reshape(-1, 2), o[:nr.value + 1], nr.value
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.L.mlgi_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return dict(reads=a.value, bases=b.value, text_bytes=c.value)
+
+    def close(self):
+        if self.h:
+            self.L.mlgi_close(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 def _read_all(path: str) -> np.ndarray:

@@ -73,12 +73,18 @@ def run_kmc_steps(args):
     """Replaces kmc + kmc_tools intersect + kmc_dump (select_db.py:43-65): counts the canonical 60-mers of the
     reads that belong to the database sketch; the live query is parked on args for run_cmash_and_cutoff."""
     from . import ingest
-    from .api import Context, Database
+    from .api import Context, Database, pinned_array
     ctx = Context(args.device)
     db = Database.load(ctx, args.db_file)
     query = db.query(ci_min=2, gate=args.gate, count_empty_in_den=True)     # -ci2 (select_db.py:50)
-    for text, off in ingest.batches(args.reads, args.input_type):
-        query.push_ascii(text, off)
+    # the native reader (its worker count = --threads, KMC's -t in the reference) fills one pinned buffer set while
+    # the previous batch is still on its way to the GPU
+    reader = ingest.PackedBatches(args.reads, args.input_type, threads=max(1, int(getattr(args, "threads", 4) or 4)),
+                                  alloc=pinned_array)
+    for bases, nruns, off, n_reads in reader:
+        query.push_packed_nruns(bases, nruns if len(nruns) else None, off, n_reads)
+    query.sync()
+    reader.close()
     args._mlg = (ctx, db, query)
 
 

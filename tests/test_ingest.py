@@ -1,0 +1,155 @@
+"""The native read ingest (csrc/ingest.cpp) against the numpy restatement of the same record rules
+(metalign_b200/ingest.py) and the host codec: FASTQ / FASTA, gzip, CRLF, no trailing newline, empty and long
+reads, lower case, N runs, blocks and batches that cut records anywhere.  No GPU."""
+import gzip
+import os
+import random
+
+import numpy as np
+import pytest
+
+from metalign_b200 import codec, ingest
+
+
+def _write(path, text: str):
+    if str(path).endswith(".gz"):
+        with gzip.open(path, "wt", newline="") as f:
+            f.write(text)
+    else:
+        with open(path, "w", newline="") as f:
+            f.write(text)
+
+
+def _native_reads(path, kind, **kw):
+    rd = ingest.PackedBatches(str(path), kind, **kw)
+    out = []
+    nb = 0
+    for bases, runs, off, n in rd:
+        assert off[0] == 0 and len(off) == n + 1
+        total = int(off[-1])
+        mask = codec.runs_to_nmask(runs, total) if len(runs) else None
+        # runs are sorted, disjoint and inside the batch
+        if len(runs):
+            ends = runs[:, 0].astype(np.int64) + runs[:, 1]
+            assert (runs[:, 1] > 0).all() and ends[-1] <= total and (runs[1:, 0] > ends[:-1]).all()
+        # padding after the last base is zero up to a 16-byte multiple
+        used = (total + 3) // 4
+        assert not bases[used:((used + 15) // 16) * 16 + 16].any()
+        out += codec.unpack_reads(bases, mask, off)
+        nb += 1
+    st = rd.stats()
+    rd.close()
+    assert st["reads"] == len(out)
+    return out, nb
+
+
+def _numpy_reads(path, kind):
+    out = []
+    for text, off in ingest.batches(str(path), kind):
+        s = text.tobytes().decode()
+        out += [s[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+    return out
+
+
+def _norm(r):
+    return "".join(c if c in "ACGT" else "N" for c in r.upper())
+
+
+def _random_reads(rng, n):
+    reads = []
+    for _ in range(n):
+        L = rng.choice([0, 1, 3, 4, 5, 59, 60, 61, 150, 151, 250, 1000])
+        r = [rng.choice("ACGT") for _ in range(L)]
+        for i in range(L):
+            x = rng.random()
+            if x < 0.02:
+                r[i] = rng.choice("NnRYKM.-*")
+            elif x < 0.06:
+                r[i] = r[i].lower()
+        if L and rng.random() < 0.1:
+            a = rng.randrange(L)
+            for i in range(a, min(L, a + rng.randint(1, 80))):
+                r[i] = "N"
+        reads.append("".join(r))
+    return reads
+
+
+@pytest.mark.parametrize("ext,eol,trailing", [("fq", "\n", True), ("fastq.gz", "\n", False), ("fq", "\r\n", True)])
+def test_fastq(tmp_path, monkeypatch, ext, eol, trailing):
+    rng = random.Random(hash((ext, eol)) & 0xFFFF)
+    reads = _random_reads(rng, 700)
+    text = eol.join("@r%d desc\n%s\n+\n%s".replace("\n", eol) % (i, r, "I" * len(r)) for i, r in enumerate(reads))
+    if trailing:
+        text += eol
+    p = tmp_path / ("reads." + ext)
+    _write(p, text)
+    want = [_norm(r) for r in reads]
+    assert [_norm(r) for r in _numpy_reads(p, "fastq")] == want
+    for block, rpb, thr in ((1 << 23, 4_000_000, 0), (97, 50, 3), (4096, 7, 1), (1000, 1000, 16)):
+        monkeypatch.setenv("MLGI_BLOCK_BYTES", str(block))
+        got, nb = _native_reads(p, "fastq", reads_per_batch=rpb, threads=thr, bases_per_batch=max(2000, rpb * 200))
+        assert got == want, (block, rpb, thr)
+        assert nb >= len(reads) // rpb
+
+
+def test_fasta_and_gz(tmp_path, monkeypatch):
+    rng = random.Random(9)
+    reads = [r for r in _random_reads(rng, 400) if r]            # an empty FASTA line is not a record
+    lines = []
+    for i, r in enumerate(reads):
+        lines.append(">seq%d" % i)
+        if i % 17 == 0:
+            lines.append(";comment")
+        if i % 23 == 0:
+            lines.append("")
+        lines.append(r)
+    for name in ("reads.fa", "reads.fna.gz"):
+        p = tmp_path / name
+        _write(p, "\n".join(lines) + ("\n" if name.endswith("fa") else ""))
+        want = [_norm(r) for r in reads]
+        assert [_norm(r) for r in _numpy_reads(p, "fasta")] == want
+        monkeypatch.setenv("MLGI_BLOCK_BYTES", "333")
+        got, _ = _native_reads(p, "fasta", reads_per_batch=33, threads=4, bases_per_batch=40000)
+        assert got == want
+
+
+def test_limits_and_errors(tmp_path):
+    p = tmp_path / "a.fq"
+    _write(p, "@x\n" + "ACGT" * 100 + "\n+\n" + "I" * 400 + "\n")
+    rd = ingest.PackedBatches(str(p), "fastq", reads_per_batch=10, bases_per_batch=100)
+    with pytest.raises(IOError):
+        next(rd)                                   # one read longer than a whole batch
+    rd.close()
+    with pytest.raises(IOError):
+        ingest.PackedBatches(str(tmp_path / "missing.fq"), "fastq")
+    e = tmp_path / "empty.fq"
+    _write(e, "")
+    assert _native_reads(e, "fastq") == ([], 0)
+    # batches are cut by bases as well as by reads
+    q = tmp_path / "b.fq"
+    _write(q, "".join("@r\n%s\n+\n%s\n" % ("ACGTN" * 20, "I" * 100) for _ in range(50)))
+    got, nb = _native_reads(q, "fastq", reads_per_batch=1000, bases_per_batch=1000)
+    assert len(got) == 50 and nb == 5
+
+
+def test_large_parallel_pack_matches_codec(tmp_path):
+    """~6 Mbases through 8 workers: the packed stream and the run list equal codec.pack_reads exactly"""
+    rng = np.random.default_rng(5)
+    n, L = 40000, 150
+    arr = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
+    chars = np.frombuffer(b"ACGT", dtype=np.uint8)[arr]
+    chars[rng.random((n, L)) < 0.001] = ord("N")
+    reads = [bytes(row).decode() for row in chars]
+    p = tmp_path / "big.fq"
+    _write(p, "".join("@r\n%s\n+\n%s\n" % (r, "I" * L) for r in reads))
+    rd = ingest.PackedBatches(str(p), "fastq", reads_per_batch=n + 5, threads=8)
+    bases, runs, off, m = next(rd)
+    assert m == n
+    wb, wm, woff = codec.pack_reads(reads)
+    total = n * L
+    assert np.array_equal(off, woff)
+    assert np.array_equal(bases[: (total + 3) // 4], wb[: (total + 3) // 4])
+    assert np.array_equal(runs, codec.nmask_to_runs(wm, total))
+    with pytest.raises(StopIteration):
+        next(rd)
+    rd.close()
