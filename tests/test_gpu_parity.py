@@ -483,3 +483,74 @@ def test_hit_list_fallbacks(ctx, workload, monkeypatch, mode):
         _check(res, q.intersection(), *w["refs"][gate], tag=(mode, gate))
         q.close()
     db.close()
+
+
+def test_full_size_properties(ctx):
+    """BASELINE.json configs[1] at full size (2e5 genomes x 1000 slots, 10 M x 150 bp reads), where the oracle is too
+    slow to be the checker: size-independent properties of the path instead.
+      (a) batching invariance: one push == the same reads in three pushes (host N-runs path and device path);
+      (b) counting: the k-mers seen >= 2 times when every read is pushed twice == the k-mers seen >= 1 time;
+      (c) strand symmetry: reverse-complementing every read changes nothing (canonical counting);
+      (d) the per-genome numerators never exceed the denominators, and only genomes the reads were simulated
+          from (or strains sharing their sketches) collect more than a handful of k=60 hits."""
+    import torch
+    G, n, nreads, L = 200_000, 1000, 10_000_000, 150
+    p = synth.params(G=G, n=n, seed=20200529, n_present=500, read_len=L)
+    d_keys = torch.empty(G * n * 2, dtype=torch.int64, device="cuda")
+    assert synth.cuda_lib().syn_cuda_gen_sketch_keys(C.byref(p), d_keys.data_ptr(), None) == 0
+    db = Database.from_device_keys(ctx, d_keys.data_ptr(), G, n, 60, KS)
+    del d_keys
+    nbb, nmb = synth.packed_sizes(nreads, L)
+    d_b = torch.empty(nbb, dtype=torch.uint8, device="cuda")
+    d_m = torch.empty(nmb, dtype=torch.uint8, device="cuda")
+    assert synth.cuda_lib().syn_cuda_gen_reads_packed(C.byref(p), 0, nreads, d_b.data_ptr(), d_m.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+
+    def run(pushes, ci_min=2):
+        q = db.query(ci_min, "exact", True)
+        for f in pushes:
+            f(q)
+        r = q.finish()
+        I = q.intersection()
+        q.close()
+        return r, I
+
+    whole, I_whole = run([lambda q: q.push_packed_ptr(d_b.data_ptr(), d_m.data_ptr(), None, nreads, L, device=True)])
+    assert whole["n_kmers"] > 0.9 * nreads * (L - 59) and whole["n_intersect"] > 10000
+    # (a) three host pushes with N as runs; cut at read boundaries that are multiples of 64 bases (16-byte units)
+    hb, hm = d_b.cpu().numpy(), d_m.cpu().numpy()
+    cuts = [0, 3_200_000, 3_200_000 + 4_000_064, nreads]
+    assert all((c * L) % 64 == 0 for c in cuts[:-1])
+
+    def host_push(a, b):
+        nb = (b - a) * L
+        sb = np.ascontiguousarray(hb[a * L // 4: a * L // 4 + ((nb + 63) // 64) * 16 + 16])
+        sm = np.ascontiguousarray(hm[a * L // 8: a * L // 8 + ((nb + 63) // 64) * 8 + 16])
+        runs = codec.nmask_to_runs(sm, nb)
+        return lambda q: q.push_packed_nruns(sb, runs, None, b - a, L)
+
+    parts, I_parts = run([host_push(cuts[i], cuts[i + 1]) for i in range(3)])
+    for k in ("num", "den", "ci"):
+        assert np.array_equal(parts[k], whole[k]), k
+    assert parts["n_kmers"] == whole["n_kmers"] and np.array_equal(I_parts, I_whole)
+    # (b) every read twice, threshold 2 == every read once, threshold 1
+    dev = lambda q: q.push_packed_ptr(d_b.data_ptr(), d_m.data_ptr(), None, nreads, L, device=True)
+    twice, I_twice = run([dev, dev], ci_min=2)
+    once1, I_once1 = run([dev], ci_min=1)
+    assert np.array_equal(twice["num"], once1["num"]) and np.array_equal(I_twice, I_once1)
+    assert twice["n_kmers"] == 2 * whole["n_kmers"]
+    # (c) strand symmetry on the first 1 M reads
+    m = 1_000_000
+    reads = codec.unpack_reads(hb[: m * L // 4 + 16], hm[: m * L // 8 + 16], None, m, L)
+    comp = str.maketrans("ACGTN", "TGCAN")
+    rc_reads = [r.translate(comp)[::-1] for r in reads]
+    b1, m1, o1 = codec.pack_reads(reads)
+    b2, m2, o2 = codec.pack_reads(rc_reads)
+    fwd, I_f = run([lambda q: q.push_packed(b1, m1, o1, m)])
+    rev, I_r = run([lambda q: q.push_packed(b2, m2, o2, m)])
+    assert np.array_equal(fwd["num"], rev["num"]) and np.array_equal(I_f, I_r) and fwd["n_kmers"] == rev["n_kmers"]
+    # (d) sanity of the table
+    assert (whole["num"] <= whole["den"]).all() and (whole["den"][:, -1] >= 1).all()
+    high = np.flatnonzero(whole["num"][:, -1] >= 10)         # genomes with real support at k = 60
+    assert 0 < high.size <= 500 * 3
+    db.close()
