@@ -323,6 +323,14 @@ def run_native(args):
                    if traffic is not None else "no ncu capture for this database size")
     launches = int(sum(s["gpu_launches"] for s in st_dev))
 
+    if layout == 1 and tr and tr.get("layout") == 1:
+        limiter = ("instruction issue, not HBM: the super-k-mer kernel fetches one bucket pair per ~17 k-mers, so DRAM runs at "
+                   "%.0f GB/s while the SMs issue %.0f warp instructions per 32 k-mers at %.0f %% issue-slot utilisation with %.0f %% "
+                   "of the warp slots occupied (ncu, %s); frac is low by construction, see DESIGN.md section 4"
+                   % (tr.get("dram_gbs_under_ncu", 0), tr.get("warp_instructions_per_32_kmers", 0), tr.get("issue_active_pct", 0),
+                      tr.get("warps_active_pct", 0), tr.get("source", "")))
+    else:
+        limiter = "random 32-byte DRAM sectors (one per k-mer behind an L2 prefilter)" if layout == 0 else "see profiles/"
     if rank == 0:
         line = {
             "metric": "read k-mers/sec queried vs CMash DB", "value": value, "unit": "k-mers/s",
@@ -349,7 +357,8 @@ def run_native(args):
                          "finish_stage_ms_per_step": query_ms, "kmers_per_s_kernel_only": kmers_step / (probe_ms / 1e3),
                          "layout": layout, "bucket_fetches_per_step": fetches, "kmers_per_bucket_fetch": kmers_step / max(1, fetches),
                          "algorithmic_bytes_rule": "level-1 fetches x %d B + packed bases + N mask (SURVEY.md 8d; layout 1 = minimizer bucketing: one 64-byte bucket-pair fetch per super-k-mer instead of one sector per k-mer)" % bucket_bytes,
-                         "sector_per_kmer_equivalent_gbs": (kmers_step * 32 + nbases // 4 + nbases // 8) / (probe_ms / 1e3) / 1e9},
+                         "sector_per_kmer_equivalent_gbs": (kmers_step * 32 + nbases // 4 + nbases // 8) / (probe_ms / 1e3) / 1e9,
+                         "limiter": limiter},
             "clocks": clocks,
             "host_numa_binding_rank0": numa,
             "wall_ms_per_step": wall_dev * 1e3 / args.steps,

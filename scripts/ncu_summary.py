@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--kernel", default="k1_")
     ap.add_argument("--kmers", type=float, default=0)
     ap.add_argument("--genomes", type=int, default=0)
+    ap.add_argument("--layout", type=int, default=1)
     ap.add_argument("--write-traffic", default="")
     a = ap.parse_args()
     rows = list(csv.reader(open(a.raw)))
@@ -66,7 +67,12 @@ def main():
         if a.write_traffic and a.kmers:
             out = {"dram_bytes_per_kmer": (rd + wr) / a.kmers, "genomes": a.genomes, "kernel": name.split("(")[0].split("::")[-1],
                    "source": os.path.relpath(a.raw), "kmers_in_capture": a.kmers, "dram_bytes_read": rd, "dram_bytes_write": wr,
-                   "ncu_duration_ms": t_s * 1e3}
+                   "ncu_duration_ms": t_s * 1e3, "layout": a.layout,
+                   "warp_instructions_per_32_kmers": num(d["smsp__inst_executed.sum"]) / (a.kmers / 32),
+                   "issue_active_pct": num(d["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+                   "warps_active_pct": num(d["sm__warps_active.avg.pct_of_peak_sustained_active"]),
+                   "dram_gbs_under_ncu": (rd + wr) / t_s / 1e9,
+                   "top_stalls": {k.replace("smsp__average_warps_issue_stalled_", "").replace("smsp__average_warp_latency_issue_stalled_", "").replace("_per_issue_active.ratio", ""): round(v, 3) for k, v in st[:5]}}
             with open(a.write_traffic, "w") as f:
                 json.dump(out, f, indent=1)
             print("  wrote", a.write_traffic)
