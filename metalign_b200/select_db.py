@@ -123,13 +123,28 @@ def run_cmash_and_cutoff(args, taxid2info):
     return chosen
 
 
+def _inflate(path):
+    with gzip.open(path, "rb") as src:
+        return src.read()
+
+
 def make_db_and_dbinfo(args, organisms_to_include, taxid2info):
-    """Same outputs as select_db.py:99-117: the selected organism files inflated and concatenated, and the subset
-    db_info with its two fixed header lines.  (In-process gzip instead of one `zcat` per genome.)"""
-    with open(args.db, "wb") as out:
-        for organism in organisms_to_include:
-            with gzip.open(args.db_dir + organism, "rb") as src:
-                shutil.copyfileobj(src, out, 1 << 20)
+    """Same outputs as select_db.py:99-117: the selected organism files inflated and concatenated in selection
+    order, and the subset db_info with its two fixed header lines.  The reference starts one `zcat` per genome, one
+    after the other (select_db.py:103-105); here a few threads inflate ahead (zlib releases the GIL) while the
+    main thread writes the results in order -- same bytes out."""
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(1, min(16, int(getattr(args, "threads", 4) or 4)))
+    window = 4 * workers                                   # bounded look-ahead: genomes are MBs each
+    with open(args.db, "wb") as out, ThreadPoolExecutor(max_workers=workers) as pool:
+        pending = []
+        it = iter(organisms_to_include)
+        for organism in it:
+            pending.append(pool.submit(_inflate, args.db_dir + organism))
+            if len(pending) >= window:
+                out.write(pending.pop(0).result())
+        for fut in pending:
+            out.write(fut.result())
     with open(args.dbinfo_out, "w") as out:
         out.writelines(HEADER_LINES)
         for organism in organisms_to_include:
