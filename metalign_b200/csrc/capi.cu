@@ -158,7 +158,7 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
     a.base_words = nwords64 * 2;                                  // buffers cover whole 16-byte units
     a.nmask_words = round_up(nwords64, 2);
     a.cnt8 = q->cnt8.p; a.n_kmers = q->d_nkmers.p;
-    a.ci_min = (uint32_t)q->ci_min; a.present = q->present.p; a.n_present = q->d_scalar.p; a.touched = q->touched.p;
+    a.ci_min = (uint32_t)q->ci_min; a.present = q->present.p; a.n_present = q->d_scalar.p; a.touched = q->touched.p; a.tile_counter = q->d_scalar.p + 3;
     auto launch_range = [&](unsigned long long r0, unsigned long long r1) -> int {
         if (r1 <= r0) return MLG_OK;
         cudaEvent_t e0, e1;

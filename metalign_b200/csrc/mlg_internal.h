@@ -121,6 +121,7 @@ struct ProbeArgs {
     uint32_t* present;                  // nd entries
     unsigned long long* n_present;      // device cursors: [0] of present[], [1] of touched[]
     uint32_t* touched;                  // nd entries: counters that left zero
+    unsigned long long* tile_counter;   // layout 1: next 32-read tile to hand out (zeroed before every launch)
     unsigned long long* n_kmers;        // device accumulators: [0] valid windows, [1] level-1 bucket fetches (layout 1)
 };
 int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaStream_t st);

@@ -575,7 +575,6 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
     SkSlots& slots = *reinterpret_cast<SkSlots*>(smem_raw + sizeof(SkStage));
     WarpQueueSk& wq = *reinterpret_cast<WarpQueueSk*>(smem_raw + sizeof(SkStage) + sizeof(SkSlots));
     __shared__ __align__(8) unsigned long long mbar[WARPS][2];
-    __shared__ unsigned long long s_total;
     __shared__ unsigned long long s_bw0[WARPS][2], s_mw0[WARPS][2];
     __shared__ unsigned s_staged[WARPS][2];
 
@@ -583,14 +582,19 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
     constexpr unsigned K = SK_K;
     const unsigned long long nreads = a.r_end - a.r_begin;
     const unsigned long long ntiles = (nreads + 31) / 32;                 // a tile = the 32 reads of one warp pass
-    const unsigned long long gw = (unsigned long long)blockIdx.x * WARPS + warp, gstride = (unsigned long long)gridDim.x * WARPS;
+    // tiles are handed out dynamically (one global atomic per 32 reads): SMs differ in how fast they get through
+    // their tiles (die, L2 distance), and a static split leaves the fast ones idle at the end
+    auto next_tile = [&]() -> unsigned long long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+        return __shfl_sync(0xFFFFFFFFu, t, 0);
+    };
     const unsigned qshift = 33u - db.bbits;      // pair index = top bbits-1 bits of the minimizer's bucket hash; 2 <= bbits <= 31
     const unsigned long long pol_stream = policy_evict_first();
     const CountSink sink{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
     const uint32_t slot_base = smem_u32(&slots.d[0][0][tid]), wm_base = smem_u32(&slots.wm[0][tid]);
     const uint32_t wm_dump = wm_base + SK_NSLOT * SK_WM_STRIDE;
 
-    if (tid == 0) s_total = 0;
     if (lane == 0) {
         mbar_init(&mbar[warp][0], 1);
         mbar_init(&mbar[warp][1], 1);
@@ -632,12 +636,13 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
     bool have = false;
 
     unsigned it = 0;
-    for (unsigned long long t = gw; t < ntiles; t += gstride, ++it) {
+    unsigned long long t = next_tile(), t_ahead = next_tile();       // the tile being processed and the one staged behind it
+    if (lane == 0) {
+        if (t < ntiles) issue(0, t);
+        if (t_ahead < ntiles) issue(1, t_ahead);
+    }
+    for (; t < ntiles; ++it) {
         const unsigned stage = it & 1u, parity = (it >> 1) & 1u;
-        if (it == 0 && lane == 0) {
-            issue(0, t);
-            if (t + gstride < ntiles) issue(1, t + gstride);
-        }
         __syncwarp();
         mbar_wait(&mbar[warp][stage], parity);
 
@@ -776,7 +781,7 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                             P = min(P, he);
                             wm = min(min(Suf[tt], base12), P);
                         }
-                        fpv[tt] = sk_fp(fpv[tt], he);
+                        fpv[tt] += he;                              // mixed into the fingerprint after the fetches are issued
                         if (tt == 0) { wm_first = wm; sts32(wm_base, wm); }
                         else if (wm != pw) {                       // a new run starts at window tt
                             sts32(min(lst, wm_dump), wm);
@@ -808,6 +813,9 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                     }
                     my_fetch += nrun - 1u;
                 }
+                // fingerprints from the sums (kmer.cuh: sk_fp) while the fetches are in flight
+#pragma unroll
+                for (int tt = 0; tt < 16; ++tt) fpv[tt] = sk_fp(fpv[tt], 0u);
                 cp_async_wait_all();
 
                 // ---- phase B: fingerprints against the half of the held pair that the fingerprint selects
@@ -862,16 +870,18 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
             }
         }
         __syncwarp();
-        if (lane == 0 && t + 2ull * gstride < ntiles) issue(stage, t + 2ull * gstride);
+        // this stage is free again: stage the tile after next into it
+        const unsigned long long t_new = next_tile();
+        if (lane == 0 && t_new < ntiles) issue(stage, t_new);
+        t = t_ahead; t_ahead = t_new;
     }
     queue_drain_sk(wq, warp, lane, db, sink);
 
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(0xFFFFFFFFu, my_valid, o);
     my_fetch = __reduce_add_sync(0xFFFFFFFFu, my_fetch);
-    if (lane == 0 && my_valid) atomicAdd(&s_total, my_valid);
+    // every warp reports for itself: no CTA-wide barrier at the end either
+    if (lane == 0 && my_valid) atomicAdd(a.n_kmers, my_valid);
     if (lane == 0 && my_fetch) atomicAdd(a.n_kmers + 1, (unsigned long long)my_fetch);
-    __syncthreads();
-    if (tid == 0 && s_total) atomicAdd(a.n_kmers, s_total);
 }
 constexpr size_t K1SK_SMEM = sizeof(SkStage) + sizeof(SkSlots) + sizeof(WarpQueueSk);
 
@@ -880,6 +890,7 @@ int launch_probe_sk(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsig
     auto kern = k1_superkmer_probe<HAS_NMASK>;
     static bool once = false;
     if (!once) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1SK_SMEM)); once = true; }
+    CUDA_TRY(cudaMemsetAsync(a.tile_counter, 0, 8, st));
     kern<<<grid, RT, K1SK_SMEM, st>>>(a, db);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
@@ -966,6 +977,11 @@ int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaS
     unsigned grid = (unsigned)(ntiles < want ? ntiles : want);
     if (db.layout == 1) {
         if (db.K != SK_K || db.slots != 8) { mlg_set_error("super-k-mer layout needs K=60 and 8-slot buckets"); return MLG_ERR_STATE; }
+        // persistent: the CTAs that fit (2 per SM) pull 32-read tiles from a global counter
+        const unsigned long long wtiles = (a.r_end - a.r_begin + 31) / 32, res = (unsigned long long)ctx->sm_count * K1_MINCTAS;
+        const unsigned long long need = (wtiles + WARPS - 1) / WARPS;
+        grid = (unsigned)(need < res ? need : res);
+        if (const char* e = getenv("MLG_PROBE_CTAS_PER_SM")) { int x = atoi(e); if (x >= 1 && x <= 64) { unsigned long long w = (unsigned long long)ctx->sm_count * x; grid = (unsigned)(need < w ? need : w); } }
         return a.nmask ? launch_probe_sk<true>(db, a, st, grid) : launch_probe_sk<false>(db, a, st, grid);
     }
     return db.slots == 8 ? launch_probe_s<8>(db, a, st, grid) : launch_probe_s<4>(db, a, st, grid);
