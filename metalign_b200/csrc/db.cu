@@ -117,7 +117,7 @@ __global__ void k_fill_filter(const unsigned long long* h, uint32_t nd, uint32_t
     if (i < nd) atomicOr(&F[filter_word(h[i], nfw)], filter_mask(h[i], fk));
 }
 __global__ void k_fill_t1(const unsigned long long* h, uint32_t nd, uint32_t bbits, const uint32_t* bstart,
-                          uint32_t slots, uint32_t* T1) {
+                          uint32_t slots, uint32_t layout, uint32_t* T1) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nd) return;
     unsigned long long b = hash_bucket(h[e], bbits);
@@ -125,7 +125,9 @@ __global__ void k_fill_t1(const unsigned long long* h, uint32_t nd, uint32_t bbi
     uint32_t c = bstart[b + 1] - bstart[b];
     if (s < slots) {
         uint32_t v = hash_fp(h[e]);
-        if (s == 0 && c > slots) v |= 0x80000000u;   // more entries than slots: probe must take the exact path
+        // more entries than slots: the probe must take the exact path.  Layout 0 flags it in bit 31 of the first slot;
+        // layout 1 needs no flag, it treats every FULL bucket as overflowed
+        if (s == 0 && c > slots && layout == 0) v |= 0x80000000u;
         T1[b * slots + s] = v;
     }
 }
@@ -371,7 +373,7 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         MLG_TRY(exclusive_scan_u32(db->bstart.p, nb, st));
         MLG_TRY(db->T1.alloc(nb * slots_per_bucket + 8));
         CUDA_TRY(cudaMemsetAsync(db->T1.p, 0, (nb * slots_per_bucket + 8) * 4, st));
-        if (nd) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p, slots_per_bucket, db->T1.p);
+        if (nd) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p, slots_per_bucket, v.layout, db->T1.p);
         v.bstart = db->bstart.p; v.T1 = db->T1.p;
         // One-bit-per-key prefilter sized to stay L2-resident: MLG_FILTER_MB MiB at most (default 64), 16 bits per
         // key at most; below 1.5 bits per key it would pass most probes and is left out.

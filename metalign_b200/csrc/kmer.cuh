@@ -159,15 +159,16 @@ MLG_HD unsigned minimizer_bucket_hash(unsigned wmin) { return wmin * MLG_BKT_MUL
 // kernel has both at hand from the minimizer scan).  Swapping strands swaps the two, and the sum does not care.
 // It tells a window from its shifted neighbours -- all a fingerprint has to do; the exact path compares full keys.
 MLG_HD unsigned sk_fp(unsigned h_first, unsigned h_last) {
-    unsigned x = (h_first + h_last) * 0x7FEB352Du;
-    x ^= x >> 15;
-    return (x & 0x7FFFFFFFu) | 1u;       // 31 bits, never 0 (0 = empty slot; bit 31 of a bucket's first word = overflow flag)
+    const unsigned x = (h_first + h_last) * 0x7FEB352Du;      // the high bits of the product are the well-mixed ones
+    return (x >> 1) | 1u;                                     // 31 bits, never 0 (0 = empty slot)
 }
 // Level-1 buckets come in PAIRS in this layout: the minimizer picks the pair (one 64-byte fetch per super-k-mer),
-// bit 30 of the K-mer's own fingerprint picks the half it lives in.  K-mers that share a minimizer -- by descent
+// bit 13 of the K-mer's own fingerprint picks the half it lives in (bit 13 = 8192 = the byte distance of the two
+// halves in the probe kernel's shared-memory slots).  A half whose 8 slots are all taken counts as overflowed
+// (there is no flag bit): its windows go to the exact compare.  K-mers that share a minimizer -- by descent
 // or, with 16-base minimizers and >1e8 keys, by chance -- are thereby spread over 16 slots instead of 8.
 MLG_HD unsigned sk_pair_index(unsigned wmin, unsigned bbits) { return minimizer_bucket_hash(wmin) >> (33u - bbits); }   // 2 <= bbits <= 31
-MLG_HD unsigned sk_half(unsigned fp) { return (fp >> 30) & 1u; }
+MLG_HD unsigned sk_half(unsigned fp) { return (fp >> 13) & 1u; }
 // 64-bit sort / bucket / fingerprint hash of a K-mer in the super-k-mer layout: the top bbits bits are the bucket
 // (2 * pair + half; hash_bucket reads them), the low 31 bits are the fingerprint (hash_fp)
 MLG_HD unsigned long long key_hash_sk(const key128& x, unsigned K, unsigned bbits) {

@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_decode_canon_probe(ProbeArg
 //            16-mer values, both of which this scan produces anyway.  Where the minimum differs from the one
 //            whose pair the lane holds, the new pair is fetched global -> shared by predicated cp.async
 //            (up to SK_MAXCH per block; slot 0 is the pair carried in from the previous block);
-//   phase B  per window: the half of the held pair that bit 30 of the fingerprint selects is read from shared
+//   phase B  per window: the half of the held pair that bit 13 of the fingerprint selects is read from shared
 //            memory (2 x LDS.128) and its 8 slots are compared with the fingerprint.
 // Candidates (fingerprint match, overflowed half, or -- rarely -- a window whose pair found no fetch slot) are
 // rebuilt as canonical keys in a rolled loop and go through a per-warp queue to the exact compare.
@@ -826,11 +826,11 @@ __global__ void __launch_bounds__(RT, K1_MINCTAS) k1_superkmer_probe(ProbeArgs a
                     for (int tt = 0; tt < 16; ++tt) {
                         rd += ((chg >> tt) & 1u) * SK_SLOT_STRIDE;
                         const uint32_t fp = fpv[tt];
-                        const uint32_t ha = rd + ((fp >> 17) & (2u * SK_Q_STRIDE));      // bit 30 of the fingerprint: which half
+                        const uint32_t ha = rd + (fp & (2u * SK_Q_STRIDE));              // bit 13 of the fingerprint: which half
                         const uint4 x = lds128(ha), y = lds128(ha + SK_Q_STRIDE);
-                        bool hit = ((x.x & 0x7FFFFFFFu) == fp) | ((int)x.x < 0);
-                        hit |= (x.y == fp) | (x.z == fp) | (x.w == fp) | (y.x == fp) | (y.y == fp) | (y.z == fp) | (y.w == fp);
-                        candm |= (hit ? 1u : 0u) << tt;
+                        // a match, or a half with no free slot left (it may have overflowed: exact path)
+                        const bool hit = (x.x == fp) | (x.y == fp) | (x.z == fp) | (x.w == fp) | (y.x == fp) | (y.y == fp) | (y.z == fp) | (y.w != 0u);
+                        if (hit) candm |= 1u << tt;
                     }
                     candm &= __brev(vb);              // bit tt of brev(vb) = validity of window tt
                     if (__any_sync(0xFFFFFFFFu, candm != 0u)) {

@@ -554,3 +554,18 @@ def test_full_size_properties(ctx):
     high = np.flatnonzero(whole["num"][:, -1] >= 10)         # genomes with real support at k = 60
     assert 0 < high.size <= 500 * 3
     db.close()
+
+
+def test_superkmer_overfull_pairs(ctx, workload, monkeypatch):
+    """mean load 7.5 per 8-slot half: most halves are full or overflowed, so most windows go through the queue and the
+    exact compare (a full half is treated as overflowed; there is no flag bit in this layout)"""
+    w = workload
+    monkeypatch.setenv("MLG_SK_LOAD", "7.5")
+    db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
+    q = db.query()
+    q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+    res = q.finish()
+    assert res["stats"]["layout"] == 1
+    _check(res, q.intersection(), *w["refs"]["exact"])
+    q.close()
+    db.close()
