@@ -121,13 +121,35 @@ def reduce_query(query, device: int = 0, group=None, mode: str = None) -> None:
         query.counts_import()
         return
     ptr, n = query.counts_export_sparse()       # joins the library's streams
-    mine = device_view_i64(ptr, n, device) if n else torch.zeros(0, dtype=torch.int64, device="cuda:%d" % device)
-    recv, sizes = allgather_sparse(mine, group)
+    dev = "cuda:%d" % device
+    # ONE all-gather of fixed-capacity buffers: word 0 = this rank's entry count, then its entries, zero padding (count 0:
+    # ignored by the merge).  The capacity adapts: if some rank had more entries than fit, every rank sees that in
+    # the gathered counts and the gather is repeated with room for the largest.
+    global _SPARSE_CAP
+    while True:
+        cap = max(_SPARSE_CAP, 1024)
+        send = torch.zeros(cap + 1, dtype=torch.int64, device=dev)
+        send[0] = n
+        if 0 < n <= cap:
+            send[1:n + 1] = device_view_i64(ptr, n, device)
+        out = torch.empty(world * (cap + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, send, group=group)
+        counts = out[::cap + 1].tolist()        # synchronises torch's stream: the gather has landed
+        if max(counts) <= cap:
+            break
+        _SPARSE_CAP = 1 << (int(max(counts)) - 1).bit_length()
+    _SPARSE_CAP = max(1024, 1 << (2 * int(max(counts))).bit_length())     # room for twice what this job needed
+    # (the count words need no masking: read as entries their count field, bits 32.., is zero, and the merge skips those)
     torch.cuda.synchronize(device)
-    for r in range(world):
-        if r != rank:
-            query.counts_merge_sparse(recv[r].data_ptr(), sizes[r])
-    query.sync()                                # recv buffers may be released after this
+    lo, hi = rank * (cap + 1), (rank + 1) * (cap + 1)
+    if lo:
+        query.counts_merge_sparse(out.data_ptr(), lo)                      # every rank before this one ...
+    if hi < out.numel():
+        query.counts_merge_sparse(out.data_ptr() + 8 * hi, out.numel() - hi)   # ... and every rank after it
+    query.sync()                                # `out` may be released after this
+
+
+_SPARSE_CAP = 1 << 18
 
 
 def query_ci_min(query) -> int:
