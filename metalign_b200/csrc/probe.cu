@@ -888,8 +888,13 @@ constexpr size_t K1SK_SMEM = sizeof(SkStage) + sizeof(SkSlots) + sizeof(WarpQueu
 template <bool HAS_NMASK>
 int launch_probe_sk(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
     auto kern = k1_superkmer_probe<HAS_NMASK>;
-    static bool once = false;
-    if (!once) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1SK_SMEM)); once = true; }
+    static bool done[64] = {};          // the attribute is per device
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1SK_SMEM));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
     CUDA_TRY(cudaMemsetAsync(a.tile_counter, 0, 8, st));
     kern<<<grid, RT, K1SK_SMEM, st>>>(a, db);
     CUDA_TRY(cudaGetLastError());
@@ -944,13 +949,23 @@ template <int SLOTS, bool HAS_NMASK, bool USE_FILTER>
 int launch_probe_k(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
     if (db.K == 60) {
         auto kern = k1_decode_canon_probe<SLOTS, HAS_NMASK, 60, USE_FILTER>;
-        static bool once = false;
-        if (!once) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM)); once = true; }
+        static bool done[64] = {};      // the attribute is per device
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
         kern<<<grid, RT, K1_SMEM, st>>>(a, db);
     } else {
         auto kern = k1_decode_canon_probe<SLOTS, HAS_NMASK, 0, USE_FILTER>;
-        static bool once = false;
-        if (!once) { CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM)); once = true; }
+        static bool done[64] = {};      // the attribute is per device
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+            if (dev >= 0 && dev < 64) done[dev] = true;
+        }
         kern<<<grid, RT, K1_SMEM, st>>>(a, db);
     }
     CUDA_TRY(cudaGetLastError());
