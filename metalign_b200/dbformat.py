@@ -69,3 +69,55 @@ def read_keys(path: str) -> np.ndarray:
     pos = h["header_bytes"] + h["names_bytes"]
     pos += (-pos) % 16
     return np.fromfile(path, dtype="<u8", offset=pos, count=2 * h["G"] * h["n"]).reshape(-1, 2)
+
+
+def keys_from_dump_fasta(path: str, K: int, expect_records: int = 0, chunk_bytes: int = 256 << 20) -> np.ndarray:
+    """Keys of the FASTA dump that local_tests/dump_kmers.py:10-14 of the reference writes from the training HDF5:
+    one '>seq<i>' header and one sequence line per sketch slot, in CountEstimator order; the sequence line of an
+    unused slot is empty.  Vectorised and chunked (the default database has 2e8 records, ~14 GB of text)."""
+    from . import codec
+    out = []
+    carry = b""
+    pending_header = False          # a header line has been seen and its sequence line not yet
+    with open(path, "rb") as f:
+        while True:
+            block = f.read(chunk_bytes)
+            last = not block
+            buf = carry + block
+            if not buf:
+                break
+            if last and not buf.endswith(b"\n"):
+                buf += b"\n"
+            cut = buf.rfind(b"\n") + 1
+            carry, buf = buf[cut:], buf[:cut]
+            if buf:
+                a = np.frombuffer(buf, dtype=np.uint8)
+                nl = np.flatnonzero(a == 10)
+                starts = np.concatenate([[0], nl[:-1] + 1])
+                ends = nl.copy()
+                cr = (ends > starts) & (a[np.maximum(ends - 1, 0)] == 13)
+                ends = ends - cr
+                is_hdr = (ends > starts) & (a[np.minimum(starts, a.size - 1)] == ord(">"))
+                # a record = a header line followed by ONE line (possibly empty); anything else is malformed
+                prev_hdr = np.concatenate([[pending_header], is_hdr[:-1]])
+                if (is_hdr & prev_hdr).any() or (~is_hdr & ~prev_hdr & (ends > starts)).any():
+                    raise ValueError("%s: expected alternating header / sequence lines" % path)
+                seq = np.flatnonzero(prev_hdr & ~is_hdr)
+                lens = ends[seq] - starts[seq]
+                if ((lens != 0) & (lens != K)).any():
+                    raise ValueError("%s: sketch k-mer of length other than %d" % (path, K))
+                keys = np.full((seq.size, 2), codec.EMPTY, dtype=np.uint64)
+                full = np.flatnonzero(lens == K)
+                if full.size:
+                    idx = starts[seq[full]][:, None] + np.arange(K)[None, :]
+                    keys[full] = codec.ascii_to_keys(a[idx], K)
+                out.append(keys)
+                pending_header = bool(is_hdr[-1]) if is_hdr.size else pending_header
+            if last:
+                break
+    if pending_header:                  # the file ended right after a header: its (empty) sequence line was cut off
+        out.append(np.full((1, 2), codec.EMPTY, dtype=np.uint64))
+    keys = np.concatenate(out) if out else np.zeros((0, 2), dtype=np.uint64)
+    if expect_records and keys.shape[0] != expect_records:
+        raise ValueError("%s: expected %d records, found %d" % (path, expect_records, keys.shape[0]))
+    return keys

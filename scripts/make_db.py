@@ -29,24 +29,11 @@ def main():
     lo, hi, step = (int(x) for x in a.k_range.split("-"))
     ks = [k for k in range(lo, hi + 1, step) if k <= a.k]
     names = [ln.strip() for ln in open(a.names) if ln.strip()]
-    slots = []
-    with open(a.dump_fasta) as fh:
-        seq = None
-        for ln in fh:
-            if ln.startswith(">"):
-                if seq is not None:
-                    slots.append(seq)
-                seq = ""
-            else:
-                seq = (seq or "") + ln.strip().upper()
-        if seq is not None:
-            slots.append(seq)
     G = len(names)
-    if len(slots) != G * a.n:
-        sys.exit("expected %d records (%d names x %d slots), found %d" % (G * a.n, G, a.n, len(slots)))
-    keys = np.empty((G * a.n, 2), dtype=np.uint64)
-    for i, s in enumerate(slots):
-        keys[i] = codec.kmer_to_key(s)
+    try:
+        keys = dbformat.keys_from_dump_fasta(a.dump_fasta, a.k, expect_records=G * a.n)
+    except ValueError as e:
+        sys.exit(str(e))
     dbformat.write(a.out, keys, names, G, a.n, a.k, ks)
     print("wrote %s: %d genomes x %d slots, K=%d, ks=%s" % (a.out, G, a.n, a.k, ks))
 

@@ -101,3 +101,40 @@ def test_ingest_fastq_and_fasta(tmp_path, gz):
     for text, off in ingest.batches(p, "fasta"):
         reads += [bytes(text[int(off[i]):int(off[i + 1])]).decode() for i in range(off.size - 1)]
     assert reads == ["ACGT", "GGCC", "TTAA", "N"]
+
+
+def test_make_db_from_fasta_dump(tmp_path):
+    """scripts/make_db.py: the FASTA dump local_tests/dump_kmers.py writes (empty line for an unused slot) -> .mlgdb"""
+    import random
+    import subprocess
+    import sys
+    import numpy as np
+    from metalign_b200 import codec, dbformat
+    rng = random.Random(1)
+    G, n, K = 7, 13, 60
+    sk = [["" if rng.random() < 0.2 else "".join(rng.choice("ACGT") for _ in range(K)) for _ in range(n)] for _ in range(G)]
+    names = ["taxid_%d_genomic.fna.gz" % (100 + g) for g in range(G)]
+    dump = tmp_path / "dump.fa"
+    with open(dump, "w") as f:
+        i = 0
+        for g in range(G):
+            for s in sk[g]:
+                f.write(">seq%d\n%s\n" % (i, s))
+                i += 1
+    (tmp_path / "names.txt").write_text("\n".join(names) + "\n")
+    out = tmp_path / "db.mlgdb"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(root, "scripts", "make_db.py"), str(dump), str(tmp_path / "names.txt"), str(out),
+                           "-n", str(n), "-k", str(K)])
+    assert dbformat.read_names(str(out)) == names
+    h = dbformat.read_header(str(out))
+    assert (h["G"], h["n"], h["K"], h["ks"]) == (G, n, K, [30, 40, 50, 60])
+    assert np.array_equal(dbformat.read_keys(str(out)), codec.sketches_to_keys(sk, K))
+    # chunk boundaries anywhere, CRLF, last record empty and unterminated
+    with open(dump, "rb") as f:
+        raw = f.read().replace(b"\n", b"\r\n")
+    raw = raw + b">last\r\n"
+    (tmp_path / "crlf.fa").write_bytes(raw)
+    want = np.concatenate([codec.sketches_to_keys(sk, K), np.full((1, 2), codec.EMPTY, dtype=np.uint64)])
+    for chunk in (7, 64, 1000, 1 << 20):
+        assert np.array_equal(dbformat.keys_from_dump_fasta(str(tmp_path / "crlf.fa"), K, chunk_bytes=chunk), want)
