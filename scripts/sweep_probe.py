@@ -25,7 +25,7 @@ for G in Gs:
         r = q.finish(); st = q.stats(); q.close()
         ms.append(st["ms_probe"])
     t = min(ms[1:])
-    print(json.dumps({"G": G, "slots": st["bucket_bytes"] // 4, "table_MB": st["n_buckets"] * st["bucket_bytes"] / 1e6,
+    print(json.dumps({"G": G, "layout": st["layout"], "fetch_bytes": st["bucket_bytes"], "table_MB": st["n_buckets"] * 32 / 1e6,
                       "probe_ms": t, "Gkmers_s": st["n_kmers"] / t / 1e6, "GBps": st["n_kmers"] * 32 / t / 1e6,
                       "finish_ms": st["ms_query"], "I": st["n_intersect"]}), flush=True)
     db.close()
