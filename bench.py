@@ -323,7 +323,12 @@ def run_native(args):
                    if traffic is not None else "no ncu capture for this database size")
     launches = int(sum(s["gpu_launches"] for s in st_dev))
 
-    if layout == 1 and tr and tr.get("layout") == 1:
+    if layout == 2 and tr and tr.get("layout") == 2:
+        limiter = ("the ALU pipe, not HBM: one bitmap sector per ~%.0f k-mers, so DRAM runs at %.0f GB/s while the SMs issue %.0f warp "
+                   "instructions per 32 k-mers at %.0f %% issue-slot utilisation (ncu, %s); see DESIGN.md section 4"
+                   % (kmers_step / max(1, fetches), tr.get("dram_gbs_under_ncu", 0), tr.get("warp_instructions_per_32_kmers", 0),
+                      tr.get("issue_active_pct", 0), tr.get("source", "")))
+    elif layout == 1 and tr and tr.get("layout") == 1:
         limiter = ("instruction issue, not HBM: the super-k-mer kernel fetches one bucket pair per ~17 k-mers, so DRAM runs at "
                    "%.0f GB/s while the SMs issue %.0f warp instructions per 32 k-mers at %.0f %% issue-slot utilisation with %.0f %% "
                    "of the warp slots occupied (ncu, %s); frac is low by construction, see DESIGN.md section 4"
@@ -343,20 +348,20 @@ def run_native(args):
                 "genomes": G, "sketch_slots": 1000, "reads_per_gpu": reads_per_gpu, "read_len": READ_LEN,
                 "db_distinct_kmers": st_dev[-1]["n_db_distinct"], "intersect": ni,
                 "parallelism": "reads sharded x%d, DB replicated, 1 uint8 all-reduce of the counter table" % world if world > 1 else "single GPU",
-                "l2_policy": "inputs (%.2f GB packed reads) and fingerprint table (%.2f GB) both exceed the 126 MB L2; no flush needed"
-                             % ((nbb + nmb) / 1e9, st_dev[-1]["n_buckets"] * (32 if layout == 1 else bucket_bytes) / 1e9),
+                "l2_policy": "inputs (%.2f GB packed reads) and level-1 table (%.2f GB) both exceed the 126 MB L2; no flush needed"
+                             % ((nbb + nmb) / 1e9, (st_dev[-1]["filter_words"] * 4 if layout == 2 else st_dev[-1]["n_buckets"] * (32 if layout == 1 else bucket_bytes)) / 1e9),
                 "db_build_s": round(t_db, 3),
             },
             "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": int(st_e2e[-1]["h2d_bytes"]) * world,
                     "d2h_bytes_per_step": int(st_e2e[-1]["d2h_bytes"]) * world, "ms_per_step": sec_step_e2e * 1e3,
                     "gbases_per_s": bases_total / sec_step_e2e / 1e9},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k1_superkmer_probe" if int(st_dev[-1]["layout"]) == 1 else "k1_decode_canon_probe", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": {2: "k1_minimizer_probe", 1: "k1_superkmer_probe"}.get(layout, "k1_decode_canon_probe"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch_set": int(alg_bytes), "kernel_ms_per_step": probe_ms,
                          "finish_stage_ms_per_step": query_ms, "kmers_per_s_kernel_only": kmers_step / (probe_ms / 1e3),
                          "layout": layout, "bucket_fetches_per_step": fetches, "kmers_per_bucket_fetch": kmers_step / max(1, fetches),
-                         "algorithmic_bytes_rule": "level-1 fetches x %d B + packed bases + N mask (SURVEY.md 8d; layout 1 = minimizer bucketing: one 64-byte bucket-pair fetch per super-k-mer instead of one sector per k-mer)" % bucket_bytes,
+                         "algorithmic_bytes_rule": "level-1 fetches x %d B + packed bases + N mask (SURVEY.md 8d, minimizer bucketing: layout 2 = one 32-byte sector of the exact minimizer bitmap per super-k-mer, layout 1 = one 64-byte fingerprint-bucket pair per super-k-mer, layout 0 = one sector per k-mer)" % bucket_bytes,
                          "sector_per_kmer_equivalent_gbs": (kmers_step * 32 + nbases // 4 + nbases // 8) / (probe_ms / 1e3) / 1e9,
                          "limiter": limiter},
             "clocks": clocks,

@@ -64,7 +64,7 @@ typedef struct mlg_stats {
     uint64_t n_db_entries;   /* non-empty sketch slots */
     uint64_t n_db_distinct;  /* |D|: distinct canonical sketch k-mers */
     uint64_t n_buckets;      /* level-1 fingerprint buckets */
-    uint32_t bucket_bytes;   /* bytes per level-1 fetch: one 16/32-byte bucket (layout 0) or one 64-byte bucket pair (layout 1) */
+    uint32_t bucket_bytes;   /* bytes per level-1 fetch: one 16/32-byte bucket (layout 0), one 64-byte bucket pair (layout 1), one 32-byte sector of the minimizer bitmap (layout 2) */
     uint32_t gpu_launches;   /* kernels of this library launched for this query so far */
     uint64_t h2d_bytes;      /* host->device bytes copied for this query */
     uint64_t d2h_bytes;      /* device->host bytes copied for this query */
@@ -72,8 +72,8 @@ typedef struct mlg_stats {
     double ms_query;         /* CUDA-event duration of the finish stage (compact, expand, popcount, finalize) */
     uint32_t probe_launches; /* number of probe kernel launches in ms_probe */
     uint32_t filter_words;   /* L2 prefilter: number of 32-bit words, 0 = no prefilter */
-    uint64_t n_bucket_fetches; /* level-1 buckets fetched from HBM: one per k-mer in layout 0, one per super-k-mer in layout 1 */
-    uint32_t layout;         /* 0 = bucket by hash of the whole k-mer (+ L2 prefilter), 1 = bucket by minimizer (super-k-mers) */
+    uint64_t n_bucket_fetches; /* level-1 fetches from HBM: one per k-mer in layout 0, one per super-k-mer in layouts 1 and 2 */
+    uint32_t layout;         /* 0 = bucket by hash of the whole k-mer (+ L2 prefilter), 1 = fingerprint bucket pair by minimizer, 2 = exact bitmap over minimizer values (K = 60 default) */
     uint32_t reserved;
 } mlg_stats;
 

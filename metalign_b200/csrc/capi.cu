@@ -376,7 +376,7 @@ MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode,
         if (mb >= 0.25 && mb <= 4096) q->chunk_words = std::max<unsigned long long>(1024, (unsigned long long)(mb * 65536.0));
     }
     q->st.n_db_entries = db->v.np; q->st.n_db_distinct = db->v.nd;
-    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.layout == 1 ? 64u : db->v.slots * 4;   // layout 1 fetches bucket PAIRS
+    q->st.n_buckets = db->v.nbuckets; q->st.bucket_bytes = db->v.layout == 2 ? 32u : db->v.layout == 1 ? 64u : db->v.slots * 4;   // layout 1 fetches bucket PAIRS, layout 2 one sector of the minimizer bitmap
     q->st.filter_words = db->v.nfw; q->st.layout = db->v.layout;
     guard.q = nullptr;
     *out = q;
@@ -625,7 +625,7 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     CUDA_TRY(cudaGetLastError());
     q->n_present = (uint32_t)ni;
     q->st.n_kmers = nk_host; q->st.n_intersect = ni;
-    q->st.n_bucket_fetches = v.layout == 1 ? nk_host2[1] : nk_host;
+    q->st.n_bucket_fetches = v.layout >= 1 ? nk_host2[1] : nk_host;
     q->st.d2h_bytes += 16;
     // timings
     float ms = 0; double probe_ms = 0;

@@ -102,7 +102,24 @@ __global__ void k_flag_heads(const key128* a, uint32_t n, unsigned char* flag) {
 }
 __global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, uint32_t layout, uint32_t bbits, unsigned long long* h) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) h[i] = layout == 1 ? key_hash_sk(a[i], K, bbits) : key_hash(a[i], K);
+    if (i < n) h[i] = layout == 2 ? key_hash_mz(a[i], K) : layout == 1 ? key_hash_sk(a[i], K, bbits) : key_hash(a[i], K);
+}
+// layout 2: level-1 bits of the identities of every K-mer's leftmost and rightmost minimum (kmer.cuh), and the alias
+// entries of the K-mers whose two identities differ (pass 0 counts them, pass 1 writes them)
+__global__ void k_fill_mzbits(const key128* D, uint32_t nd, uint32_t K, uint32_t fbits, uint32_t* MB, int pass,
+                              unsigned long long* alias_z, uint32_t* alias_i, unsigned long long* counter) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    unsigned long long zL, zR;
+    key_mz(D[i], K, &zL, &zR);
+    if (pass == 0) {
+        const unsigned long long bl = mz_bit_index(zL, fbits), br = mz_bit_index(zR, fbits);
+        atomicOr(&MB[bl >> 5], 1u << (bl & 31ull));
+        if (zR != zL) { atomicOr(&MB[br >> 5], 1u << (br & 31ull)); atomicAdd(counter, 1ull); }
+    } else if (zR != zL) {
+        const unsigned long long j = atomicAdd(counter, 1ull);
+        alias_z[j] = zR; alias_i[j] = i;
+    }
 }
 __global__ void k_gather_key(const key128* src, const uint32_t* idx, uint32_t n, key128* dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,6 +242,11 @@ void choose_buckets(DbView& v, uint32_t nd) {
         slots_per_bucket = 8; load = 1.25; bbits = 2;
         if (const char* s = getenv("MLG_SK_LOAD")) { double x = atof(s); if (x > 0.01 && x <= 8) load = x; }
     }
+    if (v.layout == 2) {
+        // the bucket index only serves the exact compare of the few super-k-mers whose minimizer is in the database
+        slots_per_bucket = 8; load = 2.5; bbits = 1;
+        if (const char* s = getenv("MLG_MZ_LOAD")) { double x = atof(s); if (x > 0.01 && x <= 64) load = x; }
+    }
     while (bbits < 31 && (double)(1ull << bbits) * load < (double)nd) ++bbits;
     v.nbuckets = 1ull << bbits; v.bbits = bbits; v.slots = slots_per_bucket;
 }
@@ -251,10 +273,10 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
     struct Guard { mlg_db* d; ~Guard() { if (d) delete d; } } guard{db};
     DbView& v = db->v;
     v.G = G; v.n = n; v.K = K; v.nk = nk;
-    // Metalign's K = 60 gets the super-k-mer layout (bucket by minimizer); other K keep the whole-k-mer hash layout.
-    // MLG_LAYOUT=0 forces the latter (A/B measurements).
-    v.layout = (K == 60) ? 1u : 0u;
-    if (const char* s = getenv("MLG_LAYOUT")) { int x = atoi(s); if (x == 0) v.layout = 0; }
+    // Metalign's K = 60 gets the minimizer-bitmap layout (kmer.cuh); other K keep the whole-k-mer hash layout.
+    // MLG_LAYOUT=0 / 1 force the whole-k-mer hash layout / the fingerprint-pair super-k-mer layout (A/B measurements).
+    v.layout = (K == 60) ? 2u : 0u;
+    if (const char* s = getenv("MLG_LAYOUT")) { int x = atoi(s); if (x == 0 || (x == 1 && K == 60)) v.layout = (uint32_t)x; }
     for (uint32_t i = 0; i < MLG_MAX_KS; ++i) v.ks[i] = i < nk ? ks[i] : 0;
 
     // 1. non-empty slots
@@ -371,9 +393,11 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         CUDA_TRY(cudaMemsetAsync(db->bstart.p, 0, (nb + 1) * 4, st));
         if (nd) k_hbucket_hist<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p);
         MLG_TRY(exclusive_scan_u32(db->bstart.p, nb, st));
-        MLG_TRY(db->T1.alloc(nb * slots_per_bucket + 8));
-        CUDA_TRY(cudaMemsetAsync(db->T1.p, 0, (nb * slots_per_bucket + 8) * 4, st));
-        if (nd) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p, slots_per_bucket, v.layout, db->T1.p);
+        // layout 2 has no fingerprint table: its level 1 is the minimizer bitmap
+        const unsigned long long t1_words = v.layout == 2 ? 8ull : nb * slots_per_bucket + 8;
+        MLG_TRY(db->T1.alloc(t1_words));
+        CUDA_TRY(cudaMemsetAsync(db->T1.p, 0, t1_words * 4, st));
+        if (nd && v.layout != 2) k_fill_t1<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, bbits, db->bstart.p, slots_per_bucket, v.layout, db->T1.p);
         v.bstart = db->bstart.p; v.T1 = db->T1.p;
         // One-bit-per-key prefilter sized to stay L2-resident: MLG_FILTER_MB MiB at most (default 64), 16 bits per
         // key at most; below 1.5 bits per key it would pass most probes and is left out.
@@ -387,10 +411,40 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             if (nfw > 0xFFFFFFF0ull) nfw = 0xFFFFFFF0ull;
             if ((double)nfw * 32.0 < 1.5 * (double)nd) nfw = 0;
         }
+        if (v.layout == 2) {
+            // level-1 bit array: at least 32 bits per K-mer (<= 3 % of the bits set = the false-positive rate of a run),
+            // 2^20 .. 2^36 bits
+            uint32_t fbits = 20;
+            while (fbits < 36 && (1ull << fbits) < 32ull * nd) ++fbits;
+            if (const char* s = getenv("MLG_MZ_FBITS")) { int x = atoi(s); if (x >= 10 && x <= 36) fbits = (uint32_t)x; }
+            v.fbits = fbits;
+            nfw = 1ull << (fbits - 5);
+        }
         v.nfw = (uint32_t)nfw; v.F = nullptr;
         v.fk = ((double)nfw * 32.0 >= 3.0 * (double)nd) ? 2u : 1u;     // two probe bits pay off above ~3 bits per key
         if (const char* s = getenv("MLG_FILTER_K")) { int x = atoi(s); if (x == 1 || x == 2) v.fk = (uint32_t)x; }
-        if (nfw) {
+        if (v.layout == 2) {
+            MLG_TRY(db->F.alloc(nfw));
+            CUDA_TRY(cudaMemsetAsync(db->F.p, 0, nfw * 4, st));
+            v.F = db->F.p;
+            v.n_alias = 0; v.alias_z = nullptr; v.alias_i = nullptr;
+            if (nd) {
+                CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 8, st));
+                k_fill_mzbits<<<nblk(nd), TPB, 0, st>>>(db->D_key.p, nd, K, v.fbits, db->F.p, 0, nullptr, nullptr, d_cnt.p);
+                unsigned long long na = 0;
+                CUDA_TRY(cudaMemcpyAsync(&na, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (na) {
+                    DevBuf<unsigned long long> az; DevBuf<uint32_t> ai;
+                    MLG_TRY(az.alloc(na)); MLG_TRY(ai.alloc(na));
+                    MLG_TRY(db->alias_z.alloc(na)); MLG_TRY(db->alias_i.alloc(na));
+                    CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 8, st));
+                    k_fill_mzbits<<<nblk(nd), TPB, 0, st>>>(db->D_key.p, nd, K, v.fbits, db->F.p, 1, az.p, ai.p, d_cnt.p);
+                    MLG_TRY(sort_pairs_u64(az.p, db->alias_z.p, ai.p, db->alias_i.p, (uint32_t)na, 0, 64, st));
+                    v.n_alias = (uint32_t)na; v.alias_z = db->alias_z.p; v.alias_i = db->alias_i.p;
+                }
+            }
+        } else if (nfw) {
             MLG_TRY(db->F.alloc(nfw));
             CUDA_TRY(cudaMemsetAsync(db->F.p, 0, nfw * 4, st));
             k_fill_filter<<<nblk(nd), TPB, 0, st>>>(hsorted.p, nd, (uint32_t)nfw, v.fk, db->F.p);

@@ -184,3 +184,60 @@ MLG_HD unsigned long long key_hash_sk(const key128& x, unsigned K, unsigned bbit
     const unsigned long long bucket = 2ull * sk_pair_index(best, bbits) + sk_half(fp);
     return (bucket << (64u - bbits)) | fp;
 }
+
+// ---- minimizer-bitmap layout (K >= MLG_MZ_M; db.layout == 2) -------------------------------------------
+// With 16-base minimizers and >1e8 database K-mers the 2^32 minimizer values are saturated (window minima crowd the
+// low 1/45 of the value range), so a minimizer alone says nothing about membership.  This layout uses 32-BASE
+// minimizers, made of two 16-base halves so that everything stays in 32-bit words:
+//   * for the 32-mer at position p of a K-mer let a = its first 16 bases and b = the REVERSE COMPLEMENT of its last 16
+//     bases (both one word, first base most significant).  On the other strand the same 32-mer has (a, b) swapped.
+//   * order: mz_order(a, b) = low 26 bits of (a + b) * MLG_MZ_ORD_MULT -- symmetric, so both strands agree.  The
+//     minimizer of a K-mer is the 32-mer of smallest order, ties to the LEFTMOST position in reading direction.
+//     The probe kernel computes (order << 6 | position) with two multiply-adds (the multiplier carries the << 6, the
+//     position rides in the addend), so a plain unsigned min yields the minimum, the tie-break AND where it is.
+//   * identity: mz_ident(a, b), a 64-bit mix of the unordered pair {a, b}, i.e. of the canonical 32-mer.  Level 1 is
+//     a bit array indexed by the low bits of it: a run of windows sharing a minimizer (a super-k-mer) whose bit is
+//     clear contains no database K-mer, decided by ONE 32-byte DRAM sector and no per-window compare.  2^64 identities
+//     do not saturate; false positives are the bit density (<= 1/32 by the sizing rule in db.cu).
+//   * a database K-mer x is filed under the identity of its leftmost minimum (what a read carrying x forward finds);
+//     a read carrying rc(x) finds x's RIGHTMOST minimum.  The two differ only when the order ties between 32-mers of
+//     different content (~4e-7 of the K-mers); those K-mers get a second bit and an entry in a small alias table.
+#define MLG_MZ_M 32u
+#define MLG_MZ_ORD_MULT 0x9E3779B1u
+MLG_HD unsigned mz_order(unsigned a, unsigned b) { return ((a + b) * MLG_MZ_ORD_MULT) & 0x03FFFFFFu; }
+MLG_HD unsigned mz_mix(unsigned t) { t ^= t >> 16; t *= 0x7FEB352Du; t ^= t >> 15; return t; }
+// low word: bit index inside the level-1 array (plus the low bits of the high word for arrays above 2^32 bits);
+// high word: bucket of the exact-compare index (its top bbits bits)
+MLG_HD unsigned mz_ident_lo(unsigned a, unsigned b) {
+    const unsigned lo = a < b ? a : b, hi = a < b ? b : a;
+    return mz_mix(lo * 0x9E3779B1u + hi * 0x85EBCA6Bu);
+}
+MLG_HD unsigned mz_ident_hi(unsigned a, unsigned b) {
+    const unsigned lo = a < b ? a : b, hi = a < b ? b : a;
+    return mz_mix(lo * 0xC2B2AE35u + hi * 0x27D4EB2Fu + 0x165667B1u);
+}
+MLG_HD unsigned long long mz_ident(unsigned a, unsigned b) { return ((unsigned long long)mz_ident_hi(a, b) << 32) | mz_ident_lo(a, b); }
+MLG_HD unsigned long long mz_bit_index(unsigned long long ident, unsigned fbits) {       // 5 <= fbits <= 36
+    return fbits >= 64 ? ident : (ident & ((1ull << fbits) - 1ull));
+}
+MLG_HD unsigned mz_bucket(unsigned long long ident, unsigned bbits) { return (unsigned)(ident >> 32) >> (32u - bbits); }   // 1 <= bbits <= 31
+// identities of the leftmost and the rightmost minimum of a K-mer (bottom-aligned key), K >= 32
+MLG_HD void key_mz(const key128& x, unsigned K, unsigned long long* zL, unsigned long long* zR) {
+    unsigned best = 0xFFFFFFFFu, aL = 0, bL = 0, aR = 0, bR = 0;
+    for (unsigned p = 0; p + MLG_MZ_M <= K; ++p) {
+        const unsigned a = (unsigned)key_shr(x, 2 * (K - 16 - p)).lo;
+        const unsigned c = (unsigned)key_shr(x, 2 * (K - 32 - p)).lo;
+        const unsigned b = rev2_32h(~c);
+        const unsigned o = mz_order(a, b);
+        if (o < best) { best = o; aL = a; bL = b; aR = a; bR = b; }
+        else if (o == best) { aR = a; bR = b; }
+    }
+    *zL = mz_ident(aL, bL);
+    *zR = mz_ident(aR, bR);
+}
+// sort / bucket hash of a K-mer in this layout: the identity of its leftmost minimum (K-mers of one minimizer adjacent)
+MLG_HD unsigned long long key_hash_mz(const key128& x, unsigned K) {
+    unsigned long long zL, zR;
+    key_mz(x, K, &zL, &zR);
+    return zL;
+}

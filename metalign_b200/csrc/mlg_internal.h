@@ -86,8 +86,14 @@ struct DbView {
     const uint32_t* F;
     uint32_t nfw;
     uint32_t fk;                 // bits per key in the prefilter (1 or 2)
-    // 0: bucket = hash of the whole k-mer (+ L2 prefilter); 1: bucket = minimizer of the k-mer (super-k-mer layout, K = 60)
+    // 0: bucket = hash of the whole k-mer (+ L2 prefilter); 1: fingerprint bucket pair by 16-base minimizer (K = 60);
+    // 2: bit array over the identities of 32-base minimizers (K = 60 default; F holds the 2^fbits bits)
     uint32_t layout;
+    uint32_t fbits;
+    // layout 2: K-mers whose leftmost and rightmost minimum differ, by the identity of the rightmost one (sorted)
+    const unsigned long long* alias_z;
+    const uint32_t* alias_i;     // index in D
+    uint32_t n_alias;
 };
 
 struct mlg_db {
@@ -96,6 +102,8 @@ struct mlg_db {
     DevBuf<key128> P_key;
     DevBuf<uint32_t> P_slot, pidx, rep, bstart, T1;
     DevBuf<uint32_t> F;
+    DevBuf<unsigned long long> alias_z;
+    DevBuf<uint32_t> alias_i;
     DevBuf<key128> D_key;
     DevBuf<uint32_t> hoff, hits;     // precomputed hit lists per k-mer of D (hoff.p == nullptr: not built)
     unsigned long long hit_words = 0;

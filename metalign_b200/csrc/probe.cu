@@ -901,6 +901,482 @@ int launch_probe_sk(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsig
     return MLG_OK;
 }
 
+// ======================================================================================================
+// K1, minimizer-bitmap layout (db.layout == 2, K == 60; definitions in kmer.cuh).  Same lane-per-read walk and
+// per-warp TMA pipelines as the super-k-mer kernel above, but the minimizer is a 32-mer whose (order << 6 | position)
+// value is two multiply-adds, level 1 is a bit array over minimizer IDENTITIES, and there is no per-window compare:
+//   phase A  sliding minimum over the 29 32-mers under each window (van Herk / Gil-Werman on blocks of 16 positions)
+//            and the runs of equal minimizer; values of new runs go to a per-lane list in shared memory;
+//   lookup   for up to MZ_MAXRUN runs per block of 16 windows the lane fetches the two halves of the minimizer from its
+//            copy of the segment in shared memory (the position is in the value), mixes their identity and loads the
+//            bit-array word (predicated LDG);
+//   deferred the words are looked at one block LATER (after the next block's phase A, which hides the DRAM latency):
+//            a run whose bit is set becomes an ITEM (source lane, first window of the block, identity, 16-bit mask of
+//            its valid windows) in a per-warp ring in shared memory.
+// Items are rare (bit density <= 1/32, plus the true hits); the ring is drained 32 at a time, one item per lane: the
+// lane rebuilds the canonical key of each window of the item from the staged bases and compares it with the database
+// k-mers filed under that identity (bucket index on the identity's high word, plus the alias table).
+#ifndef MZ_MINCTAS
+#define MZ_MINCTAS 2
+#endif
+constexpr unsigned MZ_MAXRUN = 4;             // runs per block whose bit-array word is fetched ahead (the carried one + 3 new)
+constexpr unsigned MZ_QCAP = 64;              // per-warp item ring (power of two; holds <= 63: drained whenever 32 are waiting)
+constexpr unsigned MZ_LIST = 16;              // run list rows: a block of 16 windows starts at most 15 new runs (row 0 unused)
+constexpr uint32_t MZ_M64 = MLG_MZ_ORD_MULT << 6;   // the multiplier carries the << 6 of (order << 6 | position)
+struct MzShared {
+    SkStage stg;
+    uint32_t wm[MZ_LIST][RT];                 // [r][thread]: value of the r-th run START of the current block (r >= 1)
+    uint32_t seq[SEGW + 1][RT];               // [word][thread]: the lane's current segment (160 bases, top-aligned words)
+    uint32_t qa[WARPS][MZ_QCAP];              // item: source lane | index of the block's first window in the read << 5
+    uint32_t qk[WARPS][MZ_QCAP];              // item: windows of the block to compare exactly (bit tt = window tt)
+    uint32_t qlo[WARPS][MZ_QCAP];             // item: identity of the minimizer, low / high word
+    uint32_t qhi[WARPS][MZ_QCAP];
+    unsigned long long r0s[WARPS][32];        // stream position (in bases) of each lane's read of the current tile
+};
+constexpr uint32_t MZ_ROW = RT * 4;           // byte stride between rows of wm[] / seq[]
+
+__device__ __forceinline__ uint32_t ldg_bitmap_if(bool p, const uint32_t* ptr) {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.u32 q, %1, 0;\n"
+        "mov.u32 %0, 0;\n"
+        "@q ld.global.nc.L1::no_allocate.b32 %0, [%2];\n"
+        "}\n" : "=r"(r) : "r"((uint32_t)p), "l"(ptr));
+    return r;
+}
+// (order << 6 | position) of the 32-mer at position 16j+i of the current block: first half = bases [16j+i, +16) of
+// loc[], reverse complement of the second half = the 16-mer at 16(j+1)+i seen through rcl[] (see sk_mmer)
+__device__ __forceinline__ uint32_t mz_val(const uint32_t (&loc)[SEGW], const uint32_t (&rcl)[SEGW], int j, int i) {
+    const uint32_t a = fsl(loc[j], loc[j + 1], 2 * i);
+    const int ra = i <= 11 ? 7 - j : 6 - j, ro = i <= 11 ? 11 - i : 27 - i;
+    const uint32_t b = fsl(rcl[ra], rcl[ra + 1], 2 * ro);
+    return b * MZ_M64 + (a * MZ_M64 + (uint32_t)(16 * j + i));
+}
+// exact compare of the windows of one item (one lane): canonical key of every window in `mask` against the database
+// k-mers filed under the identity (zhi:zlo)
+__device__ __noinline__ void mz_process(uint32_t ia, uint32_t mask, uint32_t zlo, uint32_t zhi, const unsigned long long* bsrc,
+                                        unsigned long long base_words, const unsigned long long* r0s, const DbView& db,
+                                        const CountSink& cs) {
+    const uint32_t bucket = zhi >> (32u - db.bbits);
+    const uint32_t s = db.bstart[bucket], e = db.bstart[bucket + 1];
+    uint32_t j0 = 0, j1 = 0;
+    if (db.n_alias) {
+        const unsigned long long z = ((unsigned long long)zhi << 32) | zlo;
+        uint32_t lo = 0, hi = db.n_alias;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (db.alias_z[mid] < z) lo = mid + 1; else hi = mid; }
+        j0 = j1 = lo;
+        while (j1 < db.n_alias && db.alias_z[j1] == z) ++j1;
+    }
+    if (s == e && j0 == j1) return;
+    const unsigned long long p0 = r0s[ia & 31u] + (ia >> 5);
+    while (mask) {
+        const unsigned tt = (unsigned)__ffs((int)mask) - 1u;
+        mask &= mask - 1u;
+        const unsigned long long p = p0 + tt;
+        const unsigned long long q = p >> 5;
+        const unsigned sh = 2u * (unsigned)(p & 31ull);
+        unsigned long long W[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            unsigned long long idx = q + k;
+            if (idx >= base_words) idx = base_words - 1;
+            W[k] = bswap64(bsrc[idx]);
+        }
+        key128 F;                                                   // 64 bases from p, top-aligned
+        F.hi = sh ? ((W[0] << sh) | (W[1] >> (64 - sh))) : W[0];
+        F.lo = sh ? ((W[1] << sh) | (W[2] >> (64 - sh))) : W[1];
+        F = key_shr(F, 128 - 2 * SK_K);                             // the 60-mer, bottom-aligned
+        const key128 G = key_rc(F, SK_K);
+        const key128 cn = key_lt(G, F) ? G : F;
+        bool found = false;
+        for (uint32_t i = s; i < e && !found; ++i) {
+            const key128 d = db.D_key[i];
+            if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); found = true; }
+        }
+        for (uint32_t j = j0; j < j1 && !found; ++j) {
+            const uint32_t i = db.alias_i[j];
+            const key128 d = db.D_key[i];
+            if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); found = true; }
+        }
+    }
+}
+
+template <bool HAS_NMASK>
+__global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a, DbView db) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MzShared& sm = *reinterpret_cast<MzShared*>(smem_raw);
+    SkStage& stg = sm.stg;
+    __shared__ __align__(8) unsigned long long mbar[WARPS][2];
+    __shared__ unsigned long long s_bw0[WARPS][2], s_mw0[WARPS][2];
+    __shared__ unsigned s_staged[WARPS][2];
+
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    constexpr unsigned K = SK_K;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned long long nreads = a.r_end - a.r_begin;
+    const unsigned long long ntiles = (nreads + 31) / 32;                 // a tile = the 32 reads of one warp pass
+    auto next_tile = [&]() -> unsigned long long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+        return __shfl_sync(FULL, t, 0);
+    };
+    const unsigned long long pol_stream = policy_evict_first();
+    const CountSink sink{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
+    const uint32_t wm_base = smem_u32(&sm.wm[0][tid]), seq_base = smem_u32(&sm.seq[0][tid]);
+    const uint32_t* const MB = db.F;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // bit index = identity & (2^fbits - 1): mask of its low word, and of its high word (0 up to 2^32 bits)
+    const uint32_t fmask_lo = db.fbits >= 32u ? 0xFFFFFFFFu : ((1u << db.fbits) - 1u);
+    const uint32_t fmask_hi = db.fbits > 32u ? ((1u << (db.fbits - 32u)) - 1u) : 0u;
+
+    if (lane == 0) {
+        mbar_init(&mbar[warp][0], 1);
+        mbar_init(&mbar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](unsigned stage, unsigned long long t) {
+        const unsigned long long r0 = a.r_begin + t * 32ull;
+        const unsigned long long r1 = (r0 + 32 < a.r_end) ? r0 + 32 : a.r_end;
+        const unsigned long long p0 = a.off ? a.off[r0] : r0 * (unsigned long long)a.read_len;
+        const unsigned long long p1 = a.off ? a.off[r1] : r1 * (unsigned long long)a.read_len;
+        unsigned long long bw0 = (p0 >> 5) & ~1ull;
+        unsigned long long bw1 = ((p1 + 31) >> 5) + 6;
+        if (bw1 > a.base_words) bw1 = a.base_words;
+        bw1 = (bw1 + 1) & ~1ull;
+        unsigned long long mw0 = (p0 >> 6) & ~1ull;
+        unsigned long long mw1 = ((p1 + 63) >> 6) + 4;
+        if (HAS_NMASK) { if (mw1 > a.nmask_words) mw1 = a.nmask_words; mw1 = (mw1 + 1) & ~1ull; }
+        const unsigned long long bytes_b = (bw1 - bw0) * 8ull, bytes_m = HAS_NMASK ? (mw1 - mw0) * 8ull : 0ull;
+        const bool fits = bw1 > bw0 && bytes_b <= WSTAGE_B && bytes_m <= WSTAGE_M;
+        s_bw0[warp][stage] = bw0; s_mw0[warp][stage] = mw0; s_staged[warp][stage] = fits ? 1u : 0u;
+        if (fits) {
+            mbar_expect_tx(&mbar[warp][stage], (uint32_t)(bytes_b + bytes_m));
+            bulk_g2s(&stg.b[warp][stage][0], a.bases + bw0, (uint32_t)bytes_b, &mbar[warp][stage], pol_stream);
+            if (HAS_NMASK && bytes_m) bulk_g2s(&stg.m[warp][stage][0], a.nmask + mw0, (uint32_t)bytes_m, &mbar[warp][stage], pol_stream);
+        } else {
+            mbar_arrive(&mbar[warp][stage]);
+        }
+    };
+
+    unsigned long long my_valid = 0;
+    unsigned my_fetch = 0;
+    // item ring of this warp: head and count, warp-uniform
+    uint32_t qh = 0, qn = 0;
+    const unsigned long long* bsrc = a.bases;
+
+    // the two halves (a, b) of the 32-mer at base P of the lane's segment copy (b = reverse complement of the second half)
+    auto halves_at = [&](uint32_t P, uint32_t& ha, uint32_t& hb) {
+        const uint32_t ad = seq_base + (P >> 4) * MZ_ROW;
+        const uint32_t w0 = lds32(ad), w1 = lds32(ad + MZ_ROW), w2 = lds32(ad + 2u * MZ_ROW);
+        const unsigned sh = 2u * (P & 15u);
+        ha = fsl(w0, w1, sh);
+        hb = rev2_32(~fsl(w1, w2, sh));
+    };
+    // process `cnt` (<= 32) items from the head of the ring, one per lane
+    auto drain = [&](uint32_t cnt) {
+        __syncwarp();
+        if (lane < cnt) {
+            const uint32_t i = (qh + lane) & (MZ_QCAP - 1u);
+            mz_process(sm.qa[warp][i], sm.qk[warp][i], sm.qlo[warp][i], sm.qhi[warp][i], bsrc, a.base_words, &sm.r0s[warp][0], db, sink);
+        }
+        __syncwarp();
+        qh = (qh + cnt) & (MZ_QCAP - 1u);
+        qn -= cnt;
+    };
+    // all 32 lanes call this; lanes with p append one item for the run whose minimizer starts at base P of the segment
+    auto push = [&](bool p, uint32_t ia, uint32_t ik, uint32_t P) {
+        const unsigned ballot = __ballot_sync(FULL, p);
+        if (ballot) {
+            if (p) {
+                uint32_t ha, hb;
+                halves_at(P, ha, hb);
+                const uint32_t i = (qh + qn + __popc(ballot & lt_mask)) & (MZ_QCAP - 1u);
+                sm.qa[warp][i] = ia; sm.qk[warp][i] = ik; sm.qlo[warp][i] = mz_ident_lo(ha, hb); sm.qhi[warp][i] = mz_ident_hi(ha, hb);
+            }
+            qn += __popc(ballot);
+            if (qn >= 32u) drain(32u);
+        }
+    };
+
+    unsigned it = 0;
+    unsigned long long t = next_tile(), t_ahead = next_tile();       // the tile being processed and the one staged behind it
+    if (lane == 0) {
+        if (t < ntiles) issue(0, t);
+        if (t_ahead < ntiles) issue(1, t_ahead);
+    }
+    for (; t < ntiles; ++it) {
+        const unsigned stage = it & 1u, parity = (it >> 1) & 1u;
+        __syncwarp();
+        mbar_wait(&mbar[warp][stage], parity);
+
+        const unsigned long long r = a.r_begin + t * 32ull + lane;
+        const bool active = r < a.r_end;
+        unsigned long long R0 = 0, R1 = 0;
+        if (active) {
+            R0 = a.off ? a.off[r] : r * (unsigned long long)a.read_len;
+            R1 = a.off ? a.off[r + 1] : R0 + a.read_len;
+        }
+        sm.r0s[warp][lane] = R0;
+        const unsigned long long len = R1 - R0;
+        const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
+        const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
+        const unsigned max_seg = __reduce_max_sync(FULL, nseg);
+        const bool staged = s_staged[warp][stage] != 0;
+        bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[warp][stage][0]) - s_bw0[warp][stage] : a.bases;
+        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[warp][stage][0]) - s_mw0[warp][stage] : a.nmask;
+        __syncwarp();
+
+        for (unsigned seg = 0; seg < max_seg; ++seg) {
+            const unsigned c = seg < nseg ? (unsigned)((nw - (unsigned long long)seg * WMAX) < WMAX ? (nw - (unsigned long long)seg * WMAX) : WMAX) : 0u;
+            const unsigned long long s = R0 + (unsigned long long)seg * WMAX;
+
+            uint32_t loc[SEGW];
+            uint32_t nl[5];
+#pragma unroll
+            for (int k = 0; k < (int)SEGW; ++k) loc[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) nl[k] = 0;
+            if (c) {
+                const unsigned long long q = s >> 5;
+                const unsigned sh = 2u * (unsigned)(s & 31ull);
+                unsigned long long W[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    unsigned long long idx = q + k;
+                    if (idx >= a.base_words) idx = a.base_words - 1;
+                    W[k] = bswap64(bsrc[idx]);
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const unsigned long long v = sh ? ((W[k] << sh) | (W[k + 1] >> (64 - sh))) : W[k];
+                    loc[2 * k] = (uint32_t)(v >> 32); loc[2 * k + 1] = (uint32_t)v;
+                }
+                if (HAS_NMASK) {
+                    const unsigned long long qn2 = s >> 6;
+                    const unsigned shn = (unsigned)(s & 63ull);
+                    unsigned long long M[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned long long idx = qn2 + k;
+                        if (idx >= a.nmask_words) idx = a.nmask_words - 1;
+                        M[k] = bswap64(msrc[idx]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const unsigned long long v = shn ? ((M[k] << shn) | (M[k + 1] >> (64 - shn))) : M[k];
+                        if (2 * k < 5) nl[2 * k] = (uint32_t)(v >> 32);
+                        if (2 * k + 1 < 5) nl[2 * k + 1] = (uint32_t)v;
+                    }
+                }
+            }
+            uint32_t v0, v1, v2;
+            {
+                if (HAS_NMASK && __any_sync(FULL, (nl[0] | nl[1] | nl[2] | nl[3] | nl[4]) != 0u)) {
+                    unsigned cover = 1;
+                    while (cover * 2 <= K) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], cover);
+                        nl[4] |= nl[4] << cover;
+                        cover *= 2;
+                    }
+                    const unsigned rest = K - cover;
+                    if (rest) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], rest);
+                        nl[4] |= nl[4] << rest;
+                    }
+                }
+                const uint32_t c0 = c >= 32 ? 0xFFFFFFFFu : (c ? ~(0xFFFFFFFFu >> c) : 0u);
+                const uint32_t c1 = c >= 64 ? 0xFFFFFFFFu : (c > 32 ? ~(0xFFFFFFFFu >> (c - 32)) : 0u);
+                const uint32_t c2 = c >= 96 ? 0xFFFFFFFFu : (c > 64 ? ~(0xFFFFFFFFu >> (c - 64)) : 0u);
+                v0 = ~nl[0] & c0; v1 = ~nl[1] & c1; v2 = ~nl[2] & c2;
+            }
+            my_valid += __popc(v0) + __popc(v1) + __popc(v2);
+            if (__all_sync(FULL, (v0 | v1 | v2) == 0u)) continue;
+
+            // the lane's copy of the segment (minimizer halves are fetched from it by position)
+#pragma unroll
+            for (int k = 0; k < (int)SEGW; ++k) sts32(seq_base + (uint32_t)k * MZ_ROW, loc[k]);
+            sts32(seq_base + SEGW * MZ_ROW, 0u);
+
+            // reverse complement of the segment: the complement of base x sits at base 154 - x of rcl[]
+            uint32_t rcl[SEGW];
+            {
+                uint32_t t160[SEGW + 1];
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) t160[k] = rev2_32(~loc[SEGW - 1 - k]);
+                t160[SEGW] = 0;
+                constexpr unsigned bs = 2u * (160u - (WMAX + K - 1u));
+                static_assert(bs < 32, "alignment shift must stay inside one word");
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) rcl[k] = fsl(t160[k], t160[k + 1], bs);
+            }
+
+            // minimizer state carried from block to block: P = prefix minimum of position block 1 up to index 11
+            uint32_t P = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) P = min(P, mz_val(loc, rcl, 1, i));
+            // the value of the run the lane is in, re-based to the coming block (positions are block-relative), and
+            // whether its bit is set
+            uint32_t held_wm = 0;
+            bool have = false, held_pass = false;
+
+            // what the previous block left to look at once its bit-array words have arrived
+            bool pend = false, pneed0 = false;
+            uint32_t pF0 = 0, pF1 = 0, pF2 = 0, pF3 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pW3 = 0, pbits = 0, pchg = 0, pvm = 0, pnr = 0, pblk = 0;
+            auto consume = [&]() {
+                const bool b0 = pneed0 ? ((pF0 >> (pbits & 31u)) & 1u) : held_pass;
+                const bool b1 = (pnr > 1u) & ((pF1 >> ((pbits >> 8) & 31u)) & 1u);
+                const bool b2 = (pnr > 2u) & ((pF2 >> ((pbits >> 16) & 31u)) & 1u);
+                const bool b3 = (pnr > 3u) & ((pF3 >> ((pbits >> 24) & 31u)) & 1u);
+                held_pass = pnr == 1u ? b0 : pnr == 2u ? b1 : pnr == 3u ? b2 : b3;
+                // windows of run 0..3: [0, c1) [c1, c2) [c2, c3) [c3, 16); sentinels above bit 15 stand in for missing changes
+                uint32_t cc = pchg | 0x70000u;
+                const uint32_t c1 = cc & (0u - cc); cc ^= c1;
+                const uint32_t c2 = cc & (0u - cc); cc ^= c2;
+                const uint32_t c3 = cc & (0u - cc);
+                const uint32_t m0 = (c1 - 1u) & pvm, m1 = (c2 - c1) & pvm, m2 = (c3 - c2) & pvm, m3 = (0x10000u - c3) & pvm;
+                const uint32_t ia = lane | ((seg * WMAX + pblk) << 5);
+                push(b0 & (m0 != 0u), ia, m0, pblk + (pW0 & 63u));
+                push(b1 & (m1 != 0u), ia, m1, pblk + (pW1 & 63u));
+                push(b2 & (m2 != 0u), ia, m2, pblk + (pW2 & 63u));
+                push(b3 & (m3 != 0u), ia, m3, pblk + (pW3 & 63u));
+            };
+
+#pragma unroll 1
+            for (int blk = 0; blk < (int)(WMAX / 16); ++blk) {
+                if (__all_sync(FULL, (v0 | v1 | v2) == 0u)) break;       // nothing valid from here to the end of the segment
+                const uint32_t vb = v0 & 0xFFFF0000u;
+                v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
+                const uint32_t blk16 = (uint32_t)blk * 16u;
+
+                // ---- phase A: window minima and runs of equal minimizer (validity is ignored here: a window that is
+                //      not valid costs at most a wasted lookup; it is masked out of the items)
+                uint32_t chgraw = 0, wm_first = 0;
+                {
+                    uint32_t Suf[16];
+                    {
+                        uint32_t smn = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = 15; i >= 0; --i) { smn = min(smn, mz_val(loc, rcl, 0, i)); Suf[i] = smn; }
+                    }
+                    uint32_t A1 = 0, pw = 0;
+                    uint32_t lst = wm_base + MZ_ROW;              // where the next run's value goes
+#pragma unroll
+                    for (int tt = 0; tt < 16; ++tt) {
+                        uint32_t wm;
+                        if (tt < 4) {                              // window tt: positions tt..15, then block 1 up to index tt + 12
+                            P = min(P, mz_val(loc, rcl, 1, 12 + tt));
+                            wm = min(Suf[tt], P);
+                            if (tt == 3) { A1 = P; P = 0xFFFFFFFFu; }
+                        } else {                                   // positions tt..15, all of block 1, block 2 up to index tt - 4
+                            P = min(P, mz_val(loc, rcl, 2, tt - 4));
+                            wm = min(min(Suf[tt], A1), P);
+                        }
+                        if (tt == 0) wm_first = wm;
+                        else if (wm != pw) {                       // a new run starts at window tt
+                            sts32(lst, wm);
+                            lst += MZ_ROW;
+                            chgraw |= 1u << tt;
+                        }
+                        pw = wm;
+                    }
+                    P -= 16u;                                      // block 2 of this block is block 1 of the next one
+                }
+                // runs 0..3 of the block are looked up; windows of later runs (rare) become items unfiltered
+                uint32_t chg, t3;
+                {
+                    t3 = chgraw;
+                    t3 &= t3 - 1u; t3 &= t3 - 1u; t3 &= t3 - 1u;      // changes beyond the third
+                    chg = chgraw ^ t3;
+                }
+                const uint32_t ovfm = t3 ? (~((t3 & (0u - t3)) - 1u) & 0xFFFFu) : 0u;   // every window from the fourth change on
+                const uint32_t vwin = __brev(vb) & 0xFFFFu;          // bit tt = validity of window tt
+                const unsigned nrun = 1u + __popc(chg);
+                if (__any_sync(FULL, t3 != 0u)) {
+                    const uint32_t ia = lane | ((seg * WMAX + blk16) << 5);
+                    uint32_t rest = t3;
+                    unsigned rr = MZ_MAXRUN;
+                    while (__any_sync(FULL, rest != 0u)) {
+                        const uint32_t low = rest & (0u - rest), nxt = rest ^ low;
+                        const uint32_t upto = nxt ? (nxt & (0u - nxt)) : 0x10000u;
+                        const uint32_t mk = rest ? ((upto - low) & vwin) : 0u;
+                        const uint32_t w = rest ? lds32(wm_base + rr * MZ_ROW) : 0u;
+                        push(mk != 0u, ia, mk, blk16 + (w & 63u));
+                        rest = nxt; ++rr;
+                    }
+                }
+
+                // ---- the previous block's bit-array words have had a whole phase A to arrive
+                if (pend) consume();
+
+                // ---- this block's lookups
+                {
+                    const bool need0 = !have || wm_first != held_wm;
+                    const uint32_t W1 = lds32(wm_base + 1u * MZ_ROW), W2 = lds32(wm_base + 2u * MZ_ROW), W3 = lds32(wm_base + 3u * MZ_ROW);
+                    uint32_t bits = 0;
+                    auto lookup = [&](bool p, uint32_t w, unsigned sl) -> uint32_t {
+                        uint32_t ha, hb;
+                        halves_at(blk16 + (w & 63u), ha, hb);
+                        const uint32_t zlo = mz_ident_lo(ha, hb) & fmask_lo;
+                        uint32_t word = zlo >> 5;
+                        if (fmask_hi) word |= (mz_ident_hi(ha, hb) & fmask_hi) << 27;
+                        bits |= (zlo & 31u) << (8u * sl);
+                        return ldg_bitmap_if(p, MB + word);
+                    };
+                    pF0 = lookup(need0, wm_first, 0);
+                    pF1 = lookup(nrun > 1u, W1, 1);
+                    pF2 = lookup(nrun > 2u, W2, 2);
+                    pF3 = lookup(nrun > 3u, W3, 3);
+                    my_fetch += (need0 ? 1u : 0u) + nrun - 1u;
+                    pW0 = wm_first; pW1 = W1; pW2 = W2; pW3 = W3; pbits = bits;
+                    pneed0 = need0; pnr = nrun; pchg = chg; pvm = vwin & ~ovfm; pblk = blk16; pend = true;
+                    have = true;
+                    held_wm = (nrun == 1u ? wm_first : nrun == 2u ? W1 : nrun == 3u ? W2 : W3) - 16u;
+                }
+                // slide the register windows by one word
+#pragma unroll
+                for (int k = 0; k < (int)SEGW - 1; ++k) loc[k] = loc[k + 1];
+#pragma unroll
+                for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
+            }
+            if (pend) consume();
+        }
+        // items point into this tile's staged bases: finish them before the stage is refilled
+        while (qn) drain(qn < 32u ? qn : 32u);
+        __syncwarp();
+        const unsigned long long t_new = next_tile();
+        if (lane == 0 && t_new < ntiles) issue(stage, t_new);
+        t = t_ahead; t_ahead = t_new;
+    }
+
+    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(FULL, my_valid, o);
+    my_fetch = __reduce_add_sync(FULL, my_fetch);
+    if (lane == 0 && my_valid) atomicAdd(a.n_kmers, my_valid);
+    if (lane == 0 && my_fetch) atomicAdd(a.n_kmers + 1, (unsigned long long)my_fetch);
+}
+constexpr size_t K1MZ_SMEM = sizeof(MzShared);
+
+template <bool HAS_NMASK>
+int launch_probe_mz(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
+    auto kern = k1_minimizer_probe<HAS_NMASK>;
+    static bool done[64] = {};          // the attribute is per device
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1MZ_SMEM));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(a.tile_counter, 0, 8, st));
+    kern<<<grid, RT, K1MZ_SMEM, st>>>(a, db);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+
 // ---------------------------------------------------------------- prep kernels
 __device__ __forceinline__ uint32_t ascii_code(unsigned char c) {
     switch (c) {
@@ -990,6 +1466,17 @@ int launch_probe(const mlg_ctx* ctx, const DbView& db, const ProbeArgs& a, cudaS
     }
     unsigned long long want = (unsigned long long)ctx->sm_count * ctas_per_sm;
     unsigned grid = (unsigned)(ntiles < want ? ntiles : want);
+    if (db.layout == 2) {
+        if (db.K != SK_K || !db.F) { mlg_set_error("minimizer-bitmap layout needs K=60 and its bitmap"); return MLG_ERR_STATE; }
+        // persistent: the CTAs that fit pull 32-read tiles from a global counter
+        const unsigned long long wtiles = (a.r_end - a.r_begin + 31) / 32;
+        const unsigned long long need = (wtiles + WARPS - 1) / WARPS;
+        int per_sm = MZ_MINCTAS;
+        if (const char* e = getenv("MLG_PROBE_CTAS_PER_SM")) { int x = atoi(e); if (x >= 1 && x <= 64) per_sm = x; }
+        const unsigned long long res = (unsigned long long)ctx->sm_count * (unsigned)per_sm;
+        grid = (unsigned)(need < res ? need : res);
+        return a.nmask ? launch_probe_mz<true>(db, a, st, grid) : launch_probe_mz<false>(db, a, st, grid);
+    }
     if (db.layout == 1) {
         if (db.K != SK_K || db.slots != 8) { mlg_set_error("super-k-mer layout needs K=60 and 8-slot buckets"); return MLG_ERR_STATE; }
         // persistent: the CTAs that fit (2 per SM) pull 32-read tiles from a global counter

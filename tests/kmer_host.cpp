@@ -16,4 +16,9 @@ unsigned t_minimizer(unsigned long long hi, unsigned long long lo, unsigned K) {
 unsigned long long t_hash_sk(unsigned long long hi, unsigned long long lo, unsigned K, unsigned bbits) { key128 a{hi, lo}; return key_hash_sk(a, K, bbits); }
 unsigned t_mmer_mix(unsigned f, unsigned r) { return mmer_mix(f, r); }
 unsigned t_rev2_32(unsigned x) { return rev2_32h(x); }
+unsigned t_mz_order(unsigned a, unsigned b) { return mz_order(a, b); }
+unsigned long long t_mz_ident(unsigned a, unsigned b) { return mz_ident(a, b); }
+void t_key_mz(unsigned long long hi, unsigned long long lo, unsigned K, unsigned long long* out) { key128 a{hi, lo}; key_mz(a, K, out, out + 1); }
+unsigned long long t_mz_bit_index(unsigned long long z, unsigned fbits) { return mz_bit_index(z, fbits); }
+unsigned t_mz_bucket(unsigned long long z, unsigned bbits) { return mz_bucket(z, bbits); }
 }

@@ -402,9 +402,10 @@ def test_nruns_long_runs_and_no_n(ctx):
     db.close()
 
 
-def test_both_layouts_k60(ctx, workload, monkeypatch):
-    """K = 60 defaults to the super-k-mer layout (bucket by minimizer, ~5 bucket fetches per 150-base read);
-    MLG_LAYOUT=0 keeps the whole-k-mer hash layout.  Same results, and the fetch counts tell them apart."""
+def test_all_layouts_k60(ctx, workload, monkeypatch):
+    """K = 60 defaults to the minimizer-bitmap layout (one bitmap sector per super-k-mer, ~5 per 150-base read);
+    MLG_LAYOUT=1 keeps the fingerprint-pair super-k-mer layout, MLG_LAYOUT=0 the whole-k-mer hash layout.  Same
+    results, and the fetch counts tell them apart."""
     w = workload
     q = w["db"].query()
     q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
@@ -412,8 +413,20 @@ def test_both_layouts_k60(ctx, workload, monkeypatch):
     _check(res, q.intersection(), *w["refs"]["exact"])
     st = res["stats"]
     q.close()
-    assert st["layout"] == 1 and st["filter_words"] == 0
-    assert 0.03 * st["n_kmers"] < st["n_bucket_fetches"] < 0.09 * st["n_kmers"]
+    assert st["layout"] == 2 and st["filter_words"] >= 1 << 15 and st["bucket_bytes"] == 32
+    assert 0.05 * st["n_kmers"] < st["n_bucket_fetches"] < 0.14 * st["n_kmers"]      # ~8 runs of 32-base minimizers per 91 windows
+    monkeypatch.setenv("MLG_LAYOUT", "1")
+    db1 = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
+    for gate in ("exact", "none"):
+        q = db1.query(2, gate, True)
+        q.push_packed(w["bases"], w["nmask"], None, w["nreads"], w["p"].read_len)
+        res = q.finish()
+        _check(res, q.intersection(), *w["refs"][gate])
+        st = res["stats"]
+        assert st["layout"] == 1 and st["filter_words"] == 0 and st["bucket_bytes"] == 64
+        assert 0.03 * st["n_kmers"] < st["n_bucket_fetches"] < 0.09 * st["n_kmers"]
+        q.close()
+    db1.close()
     monkeypatch.setenv("MLG_LAYOUT", "0")
     db0 = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
     for gate in ("exact", "none"):
@@ -426,8 +439,9 @@ def test_both_layouts_k60(ctx, workload, monkeypatch):
     db0.close()
 
 
-def test_superkmer_adversarial_minimizers(ctx):
-    """reads built to stress the super-k-mer path: low-complexity sequence (every window shares one minimizer),
+@pytest.mark.parametrize("layout", [2, 1])
+def test_superkmer_adversarial_minimizers(ctx, monkeypatch, layout):
+    """both minimizer layouts; reads built to stress the super-k-mer path: low-complexity sequence (every window shares one minimizer),
     tandem repeats (the minimizer recurs), strictly decreasing minimizers are approximated by random sequence with
     many N (segments restart), reads of 60..400 bases (several 96-window segments per lane), and a database whose
     sketch k-mers overlap heavily (many keys per minimizer -> overflowing buckets -> exact path)."""
@@ -453,6 +467,7 @@ def test_superkmer_adversarial_minimizers(ctx):
             reads.append("".join(r))
     reads += ["A" * 200, "ACGT" * 60, "T" * 59, "", "N" * 100, genome[:60]]
     keys = codec.sketches_to_keys(sketches, K)
+    monkeypatch.setenv("MLG_LAYOUT", str(layout))
     db = Database.from_keys(ctx, keys, 3, 600, K, KS)
     for ci_min, gate in ((1, "exact"), (2, "none"), (3, "exact")):
         ref, I_ref = oracle_c_run(keys, 3, 600, K, KS, lambda q: q.push_reads(reads), ci_min, gate, True)
@@ -460,9 +475,95 @@ def test_superkmer_adversarial_minimizers(ctx):
         q.push_reads(reads)
         res = q.finish()
         _check(res, q.intersection(), ref, I_ref, (ci_min, gate))
-        assert res["stats"]["layout"] == 1
+        assert res["stats"]["layout"] == layout
         q.close()
     assert ref["n_intersect"] > 500
+    db.close()
+
+
+@pytest.mark.parametrize("layout,load", [(2, None), (2, "64"), (1, None)])
+def test_every_window_is_a_database_kmer(ctx, monkeypatch, layout, load):
+    """the sketches hold EVERY 60-mer of a 20 kb sequence and the reads come from it, so every N-free window must be
+    found exactly once: any window lost or counted twice by the run bookkeeping of the minimizer kernels (runs
+    spanning blocks, more than four runs in a block of 16 windows, segments of long reads, crowded buckets with
+    load = 64 keys per bucket) changes the counters"""
+    rng = random.Random(77)
+    K, G, n = 60, 20, 1000
+    genome = "".join(rng.choice("ACGT") for _ in range(G * n + K - 1))
+    sketches = [[genome[g * n + j:g * n + j + K] for j in range(n)] for g in range(G)]
+    reads = []
+    for _ in range(4000):
+        L = rng.choice([60, 100, 150, 150, 150, 151, 250, 330])
+        a = rng.randint(0, len(genome) - L)
+        r = genome[a:a + L]
+        if rng.random() < 0.5:
+            r = oracle_py.rc(r)
+        if rng.random() < 0.2:
+            r = list(r)
+            r[rng.randint(0, L - 1)] = "N"
+            r = "".join(r)
+        reads.append(r)
+    keys = codec.sketches_to_keys(sketches, K)
+    monkeypatch.setenv("MLG_LAYOUT", str(layout))
+    if load:
+        monkeypatch.setenv("MLG_MZ_LOAD", load)
+    db = Database.from_keys(ctx, keys, G, n, K, KS)
+    for ci_min in (1, 30):
+        ref, I_ref = oracle_c_run(keys, G, n, K, KS, lambda q: q.push_reads(reads), ci_min, "exact", True)
+        q = db.query(ci_min, "exact", True)
+        q.push_reads(reads)
+        res = q.finish()
+        _check(res, q.intersection(), ref, I_ref, (layout, load, ci_min))
+        assert res["stats"]["layout"] == layout
+        q.close()
+        if ci_min == 1:
+            assert ref["n_intersect"] > 0.95 * G * n
+    db.close()
+
+
+def _mz_order(s32):
+    """kmer.cuh mz_order of a 32-mer given as a string"""
+    a = int("".join(str("ACGT".index(ch)) for ch in s32[:16]), 4)
+    b = int("".join(str("ACGT".index(ch)) for ch in oracle_py.rc(s32[16:])), 4)
+    return ((a + b) * 0x9E3779B1) & 0x03FFFFFF
+
+
+def test_minimizer_ties_use_the_alias_table(ctx, monkeypatch):
+    """database 60-mers whose smallest 32-mer order is reached at two positions with DIFFERENT content: a read carrying
+    such a k-mer forward finds its leftmost minimum, a read carrying the reverse complement its rightmost one; the second
+    identity is served by the alias table (kmer.cuh).  The order only looks at the 26 bases in the middle of a 32-mer,
+    so planting the same low-order core twice, 28 bases apart, makes the tie."""
+    rng = random.Random(31)
+    K = 60
+    rnd = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    tied = []
+    while len(tied) < 40:
+        core = rnd(26)
+        s = rnd(3) + core + rnd(2) + core + rnd(3)
+        assert len(s) == K
+        o = [_mz_order(s[p:p + 32]) for p in range(K - 31)]
+        if o[0] == o[28] == min(o) and s[0:32] != s[28:60] and o.count(min(o)) == 2:
+            tied.append(s)
+    plain = [rnd(K) for _ in range(60)]
+    sketches = [tied[:20] + plain[:30], [oracle_py.rc(x) for x in tied[20:]] + plain[30:]]
+    reads = []
+    for x in tied + plain:
+        for strand in (0, 1):
+            r = rnd(rng.randint(0, 40)) + (x if strand == 0 else oracle_py.rc(x)) + rnd(rng.randint(0, 40))
+            reads += [r] * rng.randint(1, 3)
+    keys = codec.sketches_to_keys(sketches, K)
+    monkeypatch.setenv("MLG_LAYOUT", "2")
+    db = Database.from_keys(ctx, keys, 2, 50, K, KS)
+    for ci_min in (1, 2, 4):
+        ref, I_ref = oracle_c_run(keys, 2, 50, K, KS, lambda q: q.push_reads(reads), ci_min, "exact", True)
+        q = db.query(ci_min, "exact", True)
+        q.push_reads(reads)
+        res = q.finish()
+        _check(res, q.intersection(), ref, I_ref, ci_min)
+        assert res["stats"]["layout"] == 2
+        q.close()
+        if ci_min == 1:
+            assert ref["n_intersect"] == 100
     db.close()
 
 
@@ -560,6 +661,7 @@ def test_superkmer_overfull_pairs(ctx, workload, monkeypatch):
     """mean load 7.5 per 8-slot half: most halves are full or overflowed, so most windows go through the queue and the
     exact compare (a full half is treated as overflowed; there is no flag bit in this layout)"""
     w = workload
+    monkeypatch.setenv("MLG_LAYOUT", "1")
     monkeypatch.setenv("MLG_SK_LOAD", "7.5")
     db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
     q = db.query()

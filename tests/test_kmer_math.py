@@ -45,6 +45,15 @@ def kh(tmp_path_factory):
     L.t_mmer_mix.restype = C.c_uint
     L.t_rev2_32.argtypes = [C.c_uint]
     L.t_rev2_32.restype = C.c_uint
+    L.t_mz_order.argtypes = [C.c_uint, C.c_uint]
+    L.t_mz_order.restype = C.c_uint
+    L.t_mz_ident.argtypes = [C.c_uint, C.c_uint]
+    L.t_mz_ident.restype = u64
+    L.t_key_mz.argtypes = [u64, u64, C.c_uint, C.POINTER(u64 * 2)]
+    L.t_mz_bit_index.argtypes = [u64, C.c_uint]
+    L.t_mz_bit_index.restype = u64
+    L.t_mz_bucket.argtypes = [u64, C.c_uint]
+    L.t_mz_bucket.restype = C.c_uint
     return L
 
 
@@ -138,3 +147,57 @@ def test_minimizer_is_strand_symmetric_and_matches_strings(kh):
         mins.append(kh.t_minimizer(hi, lo, 60))
     changes = sum(1 for a, b in zip(mins, mins[1:]) if a != b)
     assert 0.02 < changes / len(mins) < 0.07
+
+
+def _mz_pair(s32):
+    """(a, b) of a 32-mer: its first 16 bases, and the reverse complement of its last 16 bases, as words"""
+    return _kmer_int(s32[:16]), _kmer_int(oracle_py.rc(s32[16:]))
+
+
+def _key_mz_strings(kh, s):
+    """string-level restatement of key_mz: identities of the leftmost / rightmost 32-mer of smallest order"""
+    vals = [kh.t_mz_order(*_mz_pair(s[p:p + 32])) for p in range(len(s) - 31)]
+    m = min(vals)
+    pl = vals.index(m)
+    pr = len(vals) - 1 - vals[::-1].index(m)
+    return kh.t_mz_ident(*_mz_pair(s[pl:pl + 32])), kh.t_mz_ident(*_mz_pair(s[pr:pr + 32]))
+
+
+def test_minimizer32_layout_math(kh):
+    """minimizer-bitmap layout (kmer.cuh): the order and the identity of a 32-mer do not depend on the strand; a K-mer's
+    leftmost minimum is its reverse complement's rightmost one; low-complexity K-mers tie without changing identity"""
+    rng = random.Random(9)
+    out = (C.c_uint64 * 2)()
+    for _ in range(300):
+        m = "".join(rng.choice("ACGT") for _ in range(32))
+        a, b = _mz_pair(m)
+        ra, rb = _mz_pair(oracle_py.rc(m))
+        assert (ra, rb) == (b, a)
+        assert kh.t_mz_order(a, b) == kh.t_mz_order(b, a) < (1 << 26)
+        assert kh.t_mz_ident(a, b) == kh.t_mz_ident(b, a)
+    seqs = ["".join(rng.choice("ACGT") for _ in range(60)) for _ in range(300)]
+    seqs += ["A" * 60, "AC" * 30, "ACG" * 20, "A" * 30 + "C" * 30, ("ACGTTGCA" * 8)[:60]]
+    ties = 0
+    for s in seqs:
+        hi, lo = codec.kmer_to_key(s)
+        kh.t_key_mz(hi, lo, 60, out)
+        zl, zr = out[0], out[1]
+        assert (zl, zr) == _key_mz_strings(kh, s)
+        rhi, rlo = codec.kmer_to_key(oracle_py.rc(s))
+        kh.t_key_mz(rhi, rlo, 60, out)
+        assert (out[0], out[1]) == (zr, zl)
+        ties += zl != zr
+        for fbits in (5, 20, 32, 33, 36):
+            assert kh.t_mz_bit_index(zl, fbits) == zl & ((1 << fbits) - 1)
+        for bbits in (1, 13, 31):
+            assert kh.t_mz_bucket(zl, bbits) == (zl >> 32) >> (32 - bbits)
+    assert ties <= 2                      # homopolymers and short tandem repeats tie between 32-mers of EQUAL content
+    # runs of equal minimizer along a sequence: ~2/(w+1) changes per window with w = 29 positions
+    seq = "".join(rng.choice("ACGT") for _ in range(5000))
+    ids = []
+    for i in range(len(seq) - 59):
+        hi, lo = codec.kmer_to_key(seq[i:i + 60])
+        kh.t_key_mz(hi, lo, 60, out)
+        ids.append(out[0])
+    changes = sum(1 for x, y in zip(ids, ids[1:]) if x != y)
+    assert 0.04 < changes / len(ids) < 0.10
