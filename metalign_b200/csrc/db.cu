@@ -107,7 +107,7 @@ __global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, uint32_t la
 // layout 2: level-1 bits of the identities of every K-mer's leftmost and rightmost minimum (kmer.cuh), and the alias
 // entries of the K-mers whose two identities differ (pass 0 counts them, pass 1 writes them)
 __global__ void k_fill_mzbits(const key128* D, uint32_t nd, uint32_t K, uint32_t fbits, uint32_t* MB, int pass,
-                              unsigned long long* alias_z, uint32_t* alias_i, unsigned long long* counter) {
+                              unsigned long long* alias_z, uint32_t* alias_i, uint32_t* alias_bloom, unsigned long long* counter) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nd) return;
     unsigned long long zL, zR;
@@ -119,6 +119,8 @@ __global__ void k_fill_mzbits(const key128* D, uint32_t nd, uint32_t K, uint32_t
     } else if (zR != zL) {
         const unsigned long long j = atomicAdd(counter, 1ull);
         alias_z[j] = zR; alias_i[j] = i;
+        const uint32_t zlo = (uint32_t)zR;
+        atomicOr(&alias_bloom[(zlo & 0xFFFFu) >> 5], 1u << (zlo & 31u));
     }
 }
 __global__ void k_gather_key(const key128* src, const uint32_t* idx, uint32_t n, key128* dst) {
@@ -412,10 +414,10 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             if ((double)nfw * 32.0 < 1.5 * (double)nd) nfw = 0;
         }
         if (v.layout == 2) {
-            // level-1 bit array: at least 32 bits per K-mer (<= 3 % of the bits set = the false-positive rate of a run),
-            // 2^20 .. 2^36 bits
+            // level-1 bit array: at least 128 bits per K-mer (<= 0.8 % of the bits set = the false-positive rate of a
+            // run; every false positive costs an exact compare of ~11 windows), 2^20 .. 2^36 bits
             uint32_t fbits = 20;
-            while (fbits < 36 && (1ull << fbits) < 32ull * nd) ++fbits;
+            while (fbits < 36 && (1ull << fbits) < 128ull * nd) ++fbits;
             if (const char* s = getenv("MLG_MZ_FBITS")) { int x = atoi(s); if (x >= 10 && x <= 36) fbits = (uint32_t)x; }
             v.fbits = fbits;
             nfw = 1ull << (fbits - 5);
@@ -428,9 +430,12 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             CUDA_TRY(cudaMemsetAsync(db->F.p, 0, nfw * 4, st));
             v.F = db->F.p;
             v.n_alias = 0; v.alias_z = nullptr; v.alias_i = nullptr;
+            MLG_TRY(db->alias_bloom.alloc(2048));
+            CUDA_TRY(cudaMemsetAsync(db->alias_bloom.p, 0, 2048 * 4, st));
+            v.alias_bloom = db->alias_bloom.p;
             if (nd) {
                 CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 8, st));
-                k_fill_mzbits<<<nblk(nd), TPB, 0, st>>>(db->D_key.p, nd, K, v.fbits, db->F.p, 0, nullptr, nullptr, d_cnt.p);
+                k_fill_mzbits<<<nblk(nd), TPB, 0, st>>>(db->D_key.p, nd, K, v.fbits, db->F.p, 0, nullptr, nullptr, nullptr, d_cnt.p);
                 unsigned long long na = 0;
                 CUDA_TRY(cudaMemcpyAsync(&na, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
@@ -439,7 +444,7 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
                     MLG_TRY(az.alloc(na)); MLG_TRY(ai.alloc(na));
                     MLG_TRY(db->alias_z.alloc(na)); MLG_TRY(db->alias_i.alloc(na));
                     CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 8, st));
-                    k_fill_mzbits<<<nblk(nd), TPB, 0, st>>>(db->D_key.p, nd, K, v.fbits, db->F.p, 1, az.p, ai.p, d_cnt.p);
+                    k_fill_mzbits<<<nblk(nd), TPB, 0, st>>>(db->D_key.p, nd, K, v.fbits, db->F.p, 1, az.p, ai.p, db->alias_bloom.p, d_cnt.p);
                     MLG_TRY(sort_pairs_u64(az.p, db->alias_z.p, ai.p, db->alias_i.p, (uint32_t)na, 0, 64, st));
                     v.n_alias = (uint32_t)na; v.alias_z = db->alias_z.p; v.alias_i = db->alias_i.p;
                 }

@@ -47,11 +47,16 @@ MLG_HD key128 key_and(const key128& a, const key128& b) { key128 r; r.hi = a.hi 
 
 // reverse the order of the 32 two-bit groups of a 64-bit word
 MLG_HD unsigned long long rev2_64(unsigned long long x) {
+#ifdef __CUDA_ARCH__
+    x = __brevll(x);
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+#else
     x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
     x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
     x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
     x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
     return (x >> 32) | (x << 32);
+#endif
 }
 // reverse complement of a k-base value (k <= 64)
 MLG_HD key128 key_rc(const key128& a, unsigned k) {

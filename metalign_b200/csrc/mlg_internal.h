@@ -93,6 +93,7 @@ struct DbView {
     // layout 2: K-mers whose leftmost and rightmost minimum differ, by the identity of the rightmost one (sorted)
     const unsigned long long* alias_z;
     const uint32_t* alias_i;     // index in D
+    const uint32_t* alias_bloom; // 2^16 bits over the low identity bits of the aliases
     uint32_t n_alias;
 };
 
@@ -103,7 +104,7 @@ struct mlg_db {
     DevBuf<uint32_t> P_slot, pidx, rep, bstart, T1;
     DevBuf<uint32_t> F;
     DevBuf<unsigned long long> alias_z;
-    DevBuf<uint32_t> alias_i;
+    DevBuf<uint32_t> alias_i, alias_bloom;
     DevBuf<key128> D_key;
     DevBuf<uint32_t> hoff, hits;     // precomputed hit lists per k-mer of D (hoff.p == nullptr: not built)
     unsigned long long hit_words = 0;

@@ -920,7 +920,8 @@ int launch_probe_sk(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsig
 #define MZ_MINCTAS 2
 #endif
 constexpr unsigned MZ_MAXRUN = 4;             // runs per block whose bit-array word is fetched ahead (the carried one + 3 new)
-constexpr unsigned MZ_QCAP = 64;              // per-warp item ring (power of two; holds <= 63: drained whenever 32 are waiting)
+constexpr unsigned MZ_QDRAIN = 32;            // per-warp item list: drained whenever this many are waiting ...
+constexpr unsigned MZ_QCAP = MZ_QDRAIN + 128; // ... and one block of 16 windows adds at most 4 x 32
 constexpr unsigned MZ_LIST = 16;              // run list rows: a block of 16 windows starts at most 15 new runs (row 0 unused)
 constexpr uint32_t MZ_M64 = MLG_MZ_ORD_MULT << 6;   // the multiplier carries the << 6 of (order << 6 | position)
 struct MzShared {
@@ -928,9 +929,10 @@ struct MzShared {
     uint32_t wm[MZ_LIST][RT];                 // [r][thread]: value of the r-th run START of the current block (r >= 1)
     uint32_t seq[SEGW + 1][RT];               // [word][thread]: the lane's current segment (160 bases, top-aligned words)
     uint32_t qa[WARPS][MZ_QCAP];              // item: source lane | index of the block's first window in the read << 5
-    uint32_t qk[WARPS][MZ_QCAP];              // item: windows of the block to compare exactly (bit tt = window tt)
-    uint32_t qlo[WARPS][MZ_QCAP];             // item: identity of the minimizer, low / high word
-    uint32_t qhi[WARPS][MZ_QCAP];
+    uint32_t qb[WARPS][MZ_QCAP];              // item: windows of the block to compare exactly (bit tt = window tt) | base of the
+                                              //       minimizer relative to the block's first window << 16
+    uint32_t qoff[WARPS][32];                 // drain: windows before each item of the batch
+    uint32_t qn[WARPS];                       // items waiting
     unsigned long long r0s[WARPS][32];        // stream position (in bases) of each lane's read of the current tile
 };
 constexpr uint32_t MZ_ROW = RT * 4;           // byte stride between rows of wm[] / seq[]
@@ -954,15 +956,34 @@ __device__ __forceinline__ uint32_t mz_val(const uint32_t (&loc)[SEGW], const ui
     const uint32_t b = fsl(rcl[ra], rcl[ra + 1], 2 * ro);
     return b * MZ_M64 + (a * MZ_M64 + (uint32_t)(16 * j + i));
 }
-// exact compare of the windows of one item (one lane): canonical key of every window in `mask` against the database
-// k-mers filed under the identity (zhi:zlo)
-__device__ __noinline__ void mz_process(uint32_t ia, uint32_t mask, uint32_t zlo, uint32_t zhi, const unsigned long long* bsrc,
-                                        unsigned long long base_words, const unsigned long long* r0s, const DbView& db,
-                                        const CountSink& cs) {
+// 64 bases of the packed stream starting at base p, top-aligned (hi = the first 32)
+__device__ __forceinline__ void mz_bases64(const unsigned long long* bsrc, unsigned long long base_words, unsigned long long p,
+                                           unsigned long long& hi, unsigned long long& lo) {
+    const unsigned long long q = p >> 5;
+    const unsigned sh = 2u * (unsigned)(p & 31ull);
+    unsigned long long W[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned long long idx = q + k;
+        if (idx >= base_words) idx = base_words - 1;
+        W[k] = bswap64(bsrc[idx]);
+    }
+    hi = sh ? ((W[0] << sh) | (W[1] >> (64 - sh))) : W[0];
+    lo = sh ? ((W[1] << sh) | (W[2] >> (64 - sh))) : W[1];
+}
+// exact compare of ONE window of an item (one lane): the window starts at base p, its minimizer at base pm of the
+// stream; its canonical key is compared with the database k-mers filed under the minimizer's identity
+__device__ __forceinline__ void mz_window(unsigned long long p, unsigned long long pm, const unsigned long long* bsrc,
+                                          unsigned long long base_words, const DbView& db, const CountSink& cs) {
+    unsigned long long mh, ml;
+    mz_bases64(bsrc, base_words, pm, mh, ml);
+    const uint32_t ha = (uint32_t)(mh >> 32), hb = rev2_32(~(uint32_t)mh);
+    const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
     const uint32_t bucket = zhi >> (32u - db.bbits);
     const uint32_t s = db.bstart[bucket], e = db.bstart[bucket + 1];
+    // K-mers filed under a second identity (order ties) are rare: a 2^16-bit array says whether to look at all
     uint32_t j0 = 0, j1 = 0;
-    if (db.n_alias) {
+    if (db.n_alias && ((db.alias_bloom[(zlo & 0xFFFFu) >> 5] >> (zlo & 31u)) & 1u)) {
         const unsigned long long z = ((unsigned long long)zhi << 32) | zlo;
         uint32_t lo = 0, hi = db.n_alias;
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (db.alias_z[mid] < z) lo = mid + 1; else hi = mid; }
@@ -970,37 +991,50 @@ __device__ __noinline__ void mz_process(uint32_t ia, uint32_t mask, uint32_t zlo
         while (j1 < db.n_alias && db.alias_z[j1] == z) ++j1;
     }
     if (s == e && j0 == j1) return;
-    const unsigned long long p0 = r0s[ia & 31u] + (ia >> 5);
-    while (mask) {
-        const unsigned tt = (unsigned)__ffs((int)mask) - 1u;
-        mask &= mask - 1u;
-        const unsigned long long p = p0 + tt;
-        const unsigned long long q = p >> 5;
-        const unsigned sh = 2u * (unsigned)(p & 31ull);
-        unsigned long long W[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            unsigned long long idx = q + k;
-            if (idx >= base_words) idx = base_words - 1;
-            W[k] = bswap64(bsrc[idx]);
-        }
-        key128 F;                                                   // 64 bases from p, top-aligned
-        F.hi = sh ? ((W[0] << sh) | (W[1] >> (64 - sh))) : W[0];
-        F.lo = sh ? ((W[1] << sh) | (W[2] >> (64 - sh))) : W[1];
-        F = key_shr(F, 128 - 2 * SK_K);                             // the 60-mer, bottom-aligned
-        const key128 G = key_rc(F, SK_K);
-        const key128 cn = key_lt(G, F) ? G : F;
-        bool found = false;
-        for (uint32_t i = s; i < e && !found; ++i) {
-            const key128 d = db.D_key[i];
-            if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); found = true; }
-        }
-        for (uint32_t j = j0; j < j1 && !found; ++j) {
-            const uint32_t i = db.alias_i[j];
-            const key128 d = db.D_key[i];
-            if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); found = true; }
-        }
+    key128 F;                                                       // 64 bases from p, top-aligned
+    mz_bases64(bsrc, base_words, p, F.hi, F.lo);
+    F = key_shr(F, 128 - 2 * SK_K);                                 // the 60-mer, bottom-aligned
+    const key128 G = key_rc(F, SK_K);
+    const key128 cn = key_lt(G, F) ? G : F;
+    for (uint32_t i = s; i < e; ++i) {
+        const key128 d = db.D_key[i];
+        if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); return; }
     }
+    for (uint32_t j = j0; j < j1; ++j) {
+        const uint32_t i = db.alias_i[j];
+        const key128 d = db.D_key[i];
+        if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); return; }
+    }
+}
+// exact compare of every window of every waiting item of one warp, one WINDOW per lane (items have 1..16 windows)
+__device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const uint32_t* qb, uint32_t* qoff, const unsigned long long* r0s,
+                                      const unsigned long long* bsrc, unsigned long long base_words, const DbView& db, const CountSink& cs) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    __syncwarp();
+    const uint32_t n = *qn;
+    for (uint32_t base = 0; base < n; base += 32u) {
+        const uint32_t i = base + lane;
+        const uint32_t cnt = i < n ? (uint32_t)__popc(qb[i] & 0xFFFFu) : 0u;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += u; }
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
+        qoff[lane] = inc - cnt;
+        __syncwarp();
+        for (uint32_t w = lane; w < total; w += 32u) {
+            uint32_t j = 0;                              // the last item of the batch that starts at or before window w
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) if (qoff[j + step] <= w) j += step;
+            const uint32_t ia = qa[base + j], kb = qb[base + j];
+            const uint32_t tt = __fns(kb & 0xFFFFu, 0u, (int)(w - qoff[j]) + 1);
+            const unsigned long long pb = r0s[ia & 31u] + (ia >> 5);
+            mz_window(pb + tt, pb + (kb >> 16), bsrc, base_words, db, cs);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *qn = 0;
+    __syncwarp();
 }
 
 template <bool HAS_NMASK>
@@ -1064,9 +1098,9 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
 
     unsigned long long my_valid = 0;
     unsigned my_fetch = 0;
-    // item ring of this warp: head and count, warp-uniform
-    uint32_t qh = 0, qn = 0;
     const unsigned long long* bsrc = a.bases;
+    if (lane == 0) sm.qn[warp] = 0;
+    __syncwarp();
 
     // the two halves (a, b) of the 32-mer at base P of the lane's segment copy (b = reverse complement of the second half)
     auto halves_at = [&](uint32_t P, uint32_t& ha, uint32_t& hb) {
@@ -1076,30 +1110,19 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         ha = fsl(w0, w1, sh);
         hb = rev2_32(~fsl(w1, w2, sh));
     };
-    // process `cnt` (<= 32) items from the head of the ring, one per lane
-    auto drain = [&](uint32_t cnt) {
-        __syncwarp();
-        if (lane < cnt) {
-            const uint32_t i = (qh + lane) & (MZ_QCAP - 1u);
-            mz_process(sm.qa[warp][i], sm.qk[warp][i], sm.qlo[warp][i], sm.qhi[warp][i], bsrc, a.base_words, &sm.r0s[warp][0], db, sink);
-        }
-        __syncwarp();
-        qh = (qh + cnt) & (MZ_QCAP - 1u);
-        qn -= cnt;
+    auto drain = [&]() {
+        mz_drain(&sm.qn[warp], &sm.qa[warp][0], &sm.qb[warp][0], &sm.qoff[warp][0], &sm.r0s[warp][0], bsrc, a.base_words, db, sink);
     };
-    // all 32 lanes call this; lanes with p append one item for the run whose minimizer starts at base P of the segment
-    auto push = [&](bool p, uint32_t ia, uint32_t ik, uint32_t P) {
-        const unsigned ballot = __ballot_sync(FULL, p);
-        if (ballot) {
-            if (p) {
-                uint32_t ha, hb;
-                halves_at(P, ha, hb);
-                const uint32_t i = (qh + qn + __popc(ballot & lt_mask)) & (MZ_QCAP - 1u);
-                sm.qa[warp][i] = ia; sm.qk[warp][i] = ik; sm.qlo[warp][i] = mz_ident_lo(ha, hb); sm.qhi[warp][i] = mz_ident_hi(ha, hb);
-            }
-            qn += __popc(ballot);
-            if (qn >= 32u) drain(32u);
+    // lanes with p append one item: windows `ik` of the block whose first window is `ia`, minimizer at base `rel` of the block
+    auto push = [&](bool p, uint32_t ia, uint32_t ik, uint32_t rel) {
+        if (p) {
+            const uint32_t i = atomicAdd(&sm.qn[warp], 1u);
+            sm.qa[warp][i] = ia; sm.qb[warp][i] = ik | (rel << 16);
         }
+    };
+    auto drain_if_full = [&]() {
+        __syncwarp();
+        if (sm.qn[warp] >= MZ_QDRAIN) drain();
     };
 
     unsigned it = 0;
@@ -1240,23 +1263,32 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                 const uint32_t c2 = cc & (0u - cc); cc ^= c2;
                 const uint32_t c3 = cc & (0u - cc);
                 const uint32_t m0 = (c1 - 1u) & pvm, m1 = (c2 - c1) & pvm, m2 = (c3 - c2) & pvm, m3 = (0x10000u - c3) & pvm;
-                const uint32_t ia = lane | ((seg * WMAX + pblk) << 5);
-                push(b0 & (m0 != 0u), ia, m0, pblk + (pW0 & 63u));
-                push(b1 & (m1 != 0u), ia, m1, pblk + (pW1 & 63u));
-                push(b2 & (m2 != 0u), ia, m2, pblk + (pW2 & 63u));
-                push(b3 & (m3 != 0u), ia, m3, pblk + (pW3 & 63u));
+                const bool q0 = b0 & (m0 != 0u), q1 = b1 & (m1 != 0u), q2 = b2 & (m2 != 0u), q3 = b3 & (m3 != 0u);
+                if (__any_sync(FULL, q0 | q1 | q2 | q3)) {
+                    const uint32_t ia = lane | ((seg * WMAX + pblk) << 5);
+                    push(q0, ia, m0, pW0 & 63u);
+                    push(q1, ia, m1, pW1 & 63u);
+                    push(q2, ia, m2, pW2 & 63u);
+                    push(q3, ia, m3, pW3 & 63u);
+                    drain_if_full();
+                }
             };
 
+            // One pass per block of 16 windows, plus a last pass that only looks at the words of the block before it.
+            // `more` (a block follows) is voted BEFORE the block's lookups are issued, so that no vote or other
+            // convergence point sits between the loads and the phase A that hides their latency.
+            bool more = true;                                       // the segment has valid windows (checked above)
 #pragma unroll 1
-            for (int blk = 0; blk < (int)(WMAX / 16); ++blk) {
-                if (__all_sync(FULL, (v0 | v1 | v2) == 0u)) break;       // nothing valid from here to the end of the segment
-                const uint32_t vb = v0 & 0xFFFF0000u;
-                v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
+            for (int blk = 0;; ++blk) {
                 const uint32_t blk16 = (uint32_t)blk * 16u;
+                uint32_t chgraw = 0, wm_first = 0, vb = 0, chg = 0, t3 = 0, ovfm = 0, vwin = 0;
+                unsigned nrun = 1;
+                if (more) {
+                vb = v0 & 0xFFFF0000u;
+                v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
 
                 // ---- phase A: window minima and runs of equal minimizer (validity is ignored here: a window that is
                 //      not valid costs at most a wasted lookup; it is masked out of the items)
-                uint32_t chgraw = 0, wm_first = 0;
                 {
                     uint32_t Suf[16];
                     {
@@ -1288,15 +1320,14 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                     P -= 16u;                                      // block 2 of this block is block 1 of the next one
                 }
                 // runs 0..3 of the block are looked up; windows of later runs (rare) become items unfiltered
-                uint32_t chg, t3;
                 {
                     t3 = chgraw;
                     t3 &= t3 - 1u; t3 &= t3 - 1u; t3 &= t3 - 1u;      // changes beyond the third
                     chg = chgraw ^ t3;
                 }
-                const uint32_t ovfm = t3 ? (~((t3 & (0u - t3)) - 1u) & 0xFFFFu) : 0u;   // every window from the fourth change on
-                const uint32_t vwin = __brev(vb) & 0xFFFFu;          // bit tt = validity of window tt
-                const unsigned nrun = 1u + __popc(chg);
+                ovfm = t3 ? (~((t3 & (0u - t3)) - 1u) & 0xFFFFu) : 0u;   // every window from the fourth change on
+                vwin = __brev(vb) & 0xFFFFu;                        // bit tt = validity of window tt
+                nrun = 1u + __popc(chg);
                 if (__any_sync(FULL, t3 != 0u)) {
                     const uint32_t ia = lane | ((seg * WMAX + blk16) << 5);
                     uint32_t rest = t3;
@@ -1306,13 +1337,19 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                         const uint32_t upto = nxt ? (nxt & (0u - nxt)) : 0x10000u;
                         const uint32_t mk = rest ? ((upto - low) & vwin) : 0u;
                         const uint32_t w = rest ? lds32(wm_base + rr * MZ_ROW) : 0u;
-                        push(mk != 0u, ia, mk, blk16 + (w & 63u));
+                        push(mk != 0u, ia, mk, w & 63u);
+                        drain_if_full();
                         rest = nxt; ++rr;
                     }
                 }
 
+                }   // if (more)
+
                 // ---- the previous block's bit-array words have had a whole phase A to arrive
                 if (pend) consume();
+                if (!more) break;
+                pend = false;
+                more = blk + 1 < (int)(WMAX / 16) && !__all_sync(FULL, (v0 | v1 | v2) == 0u);   // anything valid after this block?
 
                 // ---- this block's lookups
                 {
@@ -1344,11 +1381,9 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
 #pragma unroll
                 for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
             }
-            if (pend) consume();
         }
         // items point into this tile's staged bases: finish them before the stage is refilled
-        while (qn) drain(qn < 32u ? qn : 32u);
-        __syncwarp();
+        drain();
         const unsigned long long t_new = next_tile();
         if (lane == 0 && t_new < ntiles) issue(stage, t_new);
         t = t_ahead; t_ahead = t_new;
