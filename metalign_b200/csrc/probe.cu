@@ -971,39 +971,53 @@ __device__ __forceinline__ void mz_bases64(const unsigned long long* bsrc, unsig
     hi = sh ? ((W[0] << sh) | (W[1] >> (64 - sh))) : W[0];
     lo = sh ? ((W[1] << sh) | (W[2] >> (64 - sh))) : W[1];
 }
-// exact compare of ONE window of an item (one lane): the window starts at base p, its minimizer at base pm of the
-// stream; its canonical key is compared with the database k-mers filed under the minimizer's identity
-__device__ __forceinline__ void mz_window(unsigned long long p, unsigned long long pm, const unsigned long long* bsrc,
-                                          unsigned long long base_words, const DbView& db, const CountSink& cs) {
+// Exact compare of ONE window of an item (one lane), in two stages.  Stage 1: the window starts at base p, its minimizer
+// at base pm of the stream; identity, bucket range and the first two database k-mers of the bucket (both loads in flight
+// together).  (Two windows per lane and round were tried: the drain's code doubles and the kernel starts missing in the
+// instruction cache, which costs more than the extra memory parallelism gains.)
+struct MzWin {
+    key128 cn, d0, d1;           // canonical key of the window; first two k-mers of the bucket
+    uint32_t s, e, j0, j1;       // bucket range in D, alias range
+};
+__device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long long p, unsigned long long pm,
+                                                const unsigned long long* bsrc, unsigned long long base_words, const DbView& db) {
+    w.s = w.e = w.j0 = w.j1 = 0;
+    w.cn.hi = w.cn.lo = 0; w.d0 = w.cn; w.d1 = w.cn;
+    if (!on) return;
     unsigned long long mh, ml;
     mz_bases64(bsrc, base_words, pm, mh, ml);
     const uint32_t ha = (uint32_t)(mh >> 32), hb = rev2_32(~(uint32_t)mh);
     const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
     const uint32_t bucket = zhi >> (32u - db.bbits);
-    const uint32_t s = db.bstart[bucket], e = db.bstart[bucket + 1];
+    w.s = db.bstart[bucket]; w.e = db.bstart[bucket + 1];
     // K-mers filed under a second identity (order ties) are rare: a 2^16-bit array says whether to look at all
-    uint32_t j0 = 0, j1 = 0;
     if (db.n_alias && ((db.alias_bloom[(zlo & 0xFFFFu) >> 5] >> (zlo & 31u)) & 1u)) {
         const unsigned long long z = ((unsigned long long)zhi << 32) | zlo;
         uint32_t lo = 0, hi = db.n_alias;
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (db.alias_z[mid] < z) lo = mid + 1; else hi = mid; }
-        j0 = j1 = lo;
-        while (j1 < db.n_alias && db.alias_z[j1] == z) ++j1;
+        w.j0 = w.j1 = lo;
+        while (w.j1 < db.n_alias && db.alias_z[w.j1] == z) ++w.j1;
     }
-    if (s == e && j0 == j1) return;
     key128 F;                                                       // 64 bases from p, top-aligned
     mz_bases64(bsrc, base_words, p, F.hi, F.lo);
     F = key_shr(F, 128 - 2 * SK_K);                                 // the 60-mer, bottom-aligned
     const key128 G = key_rc(F, SK_K);
-    const key128 cn = key_lt(G, F) ? G : F;
-    for (uint32_t i = s; i < e; ++i) {
+    w.cn = key_lt(G, F) ? G : F;
+    if (w.s < w.e) w.d0 = db.D_key[w.s];
+    if (w.s + 1u < w.e) w.d1 = db.D_key[w.s + 1u];
+}
+// stage 2: compare with the database k-mers filed under the identity, count a match
+__device__ __forceinline__ void mz_window_end(const MzWin& w, const DbView& db, const CountSink& cs) {
+    if (w.s < w.e && w.d0.hi == w.cn.hi && w.d0.lo == w.cn.lo) { bump_counter(cs, w.s); return; }
+    if (w.s + 1u < w.e && w.d1.hi == w.cn.hi && w.d1.lo == w.cn.lo) { bump_counter(cs, w.s + 1u); return; }
+    for (uint32_t i = w.s + 2u; i < w.e; ++i) {
         const key128 d = db.D_key[i];
-        if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); return; }
+        if (d.hi == w.cn.hi && d.lo == w.cn.lo) { bump_counter(cs, i); return; }
     }
-    for (uint32_t j = j0; j < j1; ++j) {
+    for (uint32_t j = w.j0; j < w.j1; ++j) {
         const uint32_t i = db.alias_i[j];
         const key128 d = db.D_key[i];
-        if (d.hi == cn.hi && d.lo == cn.lo) { bump_counter(cs, i); return; }
+        if (d.hi == w.cn.hi && d.lo == w.cn.lo) { bump_counter(cs, i); return; }
     }
 }
 // exact compare of every window of every waiting item of one warp, one WINDOW per lane (items have 1..16 windows)
@@ -1029,7 +1043,9 @@ __device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const ui
             const uint32_t ia = qa[base + j], kb = qb[base + j];
             const uint32_t tt = __fns(kb & 0xFFFFu, 0u, (int)(w - qoff[j]) + 1);
             const unsigned long long pb = r0s[ia & 31u] + (ia >> 5);
-            mz_window(pb + tt, pb + (kb >> 16), bsrc, base_words, db, cs);
+            MzWin win;
+            mz_window_begin(win, true, pb + tt, pb + (kb >> 16), bsrc, base_words, db);
+            mz_window_end(win, db, cs);
         }
         __syncwarp();
     }
@@ -1248,48 +1264,30 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
             uint32_t held_wm = 0;
             bool have = false, held_pass = false;
 
-            // what the previous block left to look at once its bit-array words have arrived
-            bool pend = false, pneed0 = false;
-            uint32_t pF0 = 0, pF1 = 0, pF2 = 0, pF3 = 0, pW0 = 0, pW1 = 0, pW2 = 0, pW3 = 0, pbits = 0, pchg = 0, pvm = 0, pnr = 0, pblk = 0;
-            auto consume = [&]() {
-                const bool b0 = pneed0 ? ((pF0 >> (pbits & 31u)) & 1u) : held_pass;
-                const bool b1 = (pnr > 1u) & ((pF1 >> ((pbits >> 8) & 31u)) & 1u);
-                const bool b2 = (pnr > 2u) & ((pF2 >> ((pbits >> 16) & 31u)) & 1u);
-                const bool b3 = (pnr > 3u) & ((pF3 >> ((pbits >> 24) & 31u)) & 1u);
-                held_pass = pnr == 1u ? b0 : pnr == 2u ? b1 : pnr == 3u ? b2 : b3;
-                // windows of run 0..3: [0, c1) [c1, c2) [c2, c3) [c3, 16); sentinels above bit 15 stand in for missing changes
-                uint32_t cc = pchg | 0x70000u;
-                const uint32_t c1 = cc & (0u - cc); cc ^= c1;
-                const uint32_t c2 = cc & (0u - cc); cc ^= c2;
-                const uint32_t c3 = cc & (0u - cc);
-                const uint32_t m0 = (c1 - 1u) & pvm, m1 = (c2 - c1) & pvm, m2 = (c3 - c2) & pvm, m3 = (0x10000u - c3) & pvm;
-                const bool q0 = b0 & (m0 != 0u), q1 = b1 & (m1 != 0u), q2 = b2 & (m2 != 0u), q3 = b3 & (m3 != 0u);
-                if (__any_sync(FULL, q0 | q1 | q2 | q3)) {
-                    const uint32_t ia = lane | ((seg * WMAX + pblk) << 5);
-                    push(q0, ia, m0, pW0 & 63u);
-                    push(q1, ia, m1, pW1 & 63u);
-                    push(q2, ia, m2, pW2 & 63u);
-                    push(q3, ia, m3, pW3 & 63u);
-                    drain_if_full();
-                }
-            };
-
-            // One pass per block of 16 windows, plus a last pass that only looks at the words of the block before it.
-            // `more` (a block follows) is voted BEFORE the block's lookups are issued, so that no vote or other
-            // convergence point sits between the loads and the phase A that hides their latency.
-            bool more = true;                                       // the segment has valid windows (checked above)
+            // Block b's runs are found by phase A in pass b; their bit-array words are loaded at the START of pass b + 1 and
+            // looked at after that pass's phase A, which hides the DRAM latency.  Loads and their use sit in the same loop
+            // body (nothing is in flight across the back edge), and no vote or other convergence point lies between them.
+            bool pend = false, pneed0 = false, more = true;          // more: the segment has valid windows (checked above)
+            uint32_t pW = 0, pchg = 0, pvm = 0, pnr = 0, pblk = 0;   // pW: positions of the minimizers of runs 0..3 (8 bits each)
+            uint32_t pX0 = 0, pX1 = 0, pX2 = 0, pX3 = 0, pbits = 0;  // word index and bit (8 bits each) of their lookups
 #pragma unroll 1
             for (int blk = 0;; ++blk) {
                 const uint32_t blk16 = (uint32_t)blk * 16u;
-                uint32_t chgraw = 0, wm_first = 0, vb = 0, chg = 0, t3 = 0, ovfm = 0, vwin = 0;
-                unsigned nrun = 1;
+                // ---- load the bit-array words of the previous block's runs 0..3
+                uint32_t F0 = 0, F1 = 0, F2 = 0, F3 = 0;
+                if (pend) {
+                    F0 = ldg_bitmap_if(pneed0, MB + pX0);
+                    F1 = ldg_bitmap_if(pnr > 1u, MB + pX1);
+                    F2 = ldg_bitmap_if(pnr > 2u, MB + pX2);
+                    F3 = ldg_bitmap_if(pnr > 3u, MB + pX3);
+                    my_fetch += (pneed0 ? 1u : 0u) + pnr - 1u;
+                }
+                // ---- phase A of this block: window minima and runs of equal minimizer (validity is ignored here: a window
+                //      that is not valid costs at most a wasted lookup; it is masked out of the items)
+                uint32_t chgraw = 0, wm_first = 0, vb = 0;
                 if (more) {
-                vb = v0 & 0xFFFF0000u;
-                v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
-
-                // ---- phase A: window minima and runs of equal minimizer (validity is ignored here: a window that is
-                //      not valid costs at most a wasted lookup; it is masked out of the items)
-                {
+                    vb = v0 & 0xFFFF0000u;
+                    v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
                     uint32_t Suf[16];
                     {
                         uint32_t smn = 0xFFFFFFFFu;
@@ -1319,62 +1317,75 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                     }
                     P -= 16u;                                      // block 2 of this block is block 1 of the next one
                 }
-                // runs 0..3 of the block are looked up; windows of later runs (rare) become items unfiltered
-                {
-                    t3 = chgraw;
+                // ---- this block's runs: 0..3 are looked up (addresses now, loads at the start of the next pass, use after
+                //      the next phase A); windows of later runs (rare) become items unfiltered
+                bool nneed0 = false;
+                uint32_t nW = 0, nchg = 0, nvm = 0, nnr = 1, nX0 = 0, nX1 = 0, nX2 = 0, nX3 = 0, nbits = 0;
+                if (more) {
+                    uint32_t t3 = chgraw;
                     t3 &= t3 - 1u; t3 &= t3 - 1u; t3 &= t3 - 1u;      // changes beyond the third
-                    chg = chgraw ^ t3;
-                }
-                ovfm = t3 ? (~((t3 & (0u - t3)) - 1u) & 0xFFFFu) : 0u;   // every window from the fourth change on
-                vwin = __brev(vb) & 0xFFFFu;                        // bit tt = validity of window tt
-                nrun = 1u + __popc(chg);
-                if (__any_sync(FULL, t3 != 0u)) {
-                    const uint32_t ia = lane | ((seg * WMAX + blk16) << 5);
-                    uint32_t rest = t3;
-                    unsigned rr = MZ_MAXRUN;
-                    while (__any_sync(FULL, rest != 0u)) {
-                        const uint32_t low = rest & (0u - rest), nxt = rest ^ low;
-                        const uint32_t upto = nxt ? (nxt & (0u - nxt)) : 0x10000u;
-                        const uint32_t mk = rest ? ((upto - low) & vwin) : 0u;
-                        const uint32_t w = rest ? lds32(wm_base + rr * MZ_ROW) : 0u;
-                        push(mk != 0u, ia, mk, w & 63u);
-                        drain_if_full();
-                        rest = nxt; ++rr;
+                    nchg = chgraw ^ t3;
+                    const uint32_t ovfm = t3 ? (~((t3 & (0u - t3)) - 1u) & 0xFFFFu) : 0u;   // every window from the fourth change on
+                    const uint32_t vwin = __brev(vb) & 0xFFFFu;      // bit tt = validity of window tt
+                    nnr = 1u + __popc(nchg);
+                    nvm = vwin & ~ovfm;
+                    if (__any_sync(FULL, t3 != 0u)) {
+                        const uint32_t ia = lane | ((seg * WMAX + blk16) << 5);
+                        uint32_t rest = t3;
+                        unsigned rr = MZ_MAXRUN;
+                        while (__any_sync(FULL, rest != 0u)) {
+                            const uint32_t low = rest & (0u - rest), nxt = rest ^ low;
+                            const uint32_t upto = nxt ? (nxt & (0u - nxt)) : 0x10000u;
+                            const uint32_t mk = rest ? ((upto - low) & vwin) : 0u;
+                            const uint32_t w = rest ? lds32(wm_base + rr * MZ_ROW) : 0u;
+                            push(mk != 0u, ia, mk, w & 63u);
+                            drain_if_full();
+                            rest = nxt; ++rr;
+                        }
                     }
-                }
-
-                }   // if (more)
-
-                // ---- the previous block's bit-array words have had a whole phase A to arrive
-                if (pend) consume();
-                if (!more) break;
-                pend = false;
-                more = blk + 1 < (int)(WMAX / 16) && !__all_sync(FULL, (v0 | v1 | v2) == 0u);   // anything valid after this block?
-
-                // ---- this block's lookups
-                {
-                    const bool need0 = !have || wm_first != held_wm;
                     const uint32_t W1 = lds32(wm_base + 1u * MZ_ROW), W2 = lds32(wm_base + 2u * MZ_ROW), W3 = lds32(wm_base + 3u * MZ_ROW);
-                    uint32_t bits = 0;
-                    auto lookup = [&](bool p, uint32_t w, unsigned sl) -> uint32_t {
+                    nneed0 = !have || wm_first != held_wm;
+                    have = true;
+                    held_wm = (nnr == 1u ? wm_first : nnr == 2u ? W1 : nnr == 3u ? W2 : W3) - 16u;
+                    nW = (wm_first & 63u) | ((W1 & 63u) << 8) | ((W2 & 63u) << 16) | ((W3 & 63u) << 24);
+                    auto locate = [&](uint32_t w, unsigned sl) -> uint32_t {
                         uint32_t ha, hb;
                         halves_at(blk16 + (w & 63u), ha, hb);
                         const uint32_t zlo = mz_ident_lo(ha, hb) & fmask_lo;
                         uint32_t word = zlo >> 5;
                         if (fmask_hi) word |= (mz_ident_hi(ha, hb) & fmask_hi) << 27;
-                        bits |= (zlo & 31u) << (8u * sl);
-                        return ldg_bitmap_if(p, MB + word);
+                        nbits |= (zlo & 31u) << (8u * sl);
+                        return word;
                     };
-                    pF0 = lookup(need0, wm_first, 0);
-                    pF1 = lookup(nrun > 1u, W1, 1);
-                    pF2 = lookup(nrun > 2u, W2, 2);
-                    pF3 = lookup(nrun > 3u, W3, 3);
-                    my_fetch += (need0 ? 1u : 0u) + nrun - 1u;
-                    pW0 = wm_first; pW1 = W1; pW2 = W2; pW3 = W3; pbits = bits;
-                    pneed0 = need0; pnr = nrun; pchg = chg; pvm = vwin & ~ovfm; pblk = blk16; pend = true;
-                    have = true;
-                    held_wm = (nrun == 1u ? wm_first : nrun == 2u ? W1 : nrun == 3u ? W2 : W3) - 16u;
+                    nX0 = locate(wm_first, 0); nX1 = locate(W1, 1); nX2 = locate(W2, 2); nX3 = locate(W3, 3);
                 }
+                // ---- the previous block's words have had a phase A and the address work above to arrive
+                if (pend) {
+                    const bool b0 = pneed0 ? ((F0 >> (pbits & 31u)) & 1u) : held_pass;
+                    const bool b1 = (pnr > 1u) & ((F1 >> ((pbits >> 8) & 31u)) & 1u);
+                    const bool b2 = (pnr > 2u) & ((F2 >> ((pbits >> 16) & 31u)) & 1u);
+                    const bool b3 = (pnr > 3u) & ((F3 >> ((pbits >> 24) & 31u)) & 1u);
+                    held_pass = pnr == 1u ? b0 : pnr == 2u ? b1 : pnr == 3u ? b2 : b3;
+                    // windows of run 0..3: [0, c1) [c1, c2) [c2, c3) [c3, 16); sentinels above bit 15 stand in for missing changes
+                    uint32_t cc = pchg | 0x70000u;
+                    const uint32_t c1 = cc & (0u - cc); cc ^= c1;
+                    const uint32_t c2 = cc & (0u - cc); cc ^= c2;
+                    const uint32_t c3 = cc & (0u - cc);
+                    const uint32_t m0 = (c1 - 1u) & pvm, m1 = (c2 - c1) & pvm, m2 = (c3 - c2) & pvm, m3 = (0x10000u - c3) & pvm;
+                    const bool q0 = b0 & (m0 != 0u), q1 = b1 & (m1 != 0u), q2 = b2 & (m2 != 0u), q3 = b3 & (m3 != 0u);
+                    if (__any_sync(FULL, q0 | q1 | q2 | q3)) {
+                        const uint32_t ia = lane | ((seg * WMAX + pblk) << 5);
+                        push(q0, ia, m0, pW & 63u);
+                        push(q1, ia, m1, (pW >> 8) & 63u);
+                        push(q2, ia, m2, (pW >> 16) & 63u);
+                        push(q3, ia, m3, pW >> 24);
+                        drain_if_full();
+                    }
+                }
+                if (!more) break;
+                pneed0 = nneed0; pW = nW; pnr = nnr; pchg = nchg; pvm = nvm; pblk = blk16; pend = true;
+                pX0 = nX0; pX1 = nX1; pX2 = nX2; pX3 = nX3; pbits = nbits;
+                more = blk + 1 < (int)(WMAX / 16) && !__all_sync(FULL, (v0 | v1 | v2) == 0u);   // anything valid after this block?
                 // slide the register windows by one word
 #pragma unroll
                 for (int k = 0; k < (int)SEGW - 1; ++k) loc[k] = loc[k + 1];

@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 ) > gpurun_out/r2d_tests.log
-( SWEEP_G=2e5 SWEEP_READS=4e6 timeout 300 python scripts/sweep_probe.py 2>&1 | tail -5 ) > gpurun_out/r2d_sweep.log
-( MLG_MZ_FBITS=33 SWEEP_G=2e5 SWEEP_READS=4e6 timeout 300 python scripts/sweep_probe.py 2>&1 | tail -5 ) >> gpurun_out/r2d_sweep.log
-( MLG_LIB_PATH=$PWD/metalign_b200/libmlg_var_m3.so SWEEP_G=2e5 SWEEP_READS=4e6 timeout 300 python scripts/sweep_probe.py 2>&1 | tail -5 ) >> gpurun_out/r2d_sweep.log
-SWEEP_G=2e5 SWEEP_READS=4e6 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_minimizer -s 2 -c 1 -f -o gpurun_out/r2d_k1mz python scripts/sweep_probe.py > gpurun_out/r2d_ncu.log 2>&1
-cat gpurun_out/r2d_tests.log gpurun_out/r2d_sweep.log
+( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 ) > gpurun_out/r2g_tests.log
+( SWEEP_G=2e5 SWEEP_READS=4e6 timeout 300 python scripts/sweep_probe.py 2>&1 | tail -5 ) > gpurun_out/r2g_sweep.log
+SWEEP_G=2e5 SWEEP_READS=4e6 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_minimizer -s 2 -c 1 -f -o gpurun_out/r2g_k1mz python scripts/sweep_probe.py > gpurun_out/r2g_ncu.log 2>&1
+cat gpurun_out/r2g_tests.log gpurun_out/r2g_sweep.log
