@@ -114,8 +114,8 @@ __global__ void k_fill_mzbits(const key128* D, uint32_t nd, uint32_t K, uint32_t
     key_mz(D[i], K, &zL, &zR);
     if (pass == 0) {
         const unsigned long long bl = mz_bit_index(zL, fbits), br = mz_bit_index(zR, fbits);
-        atomicOr(&MB[bl >> 5], 1u << (bl & 31ull));
-        if (zR != zL) { atomicOr(&MB[br >> 5], 1u << (br & 31ull)); atomicAdd(counter, 1ull); }
+        atomicOr(&MB[bl >> 5], (1u << (bl & 31ull)) | (1u << mz_bit2((uint32_t)(zL >> 32))));
+        if (zR != zL) { atomicOr(&MB[br >> 5], (1u << (br & 31ull)) | (1u << mz_bit2((uint32_t)(zR >> 32)))); atomicAdd(counter, 1ull); }
     } else if (zR != zL) {
         const unsigned long long j = atomicAdd(counter, 1ull);
         alias_z[j] = zR; alias_i[j] = i;
@@ -414,10 +414,10 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             if ((double)nfw * 32.0 < 1.5 * (double)nd) nfw = 0;
         }
         if (v.layout == 2) {
-            // level-1 bit array: at least 128 bits per K-mer (<= 0.8 % of the bits set = the false-positive rate of a
-            // run; every false positive costs an exact compare of ~11 windows), 2^20 .. 2^36 bits
+            // level-1 bit array: at least 32 bits per K-mer, two bits set per K-mer (density <= 1/16, false-positive rate
+            // of a run ~ density^2 <= 0.4 %; every false positive costs an exact compare of ~11 windows), 2^20 .. 2^36 bits
             uint32_t fbits = 20;
-            while (fbits < 36 && (1ull << fbits) < 128ull * nd) ++fbits;
+            while (fbits < 36 && (1ull << fbits) < 32ull * nd) ++fbits;
             if (const char* s = getenv("MLG_MZ_FBITS")) { int x = atoi(s); if (x >= 10 && x <= 36) fbits = (uint32_t)x; }
             v.fbits = fbits;
             nfw = 1ull << (fbits - 5);

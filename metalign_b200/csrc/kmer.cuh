@@ -201,9 +201,10 @@ MLG_HD unsigned long long key_hash_sk(const key128& x, unsigned K, unsigned bbit
 //     The probe kernel computes (order << 6 | position) with two multiply-adds (the multiplier carries the << 6, the
 //     position rides in the addend), so a plain unsigned min yields the minimum, the tie-break AND where it is.
 //   * identity: mz_ident(a, b), a 64-bit mix of the unordered pair {a, b}, i.e. of the canonical 32-mer.  Level 1 is
-//     a bit array indexed by the low bits of it: a run of windows sharing a minimizer (a super-k-mer) whose bit is
-//     clear contains no database K-mer, decided by ONE 32-byte DRAM sector and no per-window compare.  2^64 identities
-//     do not saturate; false positives are the bit density (<= 1/32 by the sizing rule in db.cu).
+//     a bit array indexed by the low bits of it, two bits per identity in one word: a run of windows sharing a
+//     minimizer (a super-k-mer) with either bit clear contains no database K-mer, decided by ONE DRAM access and no
+//     per-window compare.  2^64 identities do not saturate; false positives are the square of the bit density
+//     (<= 1/16 by the sizing rule in db.cu, so ~0.2 %).
 //   * a database K-mer x is filed under the identity of its leftmost minimum (what a read carrying x forward finds);
 //     a read carrying rc(x) finds x's RIGHTMOST minimum.  The two differ only when the order ties between 32-mers of
 //     different content (~4e-7 of the K-mers); those K-mers get a second bit and an entry in a small alias table.
@@ -222,6 +223,9 @@ MLG_HD unsigned mz_ident_hi(unsigned a, unsigned b) {
     return mz_mix(lo * 0xC2B2AE35u + hi * 0x27D4EB2Fu + 0x165667B1u);
 }
 MLG_HD unsigned long long mz_ident(unsigned a, unsigned b) { return ((unsigned long long)mz_ident_hi(a, b) << 32) | mz_ident_lo(a, b); }
+// every identity sets TWO bits of its 32-bit word (blocked Bloom filter: one DRAM access, false positives ~ density^2):
+// bit (ident & 31) and this one, taken from identity bits that do not take part in the word index
+MLG_HD unsigned mz_bit2(unsigned ident_hi) { return ident_hi >> 27; }
 MLG_HD unsigned long long mz_bit_index(unsigned long long ident, unsigned fbits) {       // 5 <= fbits <= 36
     return fbits >= 64 ? ident : (ident & ((1ull << fbits) - 1ull));
 }

@@ -979,7 +979,7 @@ struct MzWin {
     key128 cn, d0, d1;           // canonical key of the window; first two k-mers of the bucket
     uint32_t s, e, j0, j1;       // bucket range in D, alias range
 };
-__device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long long p, unsigned long long pm,
+__device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long long p, unsigned long long pm, bool untested,
                                                 const unsigned long long* bsrc, unsigned long long base_words, const DbView& db) {
     w.s = w.e = w.j0 = w.j1 = 0;
     w.cn.hi = w.cn.lo = 0; w.d0 = w.cn; w.d1 = w.cn;
@@ -988,6 +988,11 @@ __device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long
     mz_bases64(bsrc, base_words, pm, mh, ml);
     const uint32_t ha = (uint32_t)(mh >> 32), hb = rev2_32(~(uint32_t)mh);
     const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
+    if (untested) {               // a run beyond the fourth of its block: its level-1 word was not fetched ahead
+        const unsigned long long idx = mz_bit_index(((unsigned long long)zhi << 32) | zlo, db.fbits);
+        const uint32_t f = db.F[idx >> 5];
+        if (!((f >> (zlo & 31u)) & (f >> mz_bit2(zhi)) & 1u)) return;
+    }
     const uint32_t bucket = zhi >> (32u - db.bbits);
     w.s = db.bstart[bucket]; w.e = db.bstart[bucket + 1];
     // K-mers filed under a second identity (order ties) are rare: a 2^16-bit array says whether to look at all
@@ -1044,7 +1049,7 @@ __device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const ui
             const uint32_t tt = __fns(kb & 0xFFFFu, 0u, (int)(w - qoff[j]) + 1);
             const unsigned long long pb = r0s[ia & 31u] + (ia >> 5);
             MzWin win;
-            mz_window_begin(win, true, pb + tt, pb + (kb >> 16), bsrc, base_words, db);
+            mz_window_begin(win, true, pb + tt, pb + ((kb >> 16) & 63u), (kb >> 31) != 0u, bsrc, base_words, db);
             mz_window_end(win, db, cs);
         }
         __syncwarp();
@@ -1269,7 +1274,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
             // body (nothing is in flight across the back edge), and no vote or other convergence point lies between them.
             bool pend = false, pneed0 = false, more = true;          // more: the segment has valid windows (checked above)
             uint32_t pW = 0, pchg = 0, pvm = 0, pnr = 0, pblk = 0;   // pW: positions of the minimizers of runs 0..3 (8 bits each)
-            uint32_t pX0 = 0, pX1 = 0, pX2 = 0, pX3 = 0, pbits = 0;  // word index and bit (8 bits each) of their lookups
+            uint32_t pX0 = 0, pX1 = 0, pX2 = 0, pX3 = 0, pbits = 0, pbit2 = 0;  // word index and the two bits (8 bits each) of their lookups
 #pragma unroll 1
             for (int blk = 0;; ++blk) {
                 const uint32_t blk16 = (uint32_t)blk * 16u;
@@ -1320,7 +1325,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                 // ---- this block's runs: 0..3 are looked up (addresses now, loads at the start of the next pass, use after
                 //      the next phase A); windows of later runs (rare) become items unfiltered
                 bool nneed0 = false;
-                uint32_t nW = 0, nchg = 0, nvm = 0, nnr = 1, nX0 = 0, nX1 = 0, nX2 = 0, nX3 = 0, nbits = 0;
+                uint32_t nW = 0, nchg = 0, nvm = 0, nnr = 1, nX0 = 0, nX1 = 0, nX2 = 0, nX3 = 0, nbits = 0, nbit2 = 0;
                 if (more) {
                     uint32_t t3 = chgraw;
                     t3 &= t3 - 1u; t3 &= t3 - 1u; t3 &= t3 - 1u;      // changes beyond the third
@@ -1338,7 +1343,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                             const uint32_t upto = nxt ? (nxt & (0u - nxt)) : 0x10000u;
                             const uint32_t mk = rest ? ((upto - low) & vwin) : 0u;
                             const uint32_t w = rest ? lds32(wm_base + rr * MZ_ROW) : 0u;
-                            push(mk != 0u, ia, mk, w & 63u);
+                            push(mk != 0u, ia, mk, (w & 63u) | 0x8000u);     // bit 31 of the item: level 1 not looked at yet
                             drain_if_full();
                             rest = nxt; ++rr;
                         }
@@ -1351,20 +1356,22 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                     auto locate = [&](uint32_t w, unsigned sl) -> uint32_t {
                         uint32_t ha, hb;
                         halves_at(blk16 + (w & 63u), ha, hb);
-                        const uint32_t zlo = mz_ident_lo(ha, hb) & fmask_lo;
-                        uint32_t word = zlo >> 5;
-                        if (fmask_hi) word |= (mz_ident_hi(ha, hb) & fmask_hi) << 27;
+                        const uint32_t zlo = mz_ident_lo(ha, hb) & fmask_lo, zhi = mz_ident_hi(ha, hb);
                         nbits |= (zlo & 31u) << (8u * sl);
-                        return word;
+                        nbit2 |= mz_bit2(zhi) << (8u * sl);
+                        return (zlo >> 5) | ((zhi & fmask_hi) << 27);
                     };
                     nX0 = locate(wm_first, 0); nX1 = locate(W1, 1); nX2 = locate(W2, 2); nX3 = locate(W3, 3);
                 }
                 // ---- the previous block's words have had a phase A and the address work above to arrive
                 if (pend) {
-                    const bool b0 = pneed0 ? ((F0 >> (pbits & 31u)) & 1u) : held_pass;
-                    const bool b1 = (pnr > 1u) & ((F1 >> ((pbits >> 8) & 31u)) & 1u);
-                    const bool b2 = (pnr > 2u) & ((F2 >> ((pbits >> 16) & 31u)) & 1u);
-                    const bool b3 = (pnr > 3u) & ((F3 >> ((pbits >> 24) & 31u)) & 1u);
+                    auto both = [&](uint32_t f, unsigned sh) -> bool {       // both bits of the identity set in its word
+                        return ((f >> ((pbits >> sh) & 31u)) & (f >> ((pbit2 >> sh) & 31u)) & 1u) != 0u;
+                    };
+                    const bool b0 = pneed0 ? both(F0, 0) : held_pass;
+                    const bool b1 = (pnr > 1u) & both(F1, 8);
+                    const bool b2 = (pnr > 2u) & both(F2, 16);
+                    const bool b3 = (pnr > 3u) & both(F3, 24);
                     held_pass = pnr == 1u ? b0 : pnr == 2u ? b1 : pnr == 3u ? b2 : b3;
                     // windows of run 0..3: [0, c1) [c1, c2) [c2, c3) [c3, 16); sentinels above bit 15 stand in for missing changes
                     uint32_t cc = pchg | 0x70000u;
@@ -1384,7 +1391,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                 }
                 if (!more) break;
                 pneed0 = nneed0; pW = nW; pnr = nnr; pchg = nchg; pvm = nvm; pblk = blk16; pend = true;
-                pX0 = nX0; pX1 = nX1; pX2 = nX2; pX3 = nX3; pbits = nbits;
+                pX0 = nX0; pX1 = nX1; pX2 = nX2; pX3 = nX3; pbits = nbits; pbit2 = nbit2;
                 more = blk + 1 < (int)(WMAX / 16) && !__all_sync(FULL, (v0 | v1 | v2) == 0u);   // anything valid after this block?
                 // slide the register windows by one word
 #pragma unroll
