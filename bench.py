@@ -324,8 +324,9 @@ def run_native(args):
     launches = int(sum(s["gpu_launches"] for s in st_dev))
 
     if layout == 2 and tr and tr.get("layout") == 2:
-        limiter = ("the ALU pipe, not HBM: one bitmap sector per ~%.0f k-mers, so DRAM runs at %.0f GB/s while the SMs issue %.0f warp "
-                   "instructions per 32 k-mers at %.0f %% issue-slot utilisation (ncu, %s); see DESIGN.md section 4"
+        limiter = ("instruction issue and load latency at 16 resident warps per SM, not HBM bandwidth: one level-1 access per ~%.0f "
+                   "k-mers (DRAM moves %.0f GB/s under ncu, 128 bytes per random access), %.0f warp instructions per 32 k-mers at "
+                   "%.0f %% issue-slot utilisation (ncu, %s); see DESIGN.md section 4"
                    % (kmers_step / max(1, fetches), tr.get("dram_gbs_under_ncu", 0), tr.get("warp_instructions_per_32_kmers", 0),
                       tr.get("issue_active_pct", 0), tr.get("source", "")))
     elif layout == 1 and tr and tr.get("layout") == 1:
@@ -361,7 +362,7 @@ def run_native(args):
                          "algorithmic_bytes_per_launch_set": int(alg_bytes), "kernel_ms_per_step": probe_ms,
                          "finish_stage_ms_per_step": query_ms, "kmers_per_s_kernel_only": kmers_step / (probe_ms / 1e3),
                          "layout": layout, "bucket_fetches_per_step": fetches, "kmers_per_bucket_fetch": kmers_step / max(1, fetches),
-                         "algorithmic_bytes_rule": "level-1 fetches x %d B + packed bases + N mask (SURVEY.md 8d, minimizer bucketing: layout 2 = one 32-byte sector of the exact minimizer bitmap per super-k-mer, layout 1 = one 64-byte fingerprint-bucket pair per super-k-mer, layout 0 = one sector per k-mer)" % bucket_bytes,
+                         "algorithmic_bytes_rule": "level-1 fetches x %d B + packed bases + N mask (SURVEY.md 8d, minimizer bucketing: layout 2 = one 32-byte sector of the minimizer-identity bit array per super-k-mer, layout 1 = one 64-byte fingerprint-bucket pair per super-k-mer, layout 0 = one sector per k-mer)" % bucket_bytes,
                          "sector_per_kmer_equivalent_gbs": (kmers_step * 32 + nbases // 4 + nbases // 8) / (probe_ms / 1e3) / 1e9,
                          "limiter": limiter},
             "clocks": clocks,

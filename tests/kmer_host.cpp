@@ -21,4 +21,5 @@ unsigned long long t_mz_ident(unsigned a, unsigned b) { return mz_ident(a, b); }
 void t_key_mz(unsigned long long hi, unsigned long long lo, unsigned K, unsigned long long* out) { key128 a{hi, lo}; key_mz(a, K, out, out + 1); }
 unsigned long long t_mz_bit_index(unsigned long long z, unsigned fbits) { return mz_bit_index(z, fbits); }
 unsigned t_mz_bucket(unsigned long long z, unsigned bbits) { return mz_bucket(z, bbits); }
+unsigned t_mz_bit2(unsigned zhi) { return mz_bit2(zhi); }
 }

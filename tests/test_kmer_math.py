@@ -54,6 +54,8 @@ def kh(tmp_path_factory):
     L.t_mz_bit_index.restype = u64
     L.t_mz_bucket.argtypes = [u64, C.c_uint]
     L.t_mz_bucket.restype = C.c_uint
+    L.t_mz_bit2.argtypes = [C.c_uint]
+    L.t_mz_bit2.restype = C.c_uint
     return L
 
 
@@ -191,6 +193,7 @@ def test_minimizer32_layout_math(kh):
             assert kh.t_mz_bit_index(zl, fbits) == zl & ((1 << fbits) - 1)
         for bbits in (1, 13, 31):
             assert kh.t_mz_bucket(zl, bbits) == (zl >> 32) >> (32 - bbits)
+        assert kh.t_mz_bit2(zl >> 32) == zl >> 59          # the second bit comes from identity bits outside the word index
     assert ties <= 2                      # homopolymers and short tandem repeats tie between 32-mers of EQUAL content
     # runs of equal minimizer along a sequence: ~2/(w+1) changes per window with w = 29 positions
     seq = "".join(rng.choice("ACGT") for _ in range(5000))
