@@ -17,6 +17,9 @@
  *                          30-60-10 -c 0 -r 1000000 -v -f <bf> --sensitive` (select_db.py:58-76) up to, but
  *                          not including, the pandas filter/sort/to_csv tail, which stays on the host
  *   mlg_query_intersection the contents of `60mers_intersection_dump` (select_db.py:58-59)
+ *   mlg_sketch_genomes     (offline) CMash `MakeStreamingDNADatabase.py <list> <h5> -n 1000 -k 60`
+ *                          (local_tests/retrain_and_test_metalign.sh:49): the bottom-n MinHash sketches the
+ *                          database above is made of
  *
  * Conventions
  *   - every function returns MLG_OK (0) or a negative error code; mlg_last_error() gives the message
@@ -73,7 +76,7 @@ typedef struct mlg_stats {
     uint32_t probe_launches; /* number of probe kernel launches in ms_probe */
     uint32_t filter_words;   /* L2 prefilter: number of 32-bit words, 0 = no prefilter */
     uint64_t n_bucket_fetches; /* level-1 fetches from HBM: one per k-mer in layout 0, one per super-k-mer in layouts 1 and 2 */
-    uint32_t layout;         /* 0 = bucket by hash of the whole k-mer (+ L2 prefilter), 1 = fingerprint bucket pair by minimizer, 2 = exact bitmap over minimizer values (K = 60 default) */
+    uint32_t layout;         /* 0 = bucket by hash of the whole k-mer (+ L2 prefilter), 1 = fingerprint bucket pair by 16-base minimizer, 2 = bit array over the identities of 32-base minimizers (K = 60 default) */
     uint32_t reserved;
 } mlg_stats;
 
@@ -137,6 +140,24 @@ int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint6
 int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n);
 int mlg_query_stats(mlg_query* q, mlg_stats* out);
 int mlg_query_free(mlg_query* q);
+
+/* Sketch builder (offline): bottom-n MinHash sketch of G genomes, CMash semantics (MinHash.CountEstimator with
+ * rev_comp=False, as MakeStreamingDNADatabase.py builds Metalign's training database): every K-long window of
+ * text[genome_off[g] .. genome_off[g+1]) that consists of ACGT/acgt only is upper-cased and hashed with
+ * MurmurHash3_x64_128 (seed 0, first 64-bit word) modulo `prime` (0 = CMash's 9999999999971); a genome's sketch is its n
+ * smallest distinct hash values in ascending order.  Records (contigs) of one genome are separated by any non-ACGT byte.
+ * Outputs (host, G*n slots): mins (prime where the slot is unused), counts (occurrences of the hash in the genome),
+ * kmers (K bytes per slot: the first k-mer with that hash, upper case; NUL-filled where unused -- the layout
+ * mlg_db_from_ascii takes).  G < 2^20 genomes per call. */
+typedef struct mlg_sketch_stats {
+    uint64_t n_windows;      /* N-free K-long windows hashed */
+    uint64_t n_candidates;   /* windows below their genome's threshold (sorted and ranked) */
+    double ms_kernels;       /* CUDA-event time of the kernels, all passes */
+    uint32_t passes;         /* device passes (more than ceil(bytes / 1 GB) when a genome needed a wider threshold) */
+    uint32_t reserved;
+} mlg_sketch_stats;
+int mlg_sketch_genomes(mlg_ctx* ctx, const char* text, const uint64_t* genome_off /* G+1 */, uint32_t G, uint32_t n, uint32_t K,
+                       uint64_t prime, uint64_t* mins, uint32_t* counts, char* kmers, mlg_sketch_stats* stats_or_null);
 
 #ifdef __cplusplus
 }

@@ -75,7 +75,13 @@ SIGNATURES = {
     "mlg_query_intersection": (C.c_int, [_vp, _u64p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mlg_query_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "mlg_query_free": (C.c_int, [_vp]),
+    "mlg_sketch_genomes": (C.c_int, [_vp, _vp, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, _u64p, _u32p, _vp, _vp]),
 }
+
+
+class SketchStats(C.Structure):
+    _fields_ = [("n_windows", C.c_uint64), ("n_candidates", C.c_uint64), ("ms_kernels", C.c_double), ("passes", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 def lib():

@@ -72,6 +72,16 @@ def ascii_to_keys(buf: np.ndarray, K: int) -> np.ndarray:
     return np.stack([hi, lo], axis=1)
 
 
+def ascii_slots_to_keys(buf: np.ndarray, K: int) -> np.ndarray:
+    """like ascii_to_keys, but a slot that starts with NUL is an empty sketch slot ('' in CMash's CE._kmers): key (~0, ~0)"""
+    buf = np.asarray(buf, dtype=np.uint8).reshape(-1, K)
+    keys = np.full((buf.shape[0], 2), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    full = buf[:, 0] != 0
+    if full.any():
+        keys[full] = ascii_to_keys(buf[full], K)
+    return keys
+
+
 def pack_reads(reads):
     """list of read strings -> (bases uint8[], nmask uint8[], off uint64[N+1]); buffers padded to 16 bytes."""
     lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
