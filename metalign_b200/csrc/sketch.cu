@@ -232,7 +232,10 @@ static int sketch_pass(mlg_ctx* ctx, const char* text, const uint64_t* off, cons
     }
     CUDA_TRY(cudaMemcpyAsync(d_gend.p, g_end.data(), ng * 8ull, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(d_gT.p, g_T.data(), ng * 8ull, cudaMemcpyHostToDevice, s));
+    // kernel time only: event pairs around the launches, allocations and host round trips outside them
     cudaEvent_t e0, e1; CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    float ms_sum = 0;
+    auto lap = [&]() { float ms = 0; if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ms_sum += ms; };
     CUDA_TRY(cudaEventRecord(e0, s));
     k_valid_mask<<<nblk(padded), TPB, 0, s>>>(d_text.p, padded, d_vmask.p);
     k_fill_u64<<<nblk(slots), TPB, 0, s>>>(d_mins.p, slots, prime);
@@ -242,6 +245,8 @@ static int sketch_pass(mlg_ctx* ctx, const char* text, const uint64_t* off, cons
     CUDA_TRY(cudaMemsetAsync(d_gfirst.p, 0, ng * 4ull, s));
     CUDA_TRY(cudaMemsetAsync(d_gseen.p, 0, ng * 4ull, s));
     CUDA_TRY(cudaMemsetAsync(d_glast.p, 0, ng * 4ull, s));
+    CUDA_TRY(cudaEventRecord(e1, s));
+    lap();
 
     // candidates: ~4n per genome are expected (more when k-mers repeat); grow and redo the pass if the list overflows
     unsigned long long cap = std::min<unsigned long long>(nwin_total, (unsigned long long)ng * 8ull * n + 4096ull);
@@ -250,14 +255,17 @@ static int sketch_pass(mlg_ctx* ctx, const char* text, const uint64_t* off, cons
         if (cap == 0) cap = 1;
         MLG_TRY(d_ckey.alloc(cap)); MLG_TRY(d_cpos.alloc(cap));
         CUDA_TRY(cudaMemsetAsync(d_cnt.p, 0, 16, s));
+        CUDA_TRY(cudaEventRecord(e0, s));
         if (!tile_g.empty()) {
             SketchArgs a{reinterpret_cast<const unsigned long long*>(d_text.p), d_vmask.p, d_tile_g.p, d_tile_pos.p, d_gend.p, d_gT.p, K, prime,
                          ~0ull / prime, d_ckey.p, d_cpos.p, cap, d_cnt.p};
             k_hash_windows<<<(unsigned)tile_g.size(), TPB, 0, s>>>(a);
             CUDA_TRY(cudaGetLastError());
         }
+        CUDA_TRY(cudaEventRecord(e1, s));
         CUDA_TRY(cudaMemcpyAsync(cnt, d_cnt.p, 16, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        lap();
         if (cnt[0] <= cap) break;
         if (attempt >= 3) { mlg_set_error("sketch: candidate list overflow (%llu > %llu)", cnt[0], cap); return MLG_ERR_STATE; }
         cap = cnt[0] + 1024;
@@ -267,37 +275,30 @@ static int sketch_pass(mlg_ctx* ctx, const char* text, const uint64_t* off, cons
     std::vector<uint32_t> h_gdist(ng, 0);
     if (nc) {
         MLG_TRY(d_ckey_s.alloc(nc)); MLG_TRY(d_cpos_s.alloc(nc)); MLG_TRY(d_head.alloc(nc)); MLG_TRY(d_rank.alloc(nc));
-        {
-            void* tmp = nullptr; size_t tb = 0;
-            int gbits = 1; while (gbits < 20 && (1u << gbits) < ng) ++gbits;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, d_ckey.p, d_ckey_s.p, d_cpos.p, d_cpos_s.p, (int)nc, 0, (int)HBITS + gbits, s));
-            CUDA_TRY(cudaMalloc(&tmp, tb ? tb : 1));
-            cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, d_ckey.p, d_ckey_s.p, d_cpos.p, d_cpos_s.p, (int)nc, 0, (int)HBITS + gbits, s);
-            cudaStreamSynchronize(s); cudaFree(tmp);
-            if (e != cudaSuccess) { mlg_set_error("DeviceRadixSort failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
-        }
+        int gbits = 1; while (gbits < 20 && (1u << gbits) < ng) ++gbits;
+        size_t tb_sort = 0, tb_scan = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb_sort, d_ckey.p, d_ckey_s.p, d_cpos.p, d_cpos_s.p, (int)nc, 0, (int)HBITS + gbits, s));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb_scan, d_head.p, d_rank.p, (int)nc, s));
+        DevBuf<unsigned char> d_tmp; MLG_TRY(d_tmp.alloc(std::max(tb_sort, tb_scan) + 16));
+        CUDA_TRY(cudaEventRecord(e0, s));
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, tb_sort, d_ckey.p, d_ckey_s.p, d_cpos.p, d_cpos_s.p, (int)nc, 0, (int)HBITS + gbits, s));
         k_heads<<<nblk(nc), TPB, 0, s>>>(d_ckey_s.p, nc, d_head.p, d_gfirst.p);
-        {
-            void* tmp = nullptr; size_t tb = 0;
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_head.p, d_rank.p, (int)nc, s));
-            CUDA_TRY(cudaMalloc(&tmp, tb ? tb : 1));
-            cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, d_head.p, d_rank.p, (int)nc, s);
-            cudaStreamSynchronize(s); cudaFree(tmp);
-            if (e != cudaSuccess) { mlg_set_error("DeviceScan failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
-        }
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_tmp.p, tb_scan, d_head.p, d_rank.p, (int)nc, s));
         k_emit<<<nblk(nc), TPB, 0, s>>>(d_ckey_s.p, d_cpos_s.p, d_head.p, d_rank.p, nc, d_gfirst.p, n, K, d_text.p, d_mins.p, d_counts.p,
                                          d_kmers.p, d_gdist.p, d_gseen.p, d_glast.p);
         k_fix_last<<<nblk(ng), TPB, 0, s>>>(d_ckey_s.p, d_cpos_s.p, nc, ng, n, d_gdist.p, d_gseen.p, d_glast.p, d_counts.p);
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(e1, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        lap();
         CUDA_TRY(cudaMemcpyAsync(h_gdist.data(), d_gdist.p, ng * 4ull, cudaMemcpyDeviceToHost, s));
     }
-    CUDA_TRY(cudaEventRecord(e1, s));
     std::vector<unsigned long long> h_mins(slots); std::vector<uint32_t> h_counts(slots); std::vector<char> h_kmers(slots * K);
     CUDA_TRY(cudaMemcpyAsync(h_mins.data(), d_mins.p, slots * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(h_counts.data(), d_counts.p, slots * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(h_kmers.data(), d_kmers.p, slots * K, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (st) st->ms_kernels += ms;
+    if (st) st->ms_kernels += ms_sum;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (uint32_t i = 0; i < ng; ++i) {
         const uint32_t g = idx[i];
