@@ -359,6 +359,8 @@ def run_native(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": {2: "k1_minimizer_probe", 1: "k1_superkmer_probe"}.get(layout, "k1_decode_canon_probe"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         # the same fraction with the bytes the DRAM really moves (ncu): this part fetches 128 bytes per random access
+                         "dram_frac_from_ncu_traffic": (traffic / (probe_ms / 1e3) / 1e9 / peak) if traffic else None,
                          "algorithmic_bytes_per_launch_set": int(alg_bytes), "kernel_ms_per_step": probe_ms,
                          "finish_stage_ms_per_step": query_ms, "kmers_per_s_kernel_only": kmers_step / (probe_ms / 1e3),
                          "layout": layout, "bucket_fetches_per_step": fetches, "kmers_per_bucket_fetch": kmers_step / max(1, fetches),
