@@ -1,0 +1,547 @@
+#include "probe_common.cuh"
+
+namespace {
+
+// ======================================================================================================
+// K1, minimizer-bitmap layout (db.layout == 2, K == 60; definitions in kmer.cuh).  Same lane-per-read walk and
+// per-warp TMA pipelines as the super-k-mer kernel above, but the minimizer is a 32-mer whose (order << 6 | position)
+// value is two multiply-adds, level 1 is a bit array over minimizer IDENTITIES, and there is no per-window compare:
+//   phase A  sliding minimum over the 29 32-mers under each window (van Herk / Gil-Werman on blocks of 16 positions)
+//            and the runs of equal minimizer; values of new runs go to a per-lane list in shared memory;
+//   lookup   for up to MZ_MAXRUN runs per block of 16 windows the lane fetches the two halves of the minimizer from its
+//            copy of the segment in shared memory (the position is in the value), mixes their identity and loads the
+//            bit-array word (predicated LDG);
+//   deferred the words are looked at one block LATER (after the next block's phase A, which hides the DRAM latency):
+//            a run whose bit is set becomes an ITEM (source lane, first window of the block, identity, 16-bit mask of
+//            its valid windows) in a per-warp ring in shared memory.
+// Items are rare (bit density <= 1/32, plus the true hits); the ring is drained 32 at a time, one item per lane: the
+// lane rebuilds the canonical key of each window of the item from the staged bases and compares it with the database
+// k-mers filed under that identity (bucket index on the identity's high word, plus the alias table).
+#ifndef MZ_MINCTAS
+#define MZ_MINCTAS 2
+#endif
+constexpr unsigned MZ_MAXRUN = 4;             // runs per block whose bit-array word is fetched ahead (the carried one + 3 new)
+constexpr unsigned MZ_QDRAIN = 32;            // per-warp item list: drained whenever this many are waiting ...
+constexpr unsigned MZ_QCAP = MZ_QDRAIN + 128; // ... and one block of 16 windows adds at most 4 x 32
+constexpr unsigned MZ_LIST = 16;              // run list rows: a block of 16 windows starts at most 15 new runs (row 0 unused)
+constexpr uint32_t MZ_M64 = MLG_MZ_ORD_MULT << 6;   // the multiplier carries the << 6 of (order << 6 | position)
+struct MzShared {
+    SkStage stg;
+    uint32_t wm[MZ_LIST][RT];                 // [r][thread]: value of the r-th run START of the current block (r >= 1)
+    uint32_t seq[SEGW + 1][RT];               // [word][thread]: the lane's current segment (160 bases, top-aligned words)
+    uint32_t qa[WARPS][MZ_QCAP];              // item: source lane | index of the block's first window in the read << 5
+    uint32_t qb[WARPS][MZ_QCAP];              // item: windows of the block to compare exactly (bit tt = window tt) | base of the
+                                              //       minimizer relative to the block's first window << 16
+    uint32_t qoff[WARPS][32];                 // drain: windows before each item of the batch
+    uint32_t qn[WARPS];                       // items waiting
+    unsigned long long r0s[WARPS][32];        // stream position (in bases) of each lane's read of the current tile
+};
+constexpr uint32_t MZ_ROW = RT * 4;           // byte stride between rows of wm[] / seq[]
+
+__device__ __forceinline__ uint32_t ldg_bitmap_if(bool p, const uint32_t* ptr) {
+    uint32_t r;
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "setp.ne.u32 q, %1, 0;\n"
+        "mov.u32 %0, 0;\n"
+        "@q ld.global.nc.L1::no_allocate.b32 %0, [%2];\n"
+        "}\n" : "=r"(r) : "r"((uint32_t)p), "l"(ptr));
+    return r;
+}
+// (order << 6 | position) of the 32-mer at position 16j+i of the current block: first half = bases [16j+i, +16) of
+// loc[], reverse complement of the second half = the 16-mer at 16(j+1)+i seen through rcl[] (see sk_mmer)
+__device__ __forceinline__ uint32_t mz_val(const uint32_t (&loc)[SEGW], const uint32_t (&rcl)[SEGW], int j, int i) {
+    const uint32_t a = fsl(loc[j], loc[j + 1], 2 * i);
+    const int ra = i <= 11 ? 7 - j : 6 - j, ro = i <= 11 ? 11 - i : 27 - i;
+    const uint32_t b = fsl(rcl[ra], rcl[ra + 1], 2 * ro);
+    return b * MZ_M64 + (a * MZ_M64 + (uint32_t)(16 * j + i));
+}
+// 64 bases of the packed stream starting at base p, top-aligned (hi = the first 32)
+__device__ __forceinline__ void mz_bases64(const unsigned long long* bsrc, unsigned long long base_words, unsigned long long p,
+                                           unsigned long long& hi, unsigned long long& lo) {
+    const unsigned long long q = p >> 5;
+    const unsigned sh = 2u * (unsigned)(p & 31ull);
+    unsigned long long W[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned long long idx = q + k;
+        if (idx >= base_words) idx = base_words - 1;
+        W[k] = bswap64(bsrc[idx]);
+    }
+    hi = sh ? ((W[0] << sh) | (W[1] >> (64 - sh))) : W[0];
+    lo = sh ? ((W[1] << sh) | (W[2] >> (64 - sh))) : W[1];
+}
+// Exact compare of ONE window of an item (one lane), in two stages.  Stage 1: the window starts at base p, its minimizer
+// at base pm of the stream; identity, bucket range and the first two database k-mers of the bucket (both loads in flight
+// together).  (Two windows per lane and round were tried: the drain's code doubles and the kernel starts missing in the
+// instruction cache, which costs more than the extra memory parallelism gains.)
+struct MzWin {
+    key128 cn, d0, d1;           // canonical key of the window; first two k-mers of the bucket
+    uint32_t s, e, j0, j1;       // bucket range in D, alias range
+};
+__device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long long p, unsigned long long pm, bool untested,
+                                                const unsigned long long* bsrc, unsigned long long base_words, const DbView& db) {
+    w.s = w.e = w.j0 = w.j1 = 0;
+    w.cn.hi = w.cn.lo = 0; w.d0 = w.cn; w.d1 = w.cn;
+    if (!on) return;
+    unsigned long long mh, ml;
+    mz_bases64(bsrc, base_words, pm, mh, ml);
+    const uint32_t ha = (uint32_t)(mh >> 32), hb = rev2_32(~(uint32_t)mh);
+    const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
+    if (untested) {               // a run beyond the fourth of its block: its level-1 word was not fetched ahead
+        const unsigned long long idx = mz_bit_index(((unsigned long long)zhi << 32) | zlo, db.fbits);
+        const uint32_t f = db.F[idx >> 5];
+        if (!((f >> (zlo & 31u)) & (f >> mz_bit2(zhi)) & 1u)) return;
+    }
+    const uint32_t bucket = zhi >> (32u - db.bbits);
+    w.s = db.bstart[bucket]; w.e = db.bstart[bucket + 1];
+    // K-mers filed under a second identity (order ties) are rare: a 2^16-bit array says whether to look at all
+    if (db.n_alias && ((db.alias_bloom[(zlo & 0xFFFFu) >> 5] >> (zlo & 31u)) & 1u)) {
+        const unsigned long long z = ((unsigned long long)zhi << 32) | zlo;
+        uint32_t lo = 0, hi = db.n_alias;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (db.alias_z[mid] < z) lo = mid + 1; else hi = mid; }
+        w.j0 = w.j1 = lo;
+        while (w.j1 < db.n_alias && db.alias_z[w.j1] == z) ++w.j1;
+    }
+    key128 F;                                                       // 64 bases from p, top-aligned
+    mz_bases64(bsrc, base_words, p, F.hi, F.lo);
+    F = key_shr(F, 128 - 2 * SK_K);                                 // the 60-mer, bottom-aligned
+    const key128 G = key_rc(F, SK_K);
+    w.cn = key_lt(G, F) ? G : F;
+    if (w.s < w.e) w.d0 = db.D_key[w.s];
+    if (w.s + 1u < w.e) w.d1 = db.D_key[w.s + 1u];
+}
+// stage 2: compare with the database k-mers filed under the identity, count a match
+__device__ __forceinline__ void mz_window_end(const MzWin& w, const DbView& db, const CountSink& cs) {
+    if (w.s < w.e && w.d0.hi == w.cn.hi && w.d0.lo == w.cn.lo) { bump_counter(cs, w.s); return; }
+    if (w.s + 1u < w.e && w.d1.hi == w.cn.hi && w.d1.lo == w.cn.lo) { bump_counter(cs, w.s + 1u); return; }
+    for (uint32_t i = w.s + 2u; i < w.e; ++i) {
+        const key128 d = db.D_key[i];
+        if (d.hi == w.cn.hi && d.lo == w.cn.lo) { bump_counter(cs, i); return; }
+    }
+    for (uint32_t j = w.j0; j < w.j1; ++j) {
+        const uint32_t i = db.alias_i[j];
+        const key128 d = db.D_key[i];
+        if (d.hi == w.cn.hi && d.lo == w.cn.lo) { bump_counter(cs, i); return; }
+    }
+}
+// exact compare of every window of every waiting item of one warp, one WINDOW per lane (items have 1..16 windows)
+__device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const uint32_t* qb, uint32_t* qoff, const unsigned long long* r0s,
+                                      const unsigned long long* bsrc, unsigned long long base_words, const DbView& db, const CountSink& cs) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    __syncwarp();
+    const uint32_t n = *qn;
+    for (uint32_t base = 0; base < n; base += 32u) {
+        const uint32_t i = base + lane;
+        const uint32_t cnt = i < n ? (uint32_t)__popc(qb[i] & 0xFFFFu) : 0u;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += u; }
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
+        qoff[lane] = inc - cnt;
+        __syncwarp();
+        for (uint32_t w = lane; w < total; w += 32u) {
+            uint32_t j = 0;                              // the last item of the batch that starts at or before window w
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) if (qoff[j + step] <= w) j += step;
+            const uint32_t ia = qa[base + j], kb = qb[base + j];
+            const uint32_t tt = __fns(kb & 0xFFFFu, 0u, (int)(w - qoff[j]) + 1);
+            const unsigned long long pb = r0s[ia & 31u] + (ia >> 5);
+            MzWin win;
+            mz_window_begin(win, true, pb + tt, pb + ((kb >> 16) & 63u), (kb >> 31) != 0u, bsrc, base_words, db);
+            mz_window_end(win, db, cs);
+        }
+        __syncwarp();
+    }
+    __syncwarp();                 // every lane has read *qn, also when the list was empty and the loop did not run
+    if (lane == 0) *qn = 0;
+    __syncwarp();
+}
+
+template <bool HAS_NMASK>
+__global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a, DbView db) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MzShared& sm = *reinterpret_cast<MzShared*>(smem_raw);
+    SkStage& stg = sm.stg;
+    __shared__ __align__(8) unsigned long long mbar[WARPS][2];
+    __shared__ unsigned long long s_bw0[WARPS][2], s_mw0[WARPS][2];
+    __shared__ unsigned s_staged[WARPS][2];
+
+    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    constexpr unsigned K = SK_K;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const unsigned long long nreads = a.r_end - a.r_begin;
+    const unsigned long long ntiles = (nreads + 31) / 32;                 // a tile = the 32 reads of one warp pass
+    auto next_tile = [&]() -> unsigned long long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+        return __shfl_sync(FULL, t, 0);
+    };
+    const unsigned long long pol_stream = policy_evict_first();
+    const CountSink sink{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
+    const uint32_t wm_base = smem_u32(&sm.wm[0][tid]), seq_base = smem_u32(&sm.seq[0][tid]);
+    const uint32_t* const MB = db.F;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // bit index = identity & (2^fbits - 1): mask of its low word, and of its high word (0 up to 2^32 bits)
+    const uint32_t fmask_lo = db.fbits >= 32u ? 0xFFFFFFFFu : ((1u << db.fbits) - 1u);
+    const uint32_t fmask_hi = db.fbits > 32u ? ((1u << (db.fbits - 32u)) - 1u) : 0u;
+
+    if (lane == 0) {
+        mbar_init(&mbar[warp][0], 1);
+        mbar_init(&mbar[warp][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](unsigned stage, unsigned long long t) {
+        const unsigned long long r0 = a.r_begin + t * 32ull;
+        const unsigned long long r1 = (r0 + 32 < a.r_end) ? r0 + 32 : a.r_end;
+        const unsigned long long p0 = a.off ? a.off[r0] : r0 * (unsigned long long)a.read_len;
+        const unsigned long long p1 = a.off ? a.off[r1] : r1 * (unsigned long long)a.read_len;
+        unsigned long long bw0 = (p0 >> 5) & ~1ull;
+        unsigned long long bw1 = ((p1 + 31) >> 5) + 6;
+        if (bw1 > a.base_words) bw1 = a.base_words;
+        bw1 = (bw1 + 1) & ~1ull;
+        unsigned long long mw0 = (p0 >> 6) & ~1ull;
+        unsigned long long mw1 = ((p1 + 63) >> 6) + 4;
+        if (HAS_NMASK) { if (mw1 > a.nmask_words) mw1 = a.nmask_words; mw1 = (mw1 + 1) & ~1ull; }
+        const unsigned long long bytes_b = (bw1 - bw0) * 8ull, bytes_m = HAS_NMASK ? (mw1 - mw0) * 8ull : 0ull;
+        const bool fits = bw1 > bw0 && bytes_b <= WSTAGE_B && bytes_m <= WSTAGE_M;
+        s_bw0[warp][stage] = bw0; s_mw0[warp][stage] = mw0; s_staged[warp][stage] = fits ? 1u : 0u;
+        if (fits) {
+            mbar_expect_tx(&mbar[warp][stage], (uint32_t)(bytes_b + bytes_m));
+            bulk_g2s(&stg.b[warp][stage][0], a.bases + bw0, (uint32_t)bytes_b, &mbar[warp][stage], pol_stream);
+            if (HAS_NMASK && bytes_m) bulk_g2s(&stg.m[warp][stage][0], a.nmask + mw0, (uint32_t)bytes_m, &mbar[warp][stage], pol_stream);
+        } else {
+            mbar_arrive(&mbar[warp][stage]);
+        }
+    };
+
+    unsigned long long my_valid = 0;
+    unsigned my_fetch = 0;
+    const unsigned long long* bsrc = a.bases;
+    if (lane == 0) sm.qn[warp] = 0;
+    __syncwarp();
+
+    // the two halves (a, b) of the 32-mer at base P of the lane's segment copy (b = reverse complement of the second half)
+    auto halves_at = [&](uint32_t P, uint32_t& ha, uint32_t& hb) {
+        const uint32_t ad = seq_base + (P >> 4) * MZ_ROW;
+        const uint32_t w0 = lds32(ad), w1 = lds32(ad + MZ_ROW), w2 = lds32(ad + 2u * MZ_ROW);
+        const unsigned sh = 2u * (P & 15u);
+        ha = fsl(w0, w1, sh);
+        hb = rev2_32(~fsl(w1, w2, sh));
+    };
+    auto drain = [&]() {
+        mz_drain(&sm.qn[warp], &sm.qa[warp][0], &sm.qb[warp][0], &sm.qoff[warp][0], &sm.r0s[warp][0], bsrc, a.base_words, db, sink);
+    };
+    // lanes with p append one item: windows `ik` of the block whose first window is `ia`, minimizer at base `rel` of the block
+    auto push = [&](bool p, uint32_t ia, uint32_t ik, uint32_t rel) {
+        if (p) {
+            const uint32_t i = atomicAdd(&sm.qn[warp], 1u);
+            sm.qa[warp][i] = ia; sm.qb[warp][i] = ik | (rel << 16);
+        }
+    };
+    auto drain_if_full = [&]() {
+        __syncwarp();
+        if (sm.qn[warp] >= MZ_QDRAIN) drain();
+    };
+
+    unsigned it = 0;
+    unsigned long long t = next_tile(), t_ahead = next_tile();       // the tile being processed and the one staged behind it
+    if (lane == 0) {
+        if (t < ntiles) issue(0, t);
+        if (t_ahead < ntiles) issue(1, t_ahead);
+    }
+    for (; t < ntiles; ++it) {
+        const unsigned stage = it & 1u, parity = (it >> 1) & 1u;
+        __syncwarp();
+        mbar_wait(&mbar[warp][stage], parity);
+
+        const unsigned long long r = a.r_begin + t * 32ull + lane;
+        const bool active = r < a.r_end;
+        unsigned long long R0 = 0, R1 = 0;
+        if (active) {
+            R0 = a.off ? a.off[r] : r * (unsigned long long)a.read_len;
+            R1 = a.off ? a.off[r + 1] : R0 + a.read_len;
+        }
+        sm.r0s[warp][lane] = R0;
+        const unsigned long long len = R1 - R0;
+        const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
+        const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
+        const unsigned max_seg = __reduce_max_sync(FULL, nseg);
+        const bool staged = s_staged[warp][stage] != 0;
+        bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[warp][stage][0]) - s_bw0[warp][stage] : a.bases;
+        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[warp][stage][0]) - s_mw0[warp][stage] : a.nmask;
+        __syncwarp();
+
+        for (unsigned seg = 0; seg < max_seg; ++seg) {
+            const unsigned c = seg < nseg ? (unsigned)((nw - (unsigned long long)seg * WMAX) < WMAX ? (nw - (unsigned long long)seg * WMAX) : WMAX) : 0u;
+            const unsigned long long s = R0 + (unsigned long long)seg * WMAX;
+
+            uint32_t loc[SEGW];
+            uint32_t nl[5];
+#pragma unroll
+            for (int k = 0; k < (int)SEGW; ++k) loc[k] = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) nl[k] = 0;
+            if (c) {
+                const unsigned long long q = s >> 5;
+                const unsigned sh = 2u * (unsigned)(s & 31ull);
+                unsigned long long W[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    unsigned long long idx = q + k;
+                    if (idx >= a.base_words) idx = a.base_words - 1;
+                    W[k] = bswap64(bsrc[idx]);
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const unsigned long long v = sh ? ((W[k] << sh) | (W[k + 1] >> (64 - sh))) : W[k];
+                    loc[2 * k] = (uint32_t)(v >> 32); loc[2 * k + 1] = (uint32_t)v;
+                }
+                if (HAS_NMASK) {
+                    const unsigned long long qn2 = s >> 6;
+                    const unsigned shn = (unsigned)(s & 63ull);
+                    unsigned long long M[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        unsigned long long idx = qn2 + k;
+                        if (idx >= a.nmask_words) idx = a.nmask_words - 1;
+                        M[k] = bswap64(msrc[idx]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const unsigned long long v = shn ? ((M[k] << shn) | (M[k + 1] >> (64 - shn))) : M[k];
+                        if (2 * k < 5) nl[2 * k] = (uint32_t)(v >> 32);
+                        if (2 * k + 1 < 5) nl[2 * k + 1] = (uint32_t)v;
+                    }
+                }
+            }
+            uint32_t v0, v1, v2;
+            {
+                if (HAS_NMASK && __any_sync(FULL, (nl[0] | nl[1] | nl[2] | nl[3] | nl[4]) != 0u)) {
+                    unsigned cover = 1;
+                    while (cover * 2 <= K) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], cover);
+                        nl[4] |= nl[4] << cover;
+                        cover *= 2;
+                    }
+                    const unsigned rest = K - cover;
+                    if (rest) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], rest);
+                        nl[4] |= nl[4] << rest;
+                    }
+                }
+                const uint32_t c0 = c >= 32 ? 0xFFFFFFFFu : (c ? ~(0xFFFFFFFFu >> c) : 0u);
+                const uint32_t c1 = c >= 64 ? 0xFFFFFFFFu : (c > 32 ? ~(0xFFFFFFFFu >> (c - 32)) : 0u);
+                const uint32_t c2 = c >= 96 ? 0xFFFFFFFFu : (c > 64 ? ~(0xFFFFFFFFu >> (c - 64)) : 0u);
+                v0 = ~nl[0] & c0; v1 = ~nl[1] & c1; v2 = ~nl[2] & c2;
+            }
+            my_valid += __popc(v0) + __popc(v1) + __popc(v2);
+            if (__all_sync(FULL, (v0 | v1 | v2) == 0u)) continue;
+
+            // the lane's copy of the segment (minimizer halves are fetched from it by position)
+#pragma unroll
+            for (int k = 0; k < (int)SEGW; ++k) sts32(seq_base + (uint32_t)k * MZ_ROW, loc[k]);
+            sts32(seq_base + SEGW * MZ_ROW, 0u);
+
+            // reverse complement of the segment: the complement of base x sits at base 154 - x of rcl[]
+            uint32_t rcl[SEGW];
+            {
+                uint32_t t160[SEGW + 1];
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) t160[k] = rev2_32(~loc[SEGW - 1 - k]);
+                t160[SEGW] = 0;
+                constexpr unsigned bs = 2u * (160u - (WMAX + K - 1u));
+                static_assert(bs < 32, "alignment shift must stay inside one word");
+#pragma unroll
+                for (int k = 0; k < (int)SEGW; ++k) rcl[k] = fsl(t160[k], t160[k + 1], bs);
+            }
+
+            // minimizer state carried from block to block: P = prefix minimum of position block 1 up to index 11
+            uint32_t P = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) P = min(P, mz_val(loc, rcl, 1, i));
+            // the value of the run the lane is in, re-based to the coming block (positions are block-relative), and
+            // whether its bit is set
+            uint32_t held_wm = 0;
+            bool have = false, held_pass = false;
+
+            // Block b's runs are found by phase A in pass b; their bit-array words are loaded at the START of pass b + 1 and
+            // looked at after that pass's phase A, which hides the DRAM latency.  Loads and their use sit in the same loop
+            // body (nothing is in flight across the back edge), and no vote or other convergence point lies between them.
+            bool pend = false, pneed0 = false, more = true;          // more: the segment has valid windows (checked above)
+            uint32_t pW = 0, pchg = 0, pvm = 0, pnr = 0, pblk = 0;   // pW: positions of the minimizers of runs 0..3 (8 bits each)
+            uint32_t pX0 = 0, pX1 = 0, pX2 = 0, pX3 = 0, pbits = 0, pbit2 = 0;  // word index and the two bits (8 bits each) of their lookups
+#pragma unroll 1
+            for (int blk = 0;; ++blk) {
+                const uint32_t blk16 = (uint32_t)blk * 16u;
+                // ---- load the bit-array words of the previous block's runs 0..3
+                uint32_t F0 = 0, F1 = 0, F2 = 0, F3 = 0;
+                if (pend) {
+                    F0 = ldg_bitmap_if(pneed0, MB + pX0);
+                    F1 = ldg_bitmap_if(pnr > 1u, MB + pX1);
+                    F2 = ldg_bitmap_if(pnr > 2u, MB + pX2);
+                    F3 = ldg_bitmap_if(pnr > 3u, MB + pX3);
+                    my_fetch += (pneed0 ? 1u : 0u) + pnr - 1u;
+                }
+                // ---- phase A of this block: window minima and runs of equal minimizer (validity is ignored here: a window
+                //      that is not valid costs at most a wasted lookup; it is masked out of the items)
+                uint32_t chgraw = 0, wm_first = 0, vb = 0;
+                if (more) {
+                    vb = v0 & 0xFFFF0000u;
+                    v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
+                    uint32_t Suf[16];
+                    {
+                        uint32_t smn = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = 15; i >= 0; --i) { smn = min(smn, mz_val(loc, rcl, 0, i)); Suf[i] = smn; }
+                    }
+                    uint32_t A1 = 0, pw = 0;
+                    uint32_t lst = wm_base + MZ_ROW;              // where the next run's value goes
+#pragma unroll
+                    for (int tt = 0; tt < 16; ++tt) {
+                        uint32_t wm;
+                        if (tt < 4) {                              // window tt: positions tt..15, then block 1 up to index tt + 12
+                            P = min(P, mz_val(loc, rcl, 1, 12 + tt));
+                            wm = min(Suf[tt], P);
+                            if (tt == 3) { A1 = P; P = 0xFFFFFFFFu; }
+                        } else {                                   // positions tt..15, all of block 1, block 2 up to index tt - 4
+                            P = min(P, mz_val(loc, rcl, 2, tt - 4));
+                            wm = min(min(Suf[tt], A1), P);
+                        }
+                        if (tt == 0) wm_first = wm;
+                        else if (wm != pw) {                       // a new run starts at window tt
+                            sts32(lst, wm);
+                            lst += MZ_ROW;
+                            chgraw |= 1u << tt;
+                        }
+                        pw = wm;
+                    }
+                    P -= 16u;                                      // block 2 of this block is block 1 of the next one
+                }
+                // ---- this block's runs: 0..3 are looked up (addresses now, loads at the start of the next pass, use after
+                //      the next phase A); windows of later runs (rare) become items unfiltered
+                bool nneed0 = false;
+                uint32_t nW = 0, nchg = 0, nvm = 0, nnr = 1, nX0 = 0, nX1 = 0, nX2 = 0, nX3 = 0, nbits = 0, nbit2 = 0;
+                if (more) {
+                    uint32_t t3 = chgraw;
+                    t3 &= t3 - 1u; t3 &= t3 - 1u; t3 &= t3 - 1u;      // changes beyond the third
+                    nchg = chgraw ^ t3;
+                    const uint32_t ovfm = t3 ? (~((t3 & (0u - t3)) - 1u) & 0xFFFFu) : 0u;   // every window from the fourth change on
+                    const uint32_t vwin = __brev(vb) & 0xFFFFu;      // bit tt = validity of window tt
+                    nnr = 1u + __popc(nchg);
+                    nvm = vwin & ~ovfm;
+                    if (__any_sync(FULL, t3 != 0u)) {
+                        const uint32_t ia = lane | ((seg * WMAX + blk16) << 5);
+                        uint32_t rest = t3;
+                        unsigned rr = MZ_MAXRUN;
+                        while (__any_sync(FULL, rest != 0u)) {
+                            const uint32_t low = rest & (0u - rest), nxt = rest ^ low;
+                            const uint32_t upto = nxt ? (nxt & (0u - nxt)) : 0x10000u;
+                            const uint32_t mk = rest ? ((upto - low) & vwin) : 0u;
+                            const uint32_t w = rest ? lds32(wm_base + rr * MZ_ROW) : 0u;
+                            push(mk != 0u, ia, mk, (w & 63u) | 0x8000u);     // bit 31 of the item: level 1 not looked at yet
+                            drain_if_full();
+                            rest = nxt; ++rr;
+                        }
+                    }
+                    const uint32_t W1 = lds32(wm_base + 1u * MZ_ROW), W2 = lds32(wm_base + 2u * MZ_ROW), W3 = lds32(wm_base + 3u * MZ_ROW);
+                    nneed0 = !have || wm_first != held_wm;
+                    have = true;
+                    held_wm = (nnr == 1u ? wm_first : nnr == 2u ? W1 : nnr == 3u ? W2 : W3) - 16u;
+                    nW = (wm_first & 63u) | ((W1 & 63u) << 8) | ((W2 & 63u) << 16) | ((W3 & 63u) << 24);
+                    auto locate = [&](uint32_t w, unsigned sl) -> uint32_t {
+                        uint32_t ha, hb;
+                        halves_at(blk16 + (w & 63u), ha, hb);
+                        const uint32_t zlo = mz_ident_lo(ha, hb) & fmask_lo, zhi = mz_ident_hi(ha, hb);
+                        nbits |= (zlo & 31u) << (8u * sl);
+                        nbit2 |= mz_bit2(zhi) << (8u * sl);
+                        return (zlo >> 5) | ((zhi & fmask_hi) << 27);
+                    };
+                    nX0 = locate(wm_first, 0); nX1 = locate(W1, 1); nX2 = locate(W2, 2); nX3 = locate(W3, 3);
+                }
+                // ---- the previous block's words have had a phase A and the address work above to arrive
+                if (pend) {
+                    auto both = [&](uint32_t f, unsigned sh) -> bool {       // both bits of the identity set in its word
+                        return ((f >> ((pbits >> sh) & 31u)) & (f >> ((pbit2 >> sh) & 31u)) & 1u) != 0u;
+                    };
+                    const bool b0 = pneed0 ? both(F0, 0) : held_pass;
+                    const bool b1 = (pnr > 1u) & both(F1, 8);
+                    const bool b2 = (pnr > 2u) & both(F2, 16);
+                    const bool b3 = (pnr > 3u) & both(F3, 24);
+                    held_pass = pnr == 1u ? b0 : pnr == 2u ? b1 : pnr == 3u ? b2 : b3;
+                    // windows of run 0..3: [0, c1) [c1, c2) [c2, c3) [c3, 16); sentinels above bit 15 stand in for missing changes
+                    uint32_t cc = pchg | 0x70000u;
+                    const uint32_t c1 = cc & (0u - cc); cc ^= c1;
+                    const uint32_t c2 = cc & (0u - cc); cc ^= c2;
+                    const uint32_t c3 = cc & (0u - cc);
+                    const uint32_t m0 = (c1 - 1u) & pvm, m1 = (c2 - c1) & pvm, m2 = (c3 - c2) & pvm, m3 = (0x10000u - c3) & pvm;
+                    const bool q0 = b0 & (m0 != 0u), q1 = b1 & (m1 != 0u), q2 = b2 & (m2 != 0u), q3 = b3 & (m3 != 0u);
+                    if (__any_sync(FULL, q0 | q1 | q2 | q3)) {
+                        const uint32_t ia = lane | ((seg * WMAX + pblk) << 5);
+                        push(q0, ia, m0, pW & 63u);
+                        push(q1, ia, m1, (pW >> 8) & 63u);
+                        push(q2, ia, m2, (pW >> 16) & 63u);
+                        push(q3, ia, m3, pW >> 24);
+                        drain_if_full();
+                    }
+                }
+                if (!more) break;
+                pneed0 = nneed0; pW = nW; pnr = nnr; pchg = nchg; pvm = nvm; pblk = blk16; pend = true;
+                pX0 = nX0; pX1 = nX1; pX2 = nX2; pX3 = nX3; pbits = nbits; pbit2 = nbit2;
+                more = blk + 1 < (int)(WMAX / 16) && !__all_sync(FULL, (v0 | v1 | v2) == 0u);   // anything valid after this block?
+                // slide the register windows by one word
+#pragma unroll
+                for (int k = 0; k < (int)SEGW - 1; ++k) loc[k] = loc[k + 1];
+#pragma unroll
+                for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
+            }
+        }
+        // items point into this tile's staged bases: finish them before the stage is refilled
+        drain();
+        const unsigned long long t_new = next_tile();
+        if (lane == 0 && t_new < ntiles) issue(stage, t_new);
+        t = t_ahead; t_ahead = t_new;
+    }
+
+    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(FULL, my_valid, o);
+    my_fetch = __reduce_add_sync(FULL, my_fetch);
+    if (lane == 0 && my_valid) atomicAdd(a.n_kmers, my_valid);
+    if (lane == 0 && my_fetch) atomicAdd(a.n_kmers + 1, (unsigned long long)my_fetch);
+}
+constexpr size_t K1MZ_SMEM = sizeof(MzShared);
+
+template <bool HAS_NMASK>
+int launch_mz_t(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
+    auto kern = k1_minimizer_probe<HAS_NMASK>;
+    static bool done[64] = {};          // the attribute is per device
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1MZ_SMEM));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(a.tile_counter, 0, 8, st));
+    kern<<<grid, RT, K1MZ_SMEM, st>>>(a, db);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+
+}  // namespace
+
+int launch_probe_mz(const DbView& db, const ProbeArgs& a, cudaStream_t st, int sm_count) {
+    if (db.K != SK_K || !db.F) { mlg_set_error("minimizer-bitmap layout needs K=60 and its bit array"); return MLG_ERR_STATE; }
+    // persistent: the CTAs that fit pull 32-read tiles from a global counter
+    const unsigned long long wtiles = (a.r_end - a.r_begin + 31) / 32;
+    const unsigned long long need = (wtiles + WARPS - 1) / WARPS;
+    int per_sm = MZ_MINCTAS;
+    if (const char* e = getenv("MLG_PROBE_CTAS_PER_SM")) { int x = atoi(e); if (x >= 1 && x <= 64) per_sm = x; }
+    const unsigned long long res = (unsigned long long)sm_count * (unsigned)per_sm;
+    const unsigned grid = (unsigned)(need < res ? need : res);
+    return a.nmask ? launch_mz_t<true>(db, a, st, grid) : launch_mz_t<false>(db, a, st, grid);
+}
