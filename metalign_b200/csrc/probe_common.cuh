@@ -102,6 +102,86 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return r;
 }
 
+// ---- one segment of a read: WMAX window starts, 160 bases, in registers (shared by the three K1 kernels) ----
+// gather the 160 bases (and their N bits) that start at stream base s, top-aligned; c = window starts of the segment (0: none)
+template <bool HAS_NMASK>
+__device__ __forceinline__ void segment_load(uint32_t (&loc)[SEGW], uint32_t (&nl)[5], unsigned c, unsigned long long s,
+                                             const unsigned long long* bsrc, const unsigned long long* msrc,
+                                             unsigned long long base_words, unsigned long long nmask_words) {
+#pragma unroll
+    for (int k = 0; k < (int)SEGW; ++k) loc[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nl[k] = 0;
+    if (c) {
+        const unsigned long long q = s >> 5;
+        const unsigned sh = 2u * (unsigned)(s & 31ull);
+        unsigned long long W[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            unsigned long long idx = q + k;
+            if (idx >= base_words) idx = base_words - 1;
+            W[k] = bswap64(bsrc[idx]);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const unsigned long long v = sh ? ((W[k] << sh) | (W[k + 1] >> (64 - sh))) : W[k];
+            loc[2 * k] = (uint32_t)(v >> 32); loc[2 * k + 1] = (uint32_t)v;
+        }
+        if (HAS_NMASK) {
+            const unsigned long long qn = s >> 6;
+            const unsigned shn = (unsigned)(s & 63ull);
+            unsigned long long M[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned long long idx = qn + k;
+                if (idx >= nmask_words) idx = nmask_words - 1;
+                M[k] = bswap64(msrc[idx]);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const unsigned long long v = shn ? ((M[k] << shn) | (M[k + 1] >> (64 - shn))) : M[k];
+                if (2 * k < 5) nl[2 * k] = (uint32_t)(v >> 32);
+                if (2 * k + 1 < 5) nl[2 * k + 1] = (uint32_t)v;
+            }
+        }
+    }
+}
+// validity of the 96 window starts (MSB first): i < c and no N in bases [i, i+K); nl[] is smeared in place
+template <bool HAS_NMASK>
+__device__ __forceinline__ void segment_valid(uint32_t (&nl)[5], unsigned c, unsigned K, uint32_t& v0, uint32_t& v1, uint32_t& v2) {
+    if (HAS_NMASK && __any_sync(0xFFFFFFFFu, (nl[0] | nl[1] | nl[2] | nl[3] | nl[4]) != 0u)) {
+        unsigned cover = 1;
+        while (cover * 2 <= K) {                   // X |= X << cover (towards the smaller base index)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], cover);
+            nl[4] |= nl[4] << cover;
+            cover *= 2;
+        }
+        const unsigned rest = K - cover;            // < cover <= 32
+        if (rest) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], rest);
+            nl[4] |= nl[4] << rest;
+        }
+    }
+    // first c bits set (MSB first)
+    const uint32_t c0 = c >= 32 ? 0xFFFFFFFFu : (c ? ~(0xFFFFFFFFu >> c) : 0u);
+    const uint32_t c1 = c >= 64 ? 0xFFFFFFFFu : (c > 32 ? ~(0xFFFFFFFFu >> (c - 32)) : 0u);
+    const uint32_t c2 = c >= 96 ? 0xFFFFFFFFu : (c > 64 ? ~(0xFFFFFFFFu >> (c - 64)) : 0u);
+    v0 = ~nl[0] & c0; v1 = ~nl[1] & c1; v2 = ~nl[2] & c2;
+}
+// K = 60: reverse complement of the segment; the complement of base x sits at base 154 - x of rcl[]
+__device__ __forceinline__ void segment_rc60(const uint32_t (&loc)[SEGW], uint32_t (&rcl)[SEGW]) {
+    uint32_t t160[SEGW + 1];
+#pragma unroll
+    for (int k = 0; k < (int)SEGW; ++k) t160[k] = rev2_32(~loc[SEGW - 1 - k]);
+    t160[SEGW] = 0;
+    constexpr unsigned bs = 2u * (160u - (WMAX + SK_K - 1u));       // 10 bits dropped at the front
+    static_assert(bs < 32, "alignment shift must stay inside one word");
+#pragma unroll
+    for (int k = 0; k < (int)SEGW; ++k) rcl[k] = fsl(t160[k], t160[k + 1], bs);
+}
+
 }  // namespace
 
 // launchers of the two K = 60 kernels (probe_sk.cu, probe_mz.cu); sm_count sizes the persistent grid

@@ -282,65 +282,9 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
 
             uint32_t loc[SEGW];
             uint32_t nl[5];
-#pragma unroll
-            for (int k = 0; k < (int)SEGW; ++k) loc[k] = 0;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) nl[k] = 0;
-            if (c) {
-                const unsigned long long q = s >> 5;
-                const unsigned sh = 2u * (unsigned)(s & 31ull);
-                unsigned long long W[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    unsigned long long idx = q + k;
-                    if (idx >= a.base_words) idx = a.base_words - 1;
-                    W[k] = bswap64(bsrc[idx]);
-                }
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const unsigned long long v = sh ? ((W[k] << sh) | (W[k + 1] >> (64 - sh))) : W[k];
-                    loc[2 * k] = (uint32_t)(v >> 32); loc[2 * k + 1] = (uint32_t)v;
-                }
-                if (HAS_NMASK) {
-                    const unsigned long long qn2 = s >> 6;
-                    const unsigned shn = (unsigned)(s & 63ull);
-                    unsigned long long M[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        unsigned long long idx = qn2 + k;
-                        if (idx >= a.nmask_words) idx = a.nmask_words - 1;
-                        M[k] = bswap64(msrc[idx]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const unsigned long long v = shn ? ((M[k] << shn) | (M[k + 1] >> (64 - shn))) : M[k];
-                        if (2 * k < 5) nl[2 * k] = (uint32_t)(v >> 32);
-                        if (2 * k + 1 < 5) nl[2 * k + 1] = (uint32_t)v;
-                    }
-                }
-            }
+            segment_load<HAS_NMASK>(loc, nl, c, s, bsrc, msrc, a.base_words, a.nmask_words);
             uint32_t v0, v1, v2;
-            {
-                if (HAS_NMASK && __any_sync(FULL, (nl[0] | nl[1] | nl[2] | nl[3] | nl[4]) != 0u)) {
-                    unsigned cover = 1;
-                    while (cover * 2 <= K) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], cover);
-                        nl[4] |= nl[4] << cover;
-                        cover *= 2;
-                    }
-                    const unsigned rest = K - cover;
-                    if (rest) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) nl[k] |= fsl(nl[k], nl[k + 1], rest);
-                        nl[4] |= nl[4] << rest;
-                    }
-                }
-                const uint32_t c0 = c >= 32 ? 0xFFFFFFFFu : (c ? ~(0xFFFFFFFFu >> c) : 0u);
-                const uint32_t c1 = c >= 64 ? 0xFFFFFFFFu : (c > 32 ? ~(0xFFFFFFFFu >> (c - 32)) : 0u);
-                const uint32_t c2 = c >= 96 ? 0xFFFFFFFFu : (c > 64 ? ~(0xFFFFFFFFu >> (c - 64)) : 0u);
-                v0 = ~nl[0] & c0; v1 = ~nl[1] & c1; v2 = ~nl[2] & c2;
-            }
+            segment_valid<HAS_NMASK>(nl, c, K, v0, v1, v2);
             my_valid += __popc(v0) + __popc(v1) + __popc(v2);
             if (__all_sync(FULL, (v0 | v1 | v2) == 0u)) continue;
 
@@ -351,16 +295,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
 
             // reverse complement of the segment: the complement of base x sits at base 154 - x of rcl[]
             uint32_t rcl[SEGW];
-            {
-                uint32_t t160[SEGW + 1];
-#pragma unroll
-                for (int k = 0; k < (int)SEGW; ++k) t160[k] = rev2_32(~loc[SEGW - 1 - k]);
-                t160[SEGW] = 0;
-                constexpr unsigned bs = 2u * (160u - (WMAX + K - 1u));
-                static_assert(bs < 32, "alignment shift must stay inside one word");
-#pragma unroll
-                for (int k = 0; k < (int)SEGW; ++k) rcl[k] = fsl(t160[k], t160[k + 1], bs);
-            }
+            segment_rc60(loc, rcl);
 
             // minimizer state carried from block to block: P = prefix minimum of position block 1 up to index 11
             uint32_t P = 0xFFFFFFFFu;
