@@ -2,13 +2,24 @@
 // mlg_query_push_packed_nruns().  Declared in include/metalign_b200_ingest.h; replaces the input side of
 // `kmc -k60 -fq|-fa` (scripts/select_db.py:46-52 of the reference).  Host code only.
 //
-//   reader thread    gzread() (transparent for plain files) into blocks
-//   scanner thread   cuts blocks into lines, keeps the sequence lines as (offset, length) pairs
+//   plain file       mapped (mmap): the scanner and the packers read the page cache directly, nothing is copied
+//   gzip file        reader thread: gzread() into recycled blocks (single-stream inflate is the bound there)
+//   scanner thread   cuts the text into lines (AVX2 compare + movemask where the CPU has it, memchr otherwise), keeps the
+//                    sequence lines as (offset, length) pairs
 //   mlgi_next()      takes sequence lines until the batch is full, prefix-sums their lengths into read offsets and
-//                    lets `threads` workers pack disjoint ranges of the output stream
+//                    lets `threads` workers pack disjoint ranges of the output stream: 32 bases at a time with AVX2
+//                    (case-folded compare for A/C/G/T, 2-bit codes from bits 1-2 of the ASCII byte, maddubs / madd /
+//                    packus to 8 output bytes), 8 at a time with 64-bit SWAR otherwise, one at a time around any
+//                    other symbol (N runs) and at read boundaries that are not byte-aligned in the output
+// MLGI_PROFILE=1 prints where the consumer and the scanner waited; MLGI_NO_MMAP / MLGI_NO_AVX2 force the other paths.
 #include <zlib.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <fcntl.h>
 #include <unistd.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -22,6 +33,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <chrono>
 #include "../../include/metalign_b200_ingest.h"
 
 #define MLGI_API __attribute__((visibility("default")))
@@ -72,11 +84,39 @@ private:
 // a block of file text with HEAD spare bytes in front of it, so that the unterminated tail of the previous block can
 // be put in front without copying the block (uninitialised storage: no zero-fill pass over every block)
 constexpr size_t HEAD = 1u << 16;
+// blocks are recycled: a fresh 8 MiB allocation per block costs a page fault (and a zero-fill by the kernel) per 4 KiB
+// inside the reader's read(2), which otherwise is the fastest stage
+struct BufPool {
+    std::mutex mu;
+    std::vector<std::unique_ptr<char[]>> free;
+    size_t bytes = 0;                          // size of the pooled blocks
+    std::unique_ptr<char[]> get() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!free.empty()) { auto p = std::move(free.back()); free.pop_back(); return p; }
+        }
+        return std::unique_ptr<char[]>(new char[bytes]);
+    }
+    void put(std::unique_ptr<char[]> p) {
+        std::lock_guard<std::mutex> g(mu);
+        if (free.size() < 16) free.push_back(std::move(p));
+    }
+};
+// a plain file is not read at all: it is mapped, and blocks are views of the mapping (no copy of the text; the page cache
+// is what the scanner and the packers read)
+struct Mapping {
+    void* p = nullptr; size_t n = 0;
+    ~Mapping() { if (p) munmap(p, n); }
+};
 struct TextBuf {
     std::unique_ptr<char[]> mem;
+    std::shared_ptr<BufPool> pool;            // set when mem came from the pool
+    std::shared_ptr<Mapping> map;             // set when the text is a view of a mapped file ...
+    const char* ext = nullptr;                // ... starting here
     size_t off = HEAD, n = 0;                 // text = mem[off, off + n)
-    const char* data() const { return mem.get() + off; }
+    const char* data() const { return ext ? ext : mem.get() + off; }
     size_t size() const { return n; }
+    ~TextBuf() { if (pool && mem) pool->put(std::move(mem)); }
 };
 struct RawBlock { std::shared_ptr<TextBuf> buf; };
 struct Lines {
@@ -93,6 +133,26 @@ struct CodeInit {
     }
 } g_code_init;
 
+bool g_have_avx2 = false;
+struct CpuInit { CpuInit() {
+#if defined(__x86_64__)
+    g_have_avx2 = __builtin_cpu_supports("avx2") && !getenv("MLGI_NO_AVX2");
+#endif
+} } g_cpu_init;
+#if defined(__x86_64__)
+// calls f(e) for the position e of every '\n' in base[0, n & ~31), in order; returns n & ~31
+template <typename F>
+__attribute__((target("avx2"))) size_t scan_newlines_avx2(const char* base, size_t n, F f) {
+    const __m256i nl = _mm256_set1_epi8('\n');
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(base + i)), nl));
+        while (m) { f(i + (size_t)__builtin_ctz(m)); m &= m - 1; }
+    }
+    return i;
+}
+#endif
+
 }  // namespace
 
 struct mlgi_reader {
@@ -101,6 +161,7 @@ struct mlgi_reader {
     int type = MLGI_FASTQ;
     int threads = 1;
     size_t block_bytes = 8u << 20;
+    std::shared_ptr<BufPool> pool = std::make_shared<BufPool>();
     BoundedQueue<RawBlock> q_raw{4};
     BoundedQueue<Lines> q_lines{4};
     std::thread t_read, t_scan;
@@ -111,12 +172,15 @@ struct mlgi_reader {
     size_t cur_i = 0;
     bool eof = false;
     uint64_t tot_reads = 0, tot_bases = 0, tot_text = 0;
+    double t_wait_lines = 0, t_gather = 0, t_pack = 0, t_scan_busy = 0, t_scan_wait = 0, t_read_busy = 0;   // MLGI_PROFILE=1
 
     void read_loop() {
         for (;;) {
             RawBlock b;
             b.buf = std::make_shared<TextBuf>();
-            b.buf->mem.reset(new char[HEAD + block_bytes]);
+            pool->bytes = HEAD + block_bytes;
+            b.buf->mem = pool->get();
+            b.buf->pool = pool;
             char* dst = b.buf->mem.get() + HEAD;
             size_t got = 0;
             while (got < block_bytes) {
@@ -140,34 +204,66 @@ struct mlgi_reader {
         }
     }
 
+    uint64_t line_no = 0;                // lines completed so far (FASTQ: record = 4 lines); scanner thread only
+    std::shared_ptr<Mapping> map;        // plain files
+    // cuts text into lines, appends the sequence lines to out; returns the bytes consumed (an incomplete last line is not)
+    size_t emit_lines(const std::shared_ptr<TextBuf>& text, bool final_block, Lines& out) {
+        const char* base = text->data();
+        const size_t n = text->size();
+        size_t p = 0;                                     // start of the current line
+        out.start.reserve(n / 128); out.len.reserve(n / 128);
+        auto line_ends_at = [&](size_t e) {               // the line [p, e) is complete (e = its '\n', or the end of the file)
+            size_t le = e;
+            if (le > p && base[le - 1] == '\r') --le;
+            bool is_seq;
+            if (type == MLGI_FASTQ) is_seq = (line_no & 3u) == 1u;
+            else is_seq = le > p && base[p] != '>' && base[p] != ';';
+            if (is_seq) { out.start.push_back((uint32_t)p); out.len.push_back((uint32_t)(le - p)); }
+            ++line_no;
+        };
+        size_t q = 0;                                     // bytes [0, q) have been searched for '\n'
+#if defined(__x86_64__)
+        if (g_have_avx2) q = scan_newlines_avx2(base, n, [&](size_t e) { line_ends_at(e); p = e + 1; });
+#endif
+        while (q < n) {
+            const char* nl = (const char*)memchr(base + q, '\n', n - q);
+            if (!nl) break;
+            const size_t e = (size_t)(nl - base);
+            line_ends_at(e);
+            p = e + 1; q = e + 1;
+        }
+        if (p < n && final_block) { line_ends_at(n); p = n; }   // the file's last line has no '\n'
+        return p;                                         // bytes consumed; an incomplete line is carried into the next block
+    }
+
+    // plain file: walk the mapping in blocks; a block's unterminated last line simply starts the next view
+    void scan_loop_mapped() {
+        const char* base = (const char*)map->p;
+        const size_t n = map->n;
+        size_t pos = 0, span = block_bytes;
+        while (pos < n) {
+            const size_t end = std::min(n, pos + span);
+            if (end - pos >= 0xFFFFFFF0ull) { std::lock_guard<std::mutex> g(err_mu); io_error = "a single line exceeds 4 GiB"; break; }
+            auto text = std::make_shared<TextBuf>();
+            text->map = map; text->ext = base + pos; text->n = end - pos;
+            Lines out;
+            out.text = text;
+            const size_t used = emit_lines(text, end == n, out);
+            if (used == 0 && end < n) { span += block_bytes; continue; }      // one line longer than the view: widen it
+            pos += used; span = block_bytes;
+            if (!out.start.empty() && !q_lines.push(std::move(out))) return;
+        }
+        q_lines.finish();
+    }
+
     void scan_loop() {
         std::string carry;               // the unterminated tail of the previous block
-        uint64_t line_no = 0;            // lines completed so far (FASTQ: record = 4 lines)
         RawBlock b;
-        auto emit_lines = [&](std::shared_ptr<TextBuf>& text, bool final_block, Lines& out) {
-            const char* base = text->data();
-            const size_t n = text->size();
-            size_t p = 0;
-            while (p < n) {
-                const char* nl = (const char*)memchr(base + p, '\n', n - p);
-                size_t e;
-                if (nl) e = (size_t)(nl - base);
-                else if (final_block) e = n;
-                else break;                                   // incomplete line: carried into the next block
-                size_t le = e;
-                if (le > p && base[le - 1] == '\r') --le;
-                bool is_seq;
-                if (type == MLGI_FASTQ) is_seq = (line_no & 3u) == 1u;
-                else is_seq = le > p && base[p] != '>' && base[p] != ';';
-                if (is_seq) { out.start.push_back((uint32_t)p); out.len.push_back((uint32_t)(le - p)); }
-                ++line_no;
-                p = nl ? e + 1 : n;
-            }
-            return p;                                         // bytes consumed
-        };
         bool more = true;
         while (more) {
+            const auto ts0 = std::chrono::steady_clock::now();
             more = q_raw.pop(b);
+            t_scan_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - ts0).count();
             std::shared_ptr<TextBuf> text;
             if (more && carry.size() <= HEAD) {                // the usual case: the carried tail fits in front of the block
                 text = b.buf;
@@ -202,6 +298,69 @@ struct PackJob {
     std::vector<uint32_t> runs;      // (start, length) pairs found in this range
 };
 
+// ---- packing: ASCII -> 2 bits per base, first base in the top bits of each byte ---------------------------------------
+// code of a base from its ASCII byte, either case: (c >> 1) & 3 gives A=0 C=1 G=3 T=2; x ^ (x >> 1) swaps the last two
+inline uint32_t codes4(uint32_t w) {
+    uint32_t x = (w >> 1) & 0x03030303u;
+    return x ^ ((x >> 1) & 0x01010101u);
+}
+// four codes (one per byte, first base in the low byte) -> one packed byte: the multiplier lines the 2-bit codes up in
+// bits 24..31 of the product
+inline uint8_t pack4(uint32_t codes) { return (uint8_t)((codes * 0x40100401u) >> 24); }
+// 0x80 in every byte of x that is NOT one of a/c/g/t (x already has bit 5 set in every byte)
+inline uint64_t not_acgt8(uint64_t x) {
+    const uint64_t L7 = 0x7F7F7F7F7F7F7F7Full;
+    auto nz = [&](uint64_t z) { return (((z & L7) + L7) | z); };          // bit 7 of every non-zero byte
+    return nz(x ^ 0x6161616161616161ull) & nz(x ^ 0x6363636363636363ull) & nz(x ^ 0x6767676767676767ull) &
+           nz(x ^ 0x7474747474747474ull) & 0x8080808080808080ull;
+}
+// n bases (n % 4 == 0), all of them A/C/G/T in either case, to n / 4 output bytes; returns false (nothing written that
+// matters) at the first 8-byte group that holds another symbol
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) size_t pack_clean_avx2(const unsigned char* s, size_t n, uint8_t* out) {
+    const __m256i lo5 = _mm256_set1_epi8((char)0xDF);
+    const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
+    const __m256i three = _mm256_set1_epi8(3), one = _mm256_set1_epi8(1);
+    const __m256i m41 = _mm256_set1_epi16(0x0104);          // bytes (4, 1): first base of a pair times 4 plus the second
+    const __m256i m161 = _mm256_set1_epi32(0x00010010);     // words (16, 1)
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i v = _mm256_loadu_si256((const __m256i*)(s + i));
+        const __m256i u = _mm256_and_si256(v, lo5);
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
+        if (_mm256_movemask_epi8(ok) != -1) break;
+        __m256i x = _mm256_and_si256(_mm256_srli_epi16(v, 1), three);
+        x = _mm256_xor_si256(x, _mm256_and_si256(_mm256_srli_epi16(x, 1), one));
+        const __m256i p2 = _mm256_maddubs_epi16(x, m41);      // 16-bit: c0 * 4 + c1
+        const __m256i p4 = _mm256_madd_epi16(p2, m161);       // 32-bit: (c0 * 4 + c1) * 16 + (c2 * 4 + c3)
+        const __m256i w16 = _mm256_packus_epi32(p4, p4);      // per 128-bit lane: 4 values as 16-bit, twice
+        const __m256i w8 = _mm256_packus_epi16(w16, w16);     // per lane: 4 bytes, four times
+        const uint32_t a = (uint32_t)_mm256_extract_epi32(w8, 0), b = (uint32_t)_mm256_extract_epi32(w8, 4);
+        memcpy(out + i / 4, &a, 4);
+        memcpy(out + i / 4 + 4, &b, 4);
+    }
+    return i;
+}
+#endif
+size_t pack_clean_swar(const unsigned char* s, size_t n, uint8_t* out) {
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t v;
+        memcpy(&v, s + i, 8);
+        if (not_acgt8(v | 0x2020202020202020ull)) break;
+        out[i / 4] = pack4(codes4((uint32_t)v));
+        out[i / 4 + 1] = pack4(codes4((uint32_t)(v >> 32)));
+    }
+    return i;
+}
+inline size_t pack_clean(const unsigned char* s, size_t n, uint8_t* out) {
+#if defined(__x86_64__)
+    if (g_have_avx2) { const size_t d = pack_clean_avx2(s, n, out); return d + pack_clean_swar(s + d, n - d, out + d / 4); }
+#endif
+    return pack_clean_swar(s, n, out);
+}
+
 void pack_range(PackJob& j) {
     if (j.a >= j.b) return;
     uint64_t pos = j.off[j.a];
@@ -210,22 +369,36 @@ void pack_range(PackJob& j) {
     unsigned acc = 0;
     bool first_partial = fill != 0;
     uint64_t run_start = 0; uint32_t run_len = 0;
+    auto one = [&](unsigned char ch) {         // the general path: one base, N bookkeeping, byte assembly
+        unsigned c = g_code[ch];
+        if (c > 3u) {
+            if (run_len && run_start + run_len == pos) ++run_len;
+            else { if (run_len) { j.runs.push_back((uint32_t)run_start); j.runs.push_back(run_len); } run_start = pos; run_len = 1; }
+            c = 0;
+        }
+        acc = (acc << 2) | c;
+        ++pos;
+        if (++fill == 4) {
+            if (first_partial) { __atomic_fetch_or(out, (uint8_t)acc, __ATOMIC_RELAXED); first_partial = false; }
+            else *out = (uint8_t)acc;
+            ++out; fill = 0; acc = 0;
+        }
+    };
     for (size_t i = j.a; i < j.b; ++i) {
         const unsigned char* s = (const unsigned char*)j.ptr[i];
         const uint32_t L = j.len[i];
-        for (uint32_t k = 0; k < L; ++k) {
-            unsigned c = g_code[s[k]];
-            if (c > 3u) {
-                if (run_len && run_start + run_len == pos) ++run_len;
-                else { if (run_len) { j.runs.push_back((uint32_t)run_start); j.runs.push_back(run_len); } run_start = pos; run_len = 1; }
-                c = 0;
-            }
-            acc = (acc << 2) | c;
-            ++pos;
-            if (++fill == 4) {
-                if (first_partial) { __atomic_fetch_or(out, (uint8_t)acc, __ATOMIC_RELAXED); first_partial = false; }
-                else *out = (uint8_t)acc;
-                ++out; fill = 0; acc = 0;
+        uint32_t k = 0;
+        while (k < L) {
+            // whole output bytes of clean bases go through the vector / SWAR path; everything else one base at a time
+            if (fill == 0 && L - k >= 8) {
+                const size_t d = pack_clean(s + k, (size_t)((L - k) & ~3u), out);
+                out += d / 4; pos += d; k += (uint32_t)d;
+                if (k >= L) break;
+                // an unclean group (or the read's tail) follows: take up to 8 bases the slow way, then try again
+                const uint32_t lim = std::min<uint32_t>(L, k + 8);
+                while (k < lim) one(s[k++]);
+            } else {
+                one(s[k++]);
             }
         }
     }
@@ -256,14 +429,31 @@ MLGI_API int mlgi_open(const char* path, int input_type, int threads, mlgi_reade
         gzbuffer(fh, 1u << 20);
         fd = -1;
     }
+#if defined(__x86_64__)
+    g_have_avx2 = __builtin_cpu_supports("avx2") && !getenv("MLGI_NO_AVX2");     // (the switch is for tests)
+#endif
     mlgi_reader* r = new mlgi_reader();
     r->fh = fh; r->fd = fd; r->type = input_type;
     int hw = (int)std::thread::hardware_concurrency();
     if (hw < 1) hw = 1;
     r->threads = threads > 0 ? threads : hw;
     if (const char* s = getenv("MLGI_BLOCK_BYTES")) { long v = atol(s); if (v >= 16) r->block_bytes = (size_t)v; }
-    r->t_read = std::thread([r] { r->read_loop(); });
-    r->t_scan = std::thread([r] { r->scan_loop(); });
+    if (fd >= 0 && !getenv("MLGI_NO_MMAP")) {
+        struct stat sb;
+        if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p != MAP_FAILED) {
+                madvise(p, (size_t)sb.st_size, MADV_SEQUENTIAL);
+                r->map = std::make_shared<Mapping>();
+                r->map->p = p; r->map->n = (size_t)sb.st_size;
+            }
+        }
+    }
+    if (r->map) r->t_scan = std::thread([r] { r->scan_loop_mapped(); });
+    else {
+        r->t_read = std::thread([r] { r->read_loop(); });
+        r->t_scan = std::thread([r] { r->scan_loop(); });
+    }
     *out = r;
     return 0;
 }
@@ -282,7 +472,10 @@ MLGI_API int mlgi_next(mlgi_reader* r, uint8_t* bases, uint64_t cap_bases_bytes,
         if (r->cur_i >= r->cur.start.size()) {
             if (r->eof) break;
             Lines nx;
-            if (!r->q_lines.pop(nx)) { r->eof = true; break; }
+            const auto tw0 = std::chrono::steady_clock::now();
+            const bool got_lines = r->q_lines.pop(nx);
+            r->t_wait_lines += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
+            if (!got_lines) { r->eof = true; break; }
             r->tot_text += nx.text->size();
             r->cur = std::move(nx); r->cur_i = 0;
         }
@@ -326,6 +519,7 @@ MLGI_API int mlgi_next(mlgi_reader* r, uint8_t* bases, uint64_t cap_bases_bytes,
     }
     const uint64_t used = (nb + 3) / 4, padded = (used + 15) / 16 * 16 + 16;
     memset(bases + used, 0, (size_t)std::min<uint64_t>(padded, cap_bases_bytes) - used);
+    const auto tp0 = std::chrono::steady_clock::now();
     if (T == 1) pack_range(jobs[0]);
     else {
         std::vector<std::thread> th;
@@ -333,6 +527,7 @@ MLGI_API int mlgi_next(mlgi_reader* r, uint8_t* bases, uint64_t cap_bases_bytes,
         pack_range(jobs[0]);
         for (auto& x : th) x.join();
     }
+    r->t_pack += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
     // N runs of the workers, in stream order; runs that touch across a worker boundary are merged
     uint64_t nr = 0;
     for (int t = 0; t < T; ++t) {
@@ -359,6 +554,9 @@ MLGI_API int mlgi_stats(mlgi_reader* r, uint64_t* reads, uint64_t* bases, uint64
 
 MLGI_API void mlgi_close(mlgi_reader* r) {
     if (!r) return;
+    if (getenv("MLGI_PROFILE"))
+        fprintf(stderr, "mlgi: consumer waited %.3f s for lines, packed %.3f s; scanner waited %.3f s for blocks\n", r->t_wait_lines, r->t_pack,
+                r->t_scan_wait);
     r->q_lines.abandon();
     r->q_raw.abandon();
     if (r->t_scan.joinable()) r->t_scan.join();

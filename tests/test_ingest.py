@@ -85,10 +85,17 @@ def test_fastq(tmp_path, monkeypatch, ext, eol, trailing):
     _write(p, text)
     want = [_norm(r) for r in reads]
     assert [_norm(r) for r in _numpy_reads(p, "fastq")] == want
-    for block, rpb, thr in ((1 << 23, 4_000_000, 0), (97, 50, 3), (4096, 7, 1), (1000, 1000, 16)):
+    # plain files are mapped (views of the page cache), gzip ones are inflated into recycled blocks; MLGI_NO_MMAP /
+    # MLGI_NO_AVX2 force the read(2) path and the SWAR packer / memchr scanner
+    for block, rpb, thr, env in ((1 << 23, 4_000_000, 0, {}), (97, 50, 3, {}), (4096, 7, 1, {"MLGI_NO_MMAP": "1"}),
+                                 (1000, 1000, 16, {"MLGI_NO_AVX2": "1"}), (97, 50, 3, {"MLGI_NO_MMAP": "1", "MLGI_NO_AVX2": "1"})):
         monkeypatch.setenv("MLGI_BLOCK_BYTES", str(block))
+        for k in ("MLGI_NO_MMAP", "MLGI_NO_AVX2"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         got, nb = _native_reads(p, "fastq", reads_per_batch=rpb, threads=thr, bases_per_batch=max(2000, rpb * 200))
-        assert got == want, (block, rpb, thr)
+        assert got == want, (block, rpb, thr, env)
         assert nb >= len(reads) // rpb
 
 
