@@ -443,7 +443,8 @@ MLGI_API int mlgi_open(const char* path, int input_type, int threads, mlgi_reade
         if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
             void* p = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
             if (p != MAP_FAILED) {
-                madvise(p, (size_t)sb.st_size, MADV_SEQUENTIAL);
+                // (no MADV_SEQUENTIAL: it lets the kernel drop the pages right behind the scan, and a file that is read
+                // again -- paired runs, several k ranges -- would come from the disk instead of the page cache)
                 r->map = std::make_shared<Mapping>();
                 r->map->p = p; r->map->n = (size_t)sb.st_size;
             }
@@ -498,6 +499,7 @@ MLGI_API int mlgi_next(mlgi_reader* r, uint8_t* bases, uint64_t cap_bases_bytes,
     }
     const size_t n = ptr.size();
     if (n == 0) return 0;
+    const auto tg0 = std::chrono::steady_clock::now();
     off[0] = 0;
     for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + len[i];
     // worker ranges: equal shares of the bases
@@ -520,6 +522,7 @@ MLGI_API int mlgi_next(mlgi_reader* r, uint8_t* bases, uint64_t cap_bases_bytes,
     const uint64_t used = (nb + 3) / 4, padded = (used + 15) / 16 * 16 + 16;
     memset(bases + used, 0, (size_t)std::min<uint64_t>(padded, cap_bases_bytes) - used);
     const auto tp0 = std::chrono::steady_clock::now();
+    r->t_gather += std::chrono::duration<double>(tp0 - tg0).count();
     if (T == 1) pack_range(jobs[0]);
     else {
         std::vector<std::thread> th;
@@ -555,8 +558,8 @@ MLGI_API int mlgi_stats(mlgi_reader* r, uint64_t* reads, uint64_t* bases, uint64
 MLGI_API void mlgi_close(mlgi_reader* r) {
     if (!r) return;
     if (getenv("MLGI_PROFILE"))
-        fprintf(stderr, "mlgi: consumer waited %.3f s for lines, packed %.3f s; scanner waited %.3f s for blocks\n", r->t_wait_lines, r->t_pack,
-                r->t_scan_wait);
+        fprintf(stderr, "mlgi: consumer waited %.3f s for lines, prepared %.3f s, packed %.3f s; scanner waited %.3f s for blocks\n",
+                r->t_wait_lines, r->t_gather, r->t_pack, r->t_scan_wait);
     r->q_lines.abandon();
     r->q_raw.abandon();
     if (r->t_scan.joinable()) r->t_scan.join();

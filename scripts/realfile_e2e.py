@@ -34,7 +34,7 @@ t0 = time.perf_counter()
 db = Database.from_device_keys(ctx, d_k.data_ptr(), G, 1000, 60, KS)
 t_db = time.perf_counter() - t0
 del d_k
-for threads in (int(os.environ.get("RF_THREADS", "0")),) * 2:
+for threads in (int(os.environ.get("RF_THREADS", "0")),) * int(os.environ.get("RF_REPEATS", "2")):
     t0 = time.perf_counter()
     rd = ingest.PackedBatches(path, "fastq", reads_per_batch=2_000_000, threads=threads, alloc=pinned_array)
     t_open = time.perf_counter() - t0
