@@ -4,8 +4,10 @@
 //
 //   plain file       mapped (mmap): the scanner and the packers read the page cache directly, nothing is copied
 //   gzip file        reader thread: gzread() into recycled blocks (single-stream inflate is the bound there)
-//   scanner thread   cuts the text into lines (AVX2 compare + movemask where the CPU has it, memchr otherwise), keeps the
-//                    sequence lines as (offset, length) pairs
+//   scanner          cuts the text into lines (AVX2 compare + movemask where the CPU has it, memchr otherwise), keeps the
+//                    sequence lines as (offset, length) pairs; for a mapped file `threads` threads do it on views of
+//                    `threads` blocks in two passes (count the newlines of every part, prefix sum = the line numbers a
+//                    part starts with, then cut), one thread for the gzip stream
 //   mlgi_next()      takes sequence lines until the batch is full, prefix-sums their lengths into read offsets and
 //                    lets `threads` workers pack disjoint ranges of the output stream: 32 bases at a time with AVX2
 //                    (case-folded compare for A/C/G/T, 2-bit codes from bits 1-2 of the ASCII byte, maddubs / madd /
@@ -151,7 +153,23 @@ __attribute__((target("avx2"))) size_t scan_newlines_avx2(const char* base, size
     }
     return i;
 }
+__attribute__((target("avx2,popcnt"))) size_t count_newlines_avx2(const char* base, size_t n) {
+    const __m256i nl = _mm256_set1_epi8('\n');
+    size_t i = 0, c = 0;
+    for (; i + 32 <= n; i += 32)
+        c += (size_t)__builtin_popcount((uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(base + i)), nl)));
+    for (; i < n; ++i) c += base[i] == '\n';
+    return c;
+}
 #endif
+size_t count_newlines(const char* base, size_t n) {
+#if defined(__x86_64__)
+    if (g_have_avx2) return count_newlines_avx2(base, n);
+#endif
+    size_t c = 0;
+    for (const char* q = base; (q = (const char*)memchr(q, '\n', (size_t)(base + n - q))) != nullptr; ++q) ++c;
+    return c;
+}
 
 }  // namespace
 
@@ -236,22 +254,89 @@ struct mlgi_reader {
         return p;                                         // bytes consumed; an incomplete line is carried into the next block
     }
 
-    // plain file: walk the mapping in blocks; a block's unterminated last line simply starts the next view
+    // One part of a parallel scan of the view vbase[0, vend): the lines that START in [b0, b1).  nl_before = lines
+    // completed before b0 (= '\n' seen so far), so every part knows its lines' numbers without waiting for the others.
+    // A line may end beyond b1; one that does not end before vend is complete only in the file's last view, otherwise
+    // *open_line is set to its start.  Sequence lines go to out (offsets relative to vbase).
+    void scan_part(const char* vbase, size_t b0, size_t b1, size_t vend, bool final_view, bool starts_line, uint64_t nl_before,
+                   Lines& out, size_t* open_line) const {
+        size_t p = b0;
+        uint64_t idx = nl_before;
+        if (!starts_line) {                                   // b0 is inside a line that belongs to an earlier part
+            const char* nl = (const char*)memchr(vbase + b0, '\n', b1 - b0);
+            if (!nl) return;                                  // no line starts in this part
+            p = (size_t)(nl - vbase) + 1; ++idx;
+        }
+        out.start.reserve((b1 - b0) / 128 + 4); out.len.reserve((b1 - b0) / 128 + 4);
+        auto line = [&](size_t e) {                           // the line [p, e) is complete
+            size_t le = e;
+            if (le > p && vbase[le - 1] == '\r') --le;
+            bool is_seq;
+            if (type == MLGI_FASTQ) is_seq = (idx & 3u) == 1u;
+            else is_seq = le > p && vbase[p] != '>' && vbase[p] != ';';
+            if (is_seq) { out.start.push_back((uint32_t)p); out.len.push_back((uint32_t)(le - p)); }
+            ++idx;
+            p = e + 1;
+        };
+        size_t q = p;                                         // bytes [p, q) hold no '\n'
+#if defined(__x86_64__)
+        if (g_have_avx2 && b1 > p) {
+            const size_t from = p;
+            q = from + scan_newlines_avx2(vbase + from, b1 - from, [&](size_t e) { line(from + e); });
+        }
+#endif
+        while (p < b1) {                                      // (also finishes the last line that starts before b1)
+            if (q < p) q = p;
+            const char* nl = (const char*)memchr(vbase + q, '\n', vend - q);
+            if (!nl) {
+                if (final_view && p < vend) line(vend);
+                else if (p < vend) *open_line = p;
+                return;
+            }
+            q = (size_t)(nl - vbase) + 1;
+            line(q - 1);
+        }
+    }
+
+    // plain file: walk the mapping in views of `threads` blocks, scanned by that many threads (pass 1 counts the '\n' of
+    // every part, pass 2 cuts the lines); a view's unterminated last line simply starts the next view
     void scan_loop_mapped() {
         const char* base = (const char*)map->p;
         const size_t n = map->n;
-        size_t pos = 0, span = block_bytes;
+        const size_t P = (size_t)std::max(1, std::min(threads, 16));
+        size_t pos = 0, span = block_bytes * P;
         while (pos < n) {
             const size_t end = std::min(n, pos + span);
-            if (end - pos >= 0xFFFFFFF0ull) { std::lock_guard<std::mutex> g(err_mu); io_error = "a single line exceeds 4 GiB"; break; }
+            const size_t vn = end - pos;
+            if (vn >= 0xFFFFFFF0ull) { std::lock_guard<std::mutex> g(err_mu); io_error = "a single line exceeds 4 GiB"; break; }
             auto text = std::make_shared<TextBuf>();
-            text->map = map; text->ext = base + pos; text->n = end - pos;
-            Lines out;
-            out.text = text;
-            const size_t used = emit_lines(text, end == n, out);
-            if (used == 0 && end < n) { span += block_bytes; continue; }      // one line longer than the view: widen it
-            pos += used; span = block_bytes;
-            if (!out.start.empty() && !q_lines.push(std::move(out))) return;
+            text->map = map; text->ext = base + pos; text->n = vn;
+            const char* vb = base + pos;
+            const size_t parts = (P > 1 && vn >= 64 * P) ? P : 1;
+            std::vector<size_t> bnd(parts + 1), cnt(parts, 0), open(parts, (size_t)-1);
+            for (size_t i = 0; i <= parts; ++i) bnd[i] = vn * i / parts;
+            std::vector<Lines> outs(parts);
+            auto run = [&](auto&& fn) {
+                std::vector<std::thread> th;
+                for (size_t i = 1; i < parts; ++i) th.emplace_back([&fn, i] { fn(i); });
+                fn(0);
+                for (auto& x : th) x.join();
+            };
+            if (parts > 1) run([&](size_t i) { cnt[i] = count_newlines(vb + bnd[i], bnd[i + 1] - bnd[i]); });
+            std::vector<uint64_t> before(parts + 1, line_no);
+            for (size_t i = 0; i < parts; ++i) before[i + 1] = before[i] + cnt[i];
+            run([&](size_t i) {
+                outs[i].text = text;
+                scan_part(vb, bnd[i], bnd[i + 1], vn, end == n, i == 0 || vb[bnd[i] - 1] == '\n', before[i], outs[i], &open[i]);
+            });
+            size_t used = vn;                                 // everything, unless some line is still open at the end of the view
+            for (size_t i = 0; i < parts; ++i) if (open[i] != (size_t)-1) { used = open[i]; break; }
+            if (used == 0 && end < n) { span += block_bytes * P; continue; }      // one line longer than the view: widen it
+            // lines completed in this view: its '\n' up to `used`, plus the file's unterminated last line
+            line_no += (parts > 1 ? before[parts] - line_no : (uint64_t)count_newlines(vb, vn)) + ((end == n && vn && vb[vn - 1] != '\n') ? 1u : 0u);
+            pos += used; span = block_bytes * P;
+            for (size_t i = 0; i < parts; ++i)
+                if (!outs[i].start.empty() && !q_lines.push(std::move(outs[i]))) return;
         }
         q_lines.finish();
     }
