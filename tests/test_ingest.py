@@ -20,6 +20,54 @@ def _write(path, text: str):
             f.write(text)
 
 
+def _write_bgzf(path, data: bytes, rng, max_block=60000):
+    """BGZF as bgzip / htslib write it: gzip members of at most 64 KiB with a 'BC' extra field holding the member size - 1,
+    and the empty end-of-file member"""
+    import struct
+    import zlib
+
+    def member(chunk):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(body) + 8 - 1
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize) + body
+                + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+    with open(path, "wb") as f:
+        i = 0
+        while i < len(data):
+            n = rng.randint(1, max_block)
+            f.write(member(data[i:i + n]))
+            i += n
+        f.write(member(b""))
+
+
+def test_bgzf_members_inflate_in_parallel(tmp_path, monkeypatch):
+    """a bgzip-style file goes through the parallel member path (and, with MLGI_NO_BGZF, through plain gzread): same reads"""
+    rng = random.Random(77)
+    reads = _random_reads(rng, 3000)
+    text = "".join("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(reads))
+    p = tmp_path / "reads.fastq.gz"
+    _write_bgzf(p, text.encode(), rng, max_block=5000)
+    want = [_norm(r) for r in reads]
+    assert gzip.open(p, "rb").read() == text.encode()            # a valid multi-member gzip file for everybody else
+    for env, block, thr in (({}, 1 << 23, 0), ({}, 3000, 5), ({"MLGI_NO_BGZF": "1"}, 4096, 3)):
+        monkeypatch.delenv("MLGI_NO_BGZF", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        monkeypatch.setenv("MLGI_BLOCK_BYTES", str(block))
+        got, _ = _native_reads(p, "fastq", reads_per_batch=700, threads=thr, bases_per_batch=200000)
+        assert got == want, (env, block, thr)
+    # a damaged member is an error, not silence
+    raw = bytearray(p.read_bytes())
+    raw[len(raw) // 2] ^= 0xFF
+    bad = tmp_path / "bad.fastq.gz"
+    bad.write_bytes(bytes(raw))
+    monkeypatch.delenv("MLGI_NO_BGZF", raising=False)
+    with pytest.raises(IOError):
+        _native_reads(bad, "fastq", reads_per_batch=700, threads=4, bases_per_batch=200000)
+
+
 def _native_reads(path, kind, **kw):
     rd = ingest.PackedBatches(str(path), kind, **kw)
     out = []
