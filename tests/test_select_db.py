@@ -5,6 +5,7 @@ import argparse
 import filecmp
 import gzip
 import os
+import random
 import shutil
 
 import numpy as np
@@ -138,3 +139,30 @@ def test_make_db_from_fasta_dump(tmp_path):
     want = np.concatenate([codec.sketches_to_keys(sk, K), np.full((1, 2), codec.EMPTY, dtype=np.uint64)])
     for chunk in (7, 64, 1000, 1 << 20):
         assert np.array_equal(dbformat.keys_from_dump_fasta(str(tmp_path / "crlf.fa"), K, chunk_bytes=chunk), want)
+
+
+def test_make_db_from_h5(tmp_path):
+    """scripts/make_db_from_h5.py against a tiny file in CMash's HDF5 layout (needs h5py: skipped where it is absent, as in
+    this repo's build image)"""
+    h5py = pytest.importorskip("h5py")
+    import importlib.util
+    from metalign_b200 import codec, dbformat
+    spec = importlib.util.spec_from_file_location("make_db_from_h5", os.path.join(ROOT, "scripts", "make_db_from_h5.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = random.Random(4)
+    K, n = 60, 5
+    sk = {"b_genome.fna.gz": ["".join(rng.choice("ACGT") for _ in range(K)) for _ in range(n)],
+          "a_genome.fna.gz": ["".join(rng.choice("ACGT") for _ in range(K)) for _ in range(3)] + ["", ""]}
+    p = str(tmp_path / "train.h5")
+    with h5py.File(p, "w") as f:
+        grp = f.create_group("CountEstimators")
+        for name, kmers in sk.items():
+            g = grp.create_group(name)
+            g.attrs["ksize"] = K
+            g.create_dataset("kmers", data=np.array([k.encode() for k in kmers], dtype="S%d" % K))
+    out = str(tmp_path / "db.mlgdb")
+    mod.main([p, out])
+    assert dbformat.read_names(out) == sorted(sk)
+    want = codec.sketches_to_keys([sk[k] for k in sorted(sk)], K)
+    assert np.array_equal(dbformat.read_keys(out).reshape(-1), np.asarray(want).reshape(-1))
