@@ -130,6 +130,40 @@ def test_read_fasta(tmp_path):
     assert read_fasta(str(p) + ".gz") == b"ACGTacgtNTTTTNGG"
 
 
+def test_build_database_host_logic(tmp_path, monkeypatch):
+    """build_database's host side (sorted-basename order, batching, empty slots, the .mlgdb it writes) with the device call
+    replaced by the oracle -- the GPU test below runs the real thing"""
+    from metalign_b200 import codec, dbformat, sketch
+    rng = random.Random(8)
+    paths = []
+    for i, L in enumerate((5000, 40, 9000, 700, 3000)):            # 40 bases: a genome without a single 60-mer
+        p = tmp_path / ("g%d_%s.fna%s" % (9 - i, "x" * i, ".gz" if i % 2 else ""))
+        seq = "".join(rng.choice("ACGT") for _ in range(L))
+        with (gzip.open if i % 2 else open)(str(p), "wb") as f:
+            f.write((">a\n%s\n>b\n%s\n" % (seq[:L // 2], seq[L // 2:])).encode())
+        paths.append(str(p))
+    calls = []
+
+    def fake(ctx, genomes, n, K, prime=0):
+        calls.append(len(genomes))
+        m, c, k = so.sketch_genomes(genomes, n, K)
+        return m, c, k, {"n_windows": 0, "n_candidates": 0, "ms_kernels": 0.0, "passes": 1}
+
+    monkeypatch.setattr(sketch, "sketch_genomes", fake)
+    out = str(tmp_path / "db.mlgdb")
+    sketch.build_database(None, paths, out, n=300, K=60, batch_bytes=6000)
+    order = sorted(paths, key=os.path.basename)
+    assert len(calls) >= 2 and sum(calls) == len(paths)
+    assert dbformat.read_names(out) == [os.path.basename(p) for p in order]
+    h = dbformat.read_header(out)
+    assert (h["G"], h["n"], h["K"], list(h["ks"])) == (5, 300, 60, [30, 40, 50, 60])
+    _, _, ok = so.sketch_genomes([sketch.read_fasta(p) for p in order], 300, 60)
+    keys = dbformat.read_keys(out).reshape(-1, 2)
+    assert np.array_equal(keys, codec.ascii_slots_to_keys(ok.reshape(-1, 60), 60))
+    empty = (keys[:, 0] == np.uint64(0xFFFFFFFFFFFFFFFF)).reshape(5, 300).sum(axis=1)
+    assert empty.max() == 300 and empty.min() == 0                # the 40-base genome has no k-mer at all
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _check(ctx, genomes, n, K, prime=0):
     from metalign_b200.sketch import sketch_genomes
