@@ -29,12 +29,12 @@ struct MzShared {
     SkStage stg;
     uint32_t wm[MZ_LIST][RT];                 // [r][thread]: value of the r-th run START of the current block (r >= 1)
     uint32_t seq[SEGW + 1][RT];               // [word][thread]: the lane's current segment (160 bases, top-aligned words)
-    uint32_t qa[WARPS][MZ_QCAP];              // item: source lane | index of the block's first window in the read << 5
+    uint32_t qa[WARPS][MZ_QCAP];              // item: stream position (in bases) of the block's first window, low / high word
+    uint32_t qc[WARPS][MZ_QCAP];
     uint32_t qb[WARPS][MZ_QCAP];              // item: windows of the block to compare exactly (bit tt = window tt) | base of the
                                               //       minimizer relative to the block's first window << 16
     uint32_t qoff[WARPS][32];                 // drain: windows before each item of the batch
     uint32_t qn[WARPS];                       // items waiting
-    unsigned long long r0s[WARPS][32];        // stream position (in bases) of each lane's read of the current tile
 };
 constexpr uint32_t MZ_ROW = RT * 4;           // byte stride between rows of wm[] / seq[]
 
@@ -127,7 +127,7 @@ __device__ __forceinline__ void mz_window_end(const MzWin& w, const DbView& db, 
     }
 }
 // exact compare of every window of every waiting item of one warp, one WINDOW per lane (items have 1..16 windows)
-__device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const uint32_t* qb, uint32_t* qoff, const unsigned long long* r0s,
+__device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const uint32_t* qc, const uint32_t* qb, uint32_t* qoff,
                                       const unsigned long long* bsrc, unsigned long long base_words, const DbView& db, const CountSink& cs) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
@@ -146,9 +146,9 @@ __device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const ui
             uint32_t j = 0;                              // the last item of the batch that starts at or before window w
 #pragma unroll
             for (uint32_t step = 16; step; step >>= 1) if (qoff[j + step] <= w) j += step;
-            const uint32_t ia = qa[base + j], kb = qb[base + j];
+            const uint32_t kb = qb[base + j];
             const uint32_t tt = __fns(kb & 0xFFFFu, 0u, (int)(w - qoff[j]) + 1);
-            const unsigned long long pb = r0s[ia & 31u] + (ia >> 5);
+            const unsigned long long pb = ((unsigned long long)qc[base + j] << 32) | qa[base + j];
             MzWin win;
             mz_window_begin(win, true, pb + tt, pb + ((kb >> 16) & 63u), (kb >> 31) != 0u, bsrc, base_words, db);
             mz_window_end(win, db, cs);
@@ -234,13 +234,15 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         hb = rev2_32(~fsl(w1, w2, sh));
     };
     auto drain = [&]() {
-        mz_drain(&sm.qn[warp], &sm.qa[warp][0], &sm.qb[warp][0], &sm.qoff[warp][0], &sm.r0s[warp][0], bsrc, a.base_words, db, sink);
+        // items carry stream positions and the drain reads the bases from global memory (L2: they were just streamed in), so
+        // items survive the tile they come from and a drain always has >= MZ_QDRAIN items' windows to spread over the lanes
+        mz_drain(&sm.qn[warp], &sm.qa[warp][0], &sm.qc[warp][0], &sm.qb[warp][0], &sm.qoff[warp][0], a.bases, a.base_words, db, sink);
     };
-    // lanes with p append one item: windows `ik` of the block whose first window is `ia`, minimizer at base `rel` of the block
-    auto push = [&](bool p, uint32_t ia, uint32_t ik, uint32_t rel) {
+    // lanes with p append one item: windows `ik` of the block whose first window is at stream base `pb`, minimizer at base `rel` of the block
+    auto push = [&](bool p, unsigned long long pb, uint32_t ik, uint32_t rel) {
         if (p) {
             const uint32_t i = atomicAdd(&sm.qn[warp], 1u);
-            sm.qa[warp][i] = ia; sm.qb[warp][i] = ik | (rel << 16);
+            sm.qa[warp][i] = (uint32_t)pb; sm.qc[warp][i] = (uint32_t)(pb >> 32); sm.qb[warp][i] = ik | (rel << 16);
         }
     };
     auto drain_if_full = [&]() {
@@ -266,7 +268,6 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
             R0 = a.off ? a.off[r] : r * (unsigned long long)a.read_len;
             R1 = a.off ? a.off[r + 1] : R0 + a.read_len;
         }
-        sm.r0s[warp][lane] = R0;
         const unsigned long long len = R1 - R0;
         const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
         const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                     nnr = 1u + __popc(nchg);
                     nvm = vwin & ~ovfm;
                     if (__any_sync(FULL, t3 != 0u)) {
-                        const uint32_t ia = lane | ((seg * WMAX + blk16) << 5);
+                        const unsigned long long ia = R0 + (unsigned long long)seg * WMAX + blk16;
                         uint32_t rest = t3;
                         unsigned rr = MZ_MAXRUN;
                         while (__any_sync(FULL, rest != 0u)) {
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                     const uint32_t m0 = (c1 - 1u) & pvm, m1 = (c2 - c1) & pvm, m2 = (c3 - c2) & pvm, m3 = (0x10000u - c3) & pvm;
                     const bool q0 = b0 & (m0 != 0u), q1 = b1 & (m1 != 0u), q2 = b2 & (m2 != 0u), q3 = b3 & (m3 != 0u);
                     if (__any_sync(FULL, q0 | q1 | q2 | q3)) {
-                        const uint32_t ia = lane | ((seg * WMAX + pblk) << 5);
+                        const unsigned long long ia = R0 + (unsigned long long)seg * WMAX + pblk;
                         push(q0, ia, m0, pW & 63u);
                         push(q1, ia, m1, (pW >> 8) & 63u);
                         push(q2, ia, m2, (pW >> 16) & 63u);
@@ -437,13 +438,13 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                 for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
             }
         }
-        // items point into this tile's staged bases: finish them before the stage is refilled
-        drain();
+        __syncwarp();             // every lane is done with this stage's staged bases before it is refilled
         const unsigned long long t_new = next_tile();
         if (lane == 0 && t_new < ntiles) issue(stage, t_new);
         t = t_ahead; t_ahead = t_new;
     }
 
+    drain();                      // the items still waiting
     for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(FULL, my_valid, o);
     my_fetch = __reduce_add_sync(FULL, my_fetch);
     if (lane == 0 && my_valid) atomicAdd(a.n_kmers, my_valid);
