@@ -192,7 +192,7 @@ struct mlgi_reader {
     size_t cur_i = 0;
     bool eof = false;
     uint64_t tot_reads = 0, tot_bases = 0, tot_text = 0;
-    double t_wait_lines = 0, t_gather = 0, t_pack = 0, t_scan_busy = 0, t_scan_wait = 0, t_read_busy = 0;   // MLGI_PROFILE=1
+    double t_wait_lines = 0, t_gather = 0, t_pack = 0, t_scan_wait = 0;   // MLGI_PROFILE=1
 
     // BGZF (bgzip / htslib): a gzip file made of independent members of at most 64 KiB, each carrying its compressed size
     // in a 'BC' extra field and its inflated size in its trailer -- so members can be found without inflating anything and
