@@ -10,7 +10,7 @@
  * CMash and khmer are third-party modules that are not in /root/reference and not installed here (SURVEY.md A.2,
  * [UPSTREAM]); the hash itself is pinned by MurmurHash3's published vectors (tests/test_sketch.py), the rest of the
  * restatement is PARITY UNPINNED.  Written byte-wise and streaming, unlike the GPU path (word-wise, threshold + sort).
- * Only tests/ and scripts/sketch_bench.py's CPU leg may call this. */
+ * Only tests/ and tests/bench_sketch.py's CPU leg may call this. */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE -- ctypes binding of oracle/_build/libsketch_oracle.so (sketch_oracle.c): CPU restatement of CMash's
 bottom-n MinHash sketch construction.  PARITY UNPINNED beyond the hash function (see the C file's header).
 
-Only tests/ and scripts/sketch_bench.py's CPU leg import this."""
+Only tests/ and tests/bench_sketch.py's CPU leg import this."""
 from __future__ import annotations
 
 import ctypes as C

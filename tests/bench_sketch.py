@@ -1,7 +1,7 @@
 #! /usr/bin/env python
 """Sketch-builder throughput: random genomes -> bottom-1000 MinHash sketches (k = 60) on one GPU, next to
 the CPU restatement of CMash's CountEstimator (oracle/sketch_oracle.c, all host threads) on a bounded sample.
-    python scripts/sketch_bench.py [--genomes 64] [--mbp 3] [--cpu_genomes 4]
+    python tests/bench_sketch.py [--genomes 64] [--mbp 3] [--cpu_genomes 4]
 Prints one JSON line.  The kernel is instruction-bound (MurmurHash3 = two 64-bit multiplies per 8 bytes), so the figure
 is windows hashed per second; each base is read from HBM once."""
 import argparse
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import numpy as np  # noqa: E402
 
 from metalign_b200.api import Context  # noqa: E402
