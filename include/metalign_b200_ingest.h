@@ -12,7 +12,7 @@
  * A trailing '\r' is stripped; a file need not end with a newline.
  *
  * Pipeline: a plain file is mapped and `threads` threads find the sequence lines (two passes: count the newlines of every
- * part, then cut); a gzip file is inflated by one thread (zlib), a BGZF one (bgzip: independent members) by `threads`
+ * part, then cut); a gzip file is inflated by one thread (an in-house DEFLATE decoder with CRC check; MLGI_ZLIB=1 = zlib), a BGZF one (bgzip: independent members) by `threads`
  * threads at a time; `threads` workers then pack a batch in parallel into the caller's (pinned) buffers, 32 bases at a time
  * with AVX2 where the CPU has it.  No CUDA dependency: this library only fills host memory.  The file must not be
  * truncated while it is being read (it is mapped).

@@ -208,3 +208,71 @@ def test_large_parallel_pack_matches_codec(tmp_path):
     with pytest.raises(StopIteration):
         next(rd)
     rd.close()
+
+
+def test_fast_inflate_against_zlib():
+    """csrc/fast_inflate.h (the gzip decoder of the ingest) against zlib: every compression level (0 = stored blocks, tiny
+    inputs = fixed Huffman), random / repetitive / text-like data, several members in one file, header fields, and stopping
+    and resuming at every few output bytes; damaged streams fail (or fail their CRC) instead of crashing"""
+    import ctypes as C
+    import zlib
+    L = ingest.ingest_lib()
+    L.mlgi_test_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+    rng = random.Random(2024)
+
+    def gz(data, level, name=b""):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = co.compress(data) + co.flush()
+        flg = 8 if name else 0
+        hdr = b"\x1f\x8b\x08" + bytes([flg]) + b"\0\0\0\0\0\xff" + (name + b"\0" if name else b"")
+        return hdr + body + (zlib.crc32(data) & 0xFFFFFFFF).to_bytes(4, "little") + (len(data) & 0xFFFFFFFF).to_bytes(4, "little")
+
+    def inflate(blob, want_len, step):
+        out = np.empty(want_len + step + 1024, dtype=np.uint8)
+        n = C.c_uint64()
+        rc = L.mlgi_test_inflate(blob, len(blob), out.ctypes.data, out.size, step, C.byref(n))
+        return rc, out[:n.value].tobytes() if rc == 0 else b""
+
+    def sample(kind, n):
+        if kind == "random":
+            return bytes(rng.randrange(256) for _ in range(n))
+        if kind == "dna":
+            return "".join("@r%d\n%s\n+\n%s\n" % (i, "".join(rng.choice("ACGT") for _ in range(100)),
+                                                   "".join(rng.choice("FFFF:,#") for _ in range(100))) for i in range(n // 210 + 1)).encode()[:n]
+        if kind == "runs":
+            return b"".join(bytes([rng.randrange(4) + 65]) * rng.randint(1, 700) for _ in range(n // 300 + 1))[:n]
+        return (b"the quick brown fox jumps over the lazy dog " * (n // 44 + 1))[:n]
+
+    cases = 0
+    for kind in ("random", "dna", "runs", "text"):
+        for n in (0, 1, 5, 300, 70000, 400000):
+            data = sample(kind, n)
+            for level in (0, 1, 6, 9):
+                blob = gz(data, level, name=b"x.fq" if level == 6 else b"")
+                for step in (1 << 22, 7, 1000):
+                    if step == 7 and n > 70000:
+                        continue
+                    rc, got = inflate(blob, len(data), step)
+                    assert rc == 0 and got == data, (kind, n, level, step, rc)
+                    cases += 1
+    # several members, and zero padding behind the last one
+    parts = [sample("dna", 5000), b"", sample("text", 100000), sample("random", 3000)]
+    blob = b"".join(gz(p, lv) for p, lv in zip(parts, (1, 6, 0, 9))) + b"\0" * 37
+    rc, got = inflate(blob, sum(map(len, parts)), 4096)
+    assert rc == 0 and got == b"".join(parts)
+    # damage: never a crash, never a silent success with wrong bytes
+    data = sample("dna", 200000)
+    blob = bytearray(gz(data, 6))
+    silent = 0
+    for _ in range(300):
+        b2 = bytearray(blob)
+        for _ in range(rng.randint(1, 3)):
+            b2[rng.randrange(len(b2))] ^= 1 << rng.randrange(8)
+        rc, got = inflate(bytes(b2), len(data) + 70000, 1 << 16)
+        if rc == 0:
+            assert got == data             # only flips in ignored header fields (mtime, xfl, os) can leave the data intact
+            silent += 1
+    assert silent < 30
+    rc, _ = inflate(bytes(blob[:len(blob) // 2]), len(data), 1 << 16)
+    assert rc != 0
+    assert cases > 200
