@@ -51,6 +51,7 @@ extern "C" {
 #define MLG_ERR_IO (-3)
 #define MLG_ERR_STATE (-4)
 #define MLG_ERR_NOMEM (-5)
+#define MLG_ERR_RETRY (-6) /* mlg_query_finish after an exchange whose blocks were too small: repeat it with a larger one */
 
 #define MLG_GATE_EXACT 0 /* smallest-k prefilter with zero false positives */
 #define MLG_GATE_NONE 1  /* no prefilter */
@@ -58,6 +59,7 @@ extern "C" {
 typedef struct mlg_ctx mlg_ctx;
 typedef struct mlg_db mlg_db;
 typedef struct mlg_query mlg_query;
+typedef struct mlg_exchange mlg_exchange;
 
 typedef struct mlg_stats {
     uint64_t n_reads;        /* reads pushed */
@@ -134,6 +136,30 @@ int mlg_query_counts_import(mlg_query* q);
  * count 0 (padding) are ignored.  After the first merge no more reads can be pushed. */
 int mlg_query_counts_export_sparse(mlg_query* q, uint64_t** d_entries, uint64_t* n_entries);
 int mlg_query_counts_merge_sparse(mlg_query* q, const uint64_t* d_entries, uint64_t n_entries);
+/* The same exchange WITHOUT a host round trip (everything below is queued on the context's compute stream; nothing
+ * synchronises the host).  An mlg_exchange is one rank's end: persistent buffers sized for cap_entries non-zero
+ * counters per rank.  A rank's contribution is one block of *block_words uint64: [0] its number of non-zero counters,
+ * [1] unused, then the entries.
+ *   all-gather form:  mlg_query_exchange_pack() fills *d_send; the caller all-gathers every rank's block into *d_recv
+ *                     (world blocks, rank order; e.g. ncclAllGather / torch.distributed on the compute stream);
+ *                     mlg_query_exchange_merge() adds the other ranks' blocks into this rank's counters.
+ *   direct form:      mlg_query_exchange_p2p() stores the block straight into every peer's mailbox over NVLink
+ *                     (peer-mapped memory: exchange the 64-byte handles of mlg_exchange_local_handle() between the
+ *                     ranks once, then mlg_exchange_connect()), publishes it with a system-scope release, waits on the
+ *                     device for the peers' blocks and merges them -- no NCCL call, no host involvement.  Collective:
+ *                     every rank must call it once per query, in the same order.
+ *   dense form:       mlg_query_exchange_dense() = mlg_query_counts_export() + _import() without the host join.
+ * If some rank had more than cap_entries non-zero counters, nothing is merged on any rank and mlg_query_finish()
+ * returns MLG_ERR_RETRY: repeat the exchange with a larger mlg_exchange and call finish again. */
+int mlg_exchange_create(mlg_ctx* ctx, uint32_t world, uint32_t rank, uint64_t cap_entries, mlg_exchange** out);
+int mlg_exchange_destroy(mlg_exchange* ex);
+int mlg_exchange_buffers(mlg_exchange* ex, uint64_t** d_send, uint64_t** d_recv, uint64_t* block_words);
+int mlg_exchange_local_handle(mlg_exchange* ex, void* handle64 /* 64 bytes out */);
+int mlg_exchange_connect(mlg_exchange* ex, const void* handles /* world * 64 bytes, rank order */);
+int mlg_query_exchange_pack(mlg_query* q, mlg_exchange* ex);
+int mlg_query_exchange_merge(mlg_query* q, mlg_exchange* ex);
+int mlg_query_exchange_p2p(mlg_query* q, mlg_exchange* ex);
+int mlg_query_exchange_dense(mlg_query* q, uint8_t** d_counts, uint64_t* n_counts);
 /* num/den: int64 [G*nk]; ci: double [G*nk] (num/den where num > 0, else 0.0); any pointer may be NULL */
 int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect);
 /* after finish: I as (hi,lo) canonical keys in increasing order; writes at most cap pairs, *n = |I| */

@@ -14,6 +14,9 @@ LIB_PATH = os.environ.get("MLG_LIB_PATH") or os.path.join(_HERE, "libmetalign_b2
 _LIB = None
 
 
+MLG_ERR_RETRY = -6
+
+
 class MlgError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__("metalign_b200 error %d: %s" % (code, msg))
@@ -71,6 +74,15 @@ SIGNATURES = {
     "mlg_query_counts_import": (C.c_int, [_vp]),
     "mlg_query_counts_export_sparse": (C.c_int, [_vp, _pp, C.POINTER(C.c_uint64)]),
     "mlg_query_counts_merge_sparse": (C.c_int, [_vp, _u64p, C.c_uint64]),
+    "mlg_exchange_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint64, _pp]),
+    "mlg_exchange_destroy": (C.c_int, [_vp]),
+    "mlg_exchange_buffers": (C.c_int, [_vp, _pp, _pp, C.POINTER(C.c_uint64)]),
+    "mlg_exchange_local_handle": (C.c_int, [_vp, _vp]),
+    "mlg_exchange_connect": (C.c_int, [_vp, _vp]),
+    "mlg_query_exchange_pack": (C.c_int, [_vp, _vp]),
+    "mlg_query_exchange_merge": (C.c_int, [_vp, _vp]),
+    "mlg_query_exchange_p2p": (C.c_int, [_vp, _vp]),
+    "mlg_query_exchange_dense": (C.c_int, [_vp, _pp, C.POINTER(C.c_uint64)]),
     "mlg_query_finish": (C.c_int, [_vp, _i64p, _i64p, _f64p, C.POINTER(C.c_uint64)]),
     "mlg_query_intersection": (C.c_int, [_vp, _u64p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mlg_query_stats": (C.c_int, [_vp, C.POINTER(Stats)]),

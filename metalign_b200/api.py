@@ -219,23 +219,50 @@ class Query:
     def counts_import(self):
         check(_lib.lib().mlg_query_counts_import(self._h))
 
+    # -- multi-GPU exchange without a host round trip (see metalign_b200.dist) -------------------------------
+    def exchange_pack(self, ex: "Exchange"):
+        check(_lib.lib().mlg_query_exchange_pack(self._h, ex._h))
+
+    def exchange_merge(self, ex: "Exchange"):
+        check(_lib.lib().mlg_query_exchange_merge(self._h, ex._h))
+
+    def exchange_p2p(self, ex: "Exchange"):
+        check(_lib.lib().mlg_query_exchange_p2p(self._h, ex._h))
+
+    def exchange_dense(self):
+        """(device pointer, length) of the clamped uint8 counters; queued on the compute stream, nothing is joined"""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(_lib.lib().mlg_query_exchange_dense(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def _finish_call(self, num_ptr, den_ptr, ci_ptr):
+        """mlg_query_finish; an exchange whose blocks turned out too small is repeated once with larger ones
+        (self._exchange_retry is set by metalign_b200.dist.reduce_query)"""
+        ni = C.c_uint64()
+        rc = _lib.lib().mlg_query_finish(self._h, num_ptr, den_ptr, ci_ptr, C.byref(ni))
+        retry = getattr(self, "_exchange_retry", None)
+        if rc == _lib.MLG_ERR_RETRY and retry is not None:
+            msg = _lib.lib().mlg_last_error().decode(errors="replace")
+            retry(int(msg.split(":")[-1].split()[0]))
+            rc = _lib.lib().mlg_query_finish(self._h, num_ptr, den_ptr, ci_ptr, C.byref(ni))
+        check(rc)
+        return ni.value
+
     def finish(self):
         G, nk = self.db.G, len(self.db.ks)
         num = np.zeros((G, nk), dtype=np.int64)
         den = np.zeros((G, nk), dtype=np.int64)
         ci = np.zeros((G, nk), dtype=np.float64)
-        ni = C.c_uint64()
-        check(_lib.lib().mlg_query_finish(self._h, num.ctypes.data, den.ctypes.data, ci.ctypes.data, C.byref(ni)))
+        ni = self._finish_call(num.ctypes.data, den.ctypes.data, ci.ctypes.data)
         self._keep = []
         st = self.stats()
-        return dict(num=num, den=den, ci=ci, n_intersect=ni.value, n_kmers=st["n_kmers"], stats=st)
+        return dict(num=num, den=den, ci=ci, n_intersect=ni, n_kmers=st["n_kmers"], stats=st)
 
     def finish_into(self, num_ptr: int, den_ptr: int, ci_ptr: int) -> int:
         """finish() writing into caller-provided (pinned) host buffers; returns |I|."""
-        ni = C.c_uint64()
-        check(_lib.lib().mlg_query_finish(self._h, num_ptr, den_ptr, ci_ptr, C.byref(ni)))
+        ni = self._finish_call(num_ptr, den_ptr, ci_ptr)
         self._keep = []
-        return ni.value
+        return ni
 
     def intersection(self) -> np.ndarray:
         n = C.c_uint64()
@@ -261,3 +288,31 @@ class Query:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class Exchange:
+    """One rank's end of the multi-GPU exchange of the per-k-mer counters (mlg_exchange in the header): persistent
+    device buffers for `cap_entries` non-zero counters per rank."""
+
+    def __init__(self, ctx: Context, world: int, rank: int, cap_entries: int):
+        self.ctx, self.world, self.rank, self.cap = ctx, int(world), int(rank), int(cap_entries)
+        self._h = C.c_void_p()
+        check(_lib.lib().mlg_exchange_create(ctx._h, self.world, self.rank, self.cap, C.byref(self._h)))
+        a, b, w = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        check(_lib.lib().mlg_exchange_buffers(self._h, C.byref(a), C.byref(b), C.byref(w)))
+        self.send_ptr, self.recv_ptr, self.block_words = a.value, b.value, w.value
+
+    def local_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(_lib.lib().mlg_exchange_local_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles: bytes):
+        if len(handles) != 64 * self.world:
+            raise ValueError("need one 64-byte handle per rank")
+        check(_lib.lib().mlg_exchange_connect(self._h, handles))
+
+    def close(self):
+        if self._h:
+            _lib.lib().mlg_exchange_destroy(self._h)
+            self._h = C.c_void_p()

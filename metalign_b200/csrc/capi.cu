@@ -111,6 +111,20 @@ inline unsigned long long round_up(unsigned long long x, unsigned long long m) {
 
 }  // namespace
 
+// One rank's end of the multi-GPU exchange (include/metalign_b200.h, "exchange"): persistent blocks for the all-gather
+// form, and the peer-mapped mailboxes of the direct (NVLink store) form.
+struct mlg_exchange {
+    mlg_ctx* ctx = nullptr;
+    uint32_t world = 1, rank = 0;
+    unsigned long long cap = 0, block_words = 0;
+    DevBuf<unsigned long long> send, recv, status;     // status: [0] largest count of an overflowing exchange, [1] peer timeout, [2] CTA counter
+    unsigned long long* mailbox = nullptr;             // [world senders][2 parities][block_words], cudaMalloc'ed (IPC-exportable)
+    unsigned long long* peer_mailbox[MLG_MAX_RANKS] = {};   // peers' mailboxes as mapped into this process (own slot unused)
+    bool connected = false;
+    unsigned long long epoch = 0;
+    unsigned long long timeout_ns = 20ull * 1000ull * 1000ull * 1000ull;
+};
+
 struct mlg_query {
     mlg_ctx* ctx = nullptr;
     mlg_db* db = nullptr;
@@ -124,6 +138,7 @@ struct mlg_query {
     cudaEvent_t ev_q0 = nullptr, ev_q1 = nullptr;
     mlg_stats st{};
     bool finished = false, reduced = false, merged = false;
+    mlg_exchange* ex_pending = nullptr;            // exchange whose status words mlg_query_finish has to look at
     DevBuf<unsigned long long> sparse;             // this rank's non-zero counters as index | count << 32
     unsigned long long chunk_words = CHUNK_WORDS;   // 64-base words per host->device copy chunk
     // results kept for mlg_query_intersection
@@ -578,6 +593,135 @@ MLG_API int mlg_query_counts_import(mlg_query* q) {
     return MLG_OK;
 }
 
+// ------------------------------------------------------------------ exchange (multi-GPU, no host round trip)
+MLG_API int mlg_exchange_create(mlg_ctx* ctx, uint32_t world, uint32_t rank, uint64_t cap_entries, mlg_exchange** out) {
+    if (!ctx || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (world < 1 || world > MLG_MAX_RANKS || rank >= world) { mlg_set_error("world=%u rank=%u out of range (1..%d ranks)", world, rank, MLG_MAX_RANKS); return MLG_ERR_ARG; }
+    if (cap_entries < 1 || cap_entries > (1ull << 32)) { mlg_set_error("cap_entries out of range"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(ctx));
+    mlg_exchange* ex = new mlg_exchange();
+    struct Guard { mlg_exchange* e; ~Guard() { if (e) mlg_exchange_destroy(e); } } guard{ex};
+    ex->ctx = ctx; ex->world = world; ex->rank = rank; ex->cap = cap_entries;
+    ex->block_words = round_up(cap_entries + 2, 2);
+    MLG_TRY(ex->send.alloc(ex->block_words)); MLG_TRY(ex->recv.alloc(ex->block_words * world)); MLG_TRY(ex->status.alloc(4));
+    const size_t mb = (size_t)world * 2 * ex->block_words * 8;
+    CUDA_TRY(cudaMalloc(&ex->mailbox, mb));
+    CUDA_TRY(cudaMemsetAsync(ex->mailbox, 0, mb, ctx->s_comp));
+    CUDA_TRY(cudaMemsetAsync(ex->send.p, 0, ex->block_words * 8, ctx->s_comp));
+    CUDA_TRY(cudaMemsetAsync(ex->recv.p, 0, ex->block_words * world * 8, ctx->s_comp));
+    CUDA_TRY(cudaMemsetAsync(ex->status.p, 0, 32, ctx->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
+    guard.e = nullptr;
+    *out = ex;
+    return MLG_OK;
+}
+MLG_API int mlg_exchange_destroy(mlg_exchange* ex) {
+    if (!ex) return MLG_OK;
+    cudaSetDevice(ex->ctx->device);
+    cudaStreamSynchronize(ex->ctx->s_comp);
+    for (uint32_t w = 0; w < ex->world; ++w)
+        if (w != ex->rank && ex->peer_mailbox[w]) cudaIpcCloseMemHandle(ex->peer_mailbox[w]);
+    if (ex->mailbox) cudaFree(ex->mailbox);
+    delete ex;
+    return MLG_OK;
+}
+MLG_API int mlg_exchange_buffers(mlg_exchange* ex, uint64_t** d_send, uint64_t** d_recv, uint64_t* block_words) {
+    if (!ex) { mlg_set_error("null exchange"); return MLG_ERR_ARG; }
+    if (d_send) *d_send = reinterpret_cast<uint64_t*>(ex->send.p);
+    if (d_recv) *d_recv = reinterpret_cast<uint64_t*>(ex->recv.p);
+    if (block_words) *block_words = ex->block_words;
+    return MLG_OK;
+}
+MLG_API int mlg_exchange_local_handle(mlg_exchange* ex, void* handle64) {
+    if (!ex || !handle64) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 opaque bytes");
+    MLG_TRY(ensure_device(ex->ctx));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, ex->mailbox));
+    memcpy(handle64, &h, 64);
+    return MLG_OK;
+}
+MLG_API int mlg_exchange_connect(mlg_exchange* ex, const void* handles) {
+    if (!ex || !handles) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (ex->connected) return MLG_OK;
+    MLG_TRY(ensure_device(ex->ctx));
+    for (uint32_t w = 0; w < ex->world; ++w) {
+        if (w == ex->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * (size_t)w, 64);
+        void* p = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ex->peer_mailbox[w] = (unsigned long long*)p;
+    }
+    ex->connected = true;
+    return MLG_OK;
+}
+static int check_exchange(mlg_query* q, mlg_exchange* ex) {
+    if (!q || !ex) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
+    if (q->reduced) { mlg_set_error("counters were already reduced densely"); return MLG_ERR_STATE; }
+    if (ex->ctx != q->ctx) { mlg_set_error("exchange belongs to another context"); return MLG_ERR_ARG; }
+    if ((unsigned long long)q->ci_min * ex->world > 255ull) { mlg_set_error("ci_min * world must fit the 8-bit counters"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(q->ctx));
+    if (!q->present.p) { MLG_TRY(q->present.alloc((size_t)q->db->v.nd + 1)); MLG_TRY(q->touched.alloc((size_t)q->db->v.nd + 1)); }
+    return MLG_OK;
+}
+// the probe kernels run on the compute stream, the copies feeding them on the copy stream, and every copy chunk is
+// already awaited by the probe launch that consumes it: work queued on the compute stream after the last push sees
+// every counter.  No host synchronisation here.
+MLG_API int mlg_query_exchange_pack(mlg_query* q, mlg_exchange* ex) {
+    MLG_TRY(check_exchange(q, ex));
+    cudaStream_t st = q->ctx->s_comp;
+    CUDA_TRY(cudaMemsetAsync(ex->status.p, 0, 16, st));
+    MLG_TRY(launch_pack_exchange(q->cnt8.p, q->touched.p, q->d_scalar.p + 1, (uint32_t)q->ci_min, ex->send.p, ex->cap, st));
+    q->st.gpu_launches += 1;
+    return MLG_OK;
+}
+MLG_API int mlg_query_exchange_merge(mlg_query* q, mlg_exchange* ex) {
+    MLG_TRY(check_exchange(q, ex));
+    MLG_TRY(launch_merge_exchange(q->cnt8.p, ex->recv.p, ex->block_words, ex->world, ex->rank, ex->cap, q->db->v.nd, (uint32_t)q->ci_min,
+                                  q->present.p, q->touched.p, q->d_scalar.p, ex->status.p, 0, 0, q->ctx->s_comp));
+    q->st.gpu_launches += 1;
+    q->merged = true; q->ex_pending = ex;
+    return MLG_OK;
+}
+MLG_API int mlg_query_exchange_p2p(mlg_query* q, mlg_exchange* ex) {
+    MLG_TRY(check_exchange(q, ex));
+    if (ex->world > 1 && !ex->connected) { mlg_set_error("mlg_exchange_connect has not been called"); return MLG_ERR_STATE; }
+    cudaStream_t st = q->ctx->s_comp;
+    const unsigned long long epoch = ++ex->epoch;
+    if (epoch >= (1ull << 23)) { mlg_set_error("exchange epoch counter exhausted; create a new exchange"); return MLG_ERR_STATE; }
+    const unsigned long long parity = epoch & 1ull;
+    unsigned long long* boxes[MLG_MAX_RANKS];
+    uint32_t np = 0;
+    for (uint32_t w = 0; w < ex->world; ++w)
+        if (w != ex->rank) boxes[np++] = ex->peer_mailbox[w] + ((unsigned long long)ex->rank * 2ull + parity) * ex->block_words;
+    CUDA_TRY(cudaMemsetAsync(ex->status.p, 0, 16, st));
+    MLG_TRY(launch_push_peers(q->cnt8.p, q->touched.p, q->d_scalar.p + 1, (uint32_t)q->ci_min, boxes, np, ex->cap, epoch,
+                              reinterpret_cast<unsigned int*>(ex->status.p + 2), st));
+    MLG_TRY(launch_merge_exchange(q->cnt8.p, ex->mailbox + parity * ex->block_words, 2ull * ex->block_words, ex->world, ex->rank, ex->cap,
+                                  q->db->v.nd, (uint32_t)q->ci_min, q->present.p, q->touched.p, q->d_scalar.p, ex->status.p, epoch,
+                                  ex->timeout_ns, st));
+    q->st.gpu_launches += 2;
+    q->merged = true; q->ex_pending = ex;
+    return MLG_OK;
+}
+// dense form without the host join of mlg_query_counts_export: the counters are clamped on the compute stream and the
+// caller's all-reduce must be ordered after it on that stream
+MLG_API int mlg_query_exchange_dense(mlg_query* q, uint8_t** d_counts, uint64_t* n_counts) {
+    if (!q || !d_counts || !n_counts) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
+    if (q->merged) { mlg_set_error("counters were already merged sparsely"); return MLG_ERR_STATE; }
+    MLG_TRY(ensure_device(q->ctx));
+    if (q->touched.p) {
+        MLG_TRY(launch_clamp_counts(q->cnt8.p, q->touched.p, q->d_scalar.p + 1, (uint32_t)q->ci_min, q->ctx->s_comp));
+        q->st.gpu_launches += 1;
+    }
+    *d_counts = q->cnt8.p; *n_counts = q->db->v.nd;
+    q->reduced = true;
+    return MLG_OK;
+}
+
 MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect) {
     if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
     if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
@@ -621,8 +765,18 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     unsigned long long& nk_host = nk_host2[0];
     CUDA_TRY(cudaMemcpyAsync(nk_host2, q->d_nkmers.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&ni, q->d_scalar.p, 8, cudaMemcpyDeviceToHost, st));
+    unsigned long long xstat[2] = {0, 0};
+    if (q->ex_pending) CUDA_TRY(cudaMemcpyAsync(xstat, q->ex_pending->status.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
+    if (xstat[1]) { mlg_set_error("exchange: a peer's block did not arrive within the time limit"); return MLG_ERR_STATE; }
+    if (xstat[0]) {
+        // some rank had more non-zero counters than a block holds: nothing was merged (on any rank), so the exchange can
+        // simply be repeated with larger blocks and finish called again
+        q->merged = false; q->ex_pending = nullptr;
+        mlg_set_error("exchange blocks too small: %llu entries needed", xstat[0]);
+        return MLG_ERR_RETRY;
+    }
     q->n_present = (uint32_t)ni;
     q->st.n_kmers = nk_host; q->st.n_intersect = ni;
     q->st.n_bucket_fetches = v.layout >= 1 ? nk_host2[1] : nk_host;

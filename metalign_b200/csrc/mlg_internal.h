@@ -9,6 +9,7 @@
 #include "../../include/metalign_b200.h"
 
 #define MLG_MAX_KS 8
+#define MLG_MAX_RANKS 16        // ranks of one exchange (one NVSwitch domain)
 #define MLG_TILE_WORDS 256u     // 64-base words per K1 tile == threads per CTA
 
 void mlg_set_error(const char* fmt, ...);
@@ -143,6 +144,15 @@ int launch_pack_touched(const unsigned char* cnt8, const uint32_t* touched, cons
                         unsigned long long* out, cudaStream_t st);
 int launch_merge_sparse(unsigned char* cnt8, const unsigned long long* entries, unsigned long long n, uint32_t nd, uint32_t ci_min,
                         uint32_t* present, uint32_t* touched, unsigned long long* d_cursors, cudaStream_t st);
+int launch_pack_exchange(const unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min,
+                         unsigned long long* out, unsigned long long cap, cudaStream_t st);
+int launch_push_peers(const unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min,
+                      unsigned long long* const* boxes, uint32_t n_peers, unsigned long long cap, unsigned long long epoch,
+                      unsigned int* done_ctas, cudaStream_t st);
+int launch_merge_exchange(unsigned char* cnt8, const unsigned long long* recv, unsigned long long stride_words, uint32_t world, uint32_t rank,
+                          unsigned long long cap, uint32_t nd, uint32_t ci_min, uint32_t* present, uint32_t* touched,
+                          unsigned long long* d_cursors, unsigned long long* d_status, unsigned long long epoch,
+                          unsigned long long timeout_ns, cudaStream_t st);
 int launch_compact_present(const unsigned char* cnt8, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* d_cursor,
                            cudaStream_t st);
 int launch_expand_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,

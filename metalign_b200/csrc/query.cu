@@ -241,6 +241,117 @@ __global__ void k_merge_sparse(unsigned char* cnt8, const unsigned long long* __
         }
     }
 }
+// ---- the multi-GPU exchange without a host round trip (mlg_exchange, capi.cu) --------------------------------------
+// A rank's contribution travels as one BLOCK of block_words 64-bit words: word 0 = number of non-zero counters n
+// (| epoch << 40 on the direct path), word 1 unused, then min(n, cap) entries index | min(count, ci_min) << 32.
+constexpr unsigned long long XCNT_MASK = (1ull << 40) - 1ull;
+// fill this rank's block in local memory (the caller all-gathers the blocks, e.g. with NCCL)
+__global__ void k_pack_exchange(const unsigned char* __restrict__ cnt8, const uint32_t* __restrict__ touched,
+                                const unsigned long long* __restrict__ d_n, uint32_t ci_min, unsigned long long* out,
+                                unsigned long long cap) {
+    const unsigned long long n = *d_n, m = n < cap ? n : cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = n; out[1] = 0; }
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t e = touched[i];
+        const uint32_t c = cnt8[e];
+        out[2 + i] = (unsigned long long)e | ((unsigned long long)(c > ci_min ? ci_min : c) << 32);
+    }
+}
+// direct path: store the block straight into every peer's mailbox over NVLink (peer-mapped pointers), then -- once every
+// CTA's stores are fenced -- publish count | epoch << 40 in word 0 of each copy with a system-scope release
+struct PeerBoxes { unsigned long long* box[MLG_MAX_RANKS]; uint32_t n; };
+__global__ void k_push_peers(const unsigned char* __restrict__ cnt8, const uint32_t* __restrict__ touched,
+                             const unsigned long long* __restrict__ d_n, uint32_t ci_min, PeerBoxes pb, unsigned long long cap,
+                             unsigned long long epoch, unsigned int* done_ctas) {
+    const unsigned long long n = *d_n, m = n < cap ? n : cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < m; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t e = touched[i];
+        const uint32_t c = cnt8[e];
+        const unsigned long long en = (unsigned long long)e | ((unsigned long long)(c > ci_min ? ci_min : c) << 32);
+        for (uint32_t p = 0; p < pb.n; ++p) pb.box[p][2 + i] = en;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(done_ctas, 1u);
+        if (t == gridDim.x - 1u) {                       // the last CTA: every other CTA's stores are fenced before its increment
+            *done_ctas = 0u;
+            __threadfence_system();
+            const unsigned long long flag = (n & XCNT_MASK) | (epoch << 40);
+            for (uint32_t p = 0; p < pb.n; ++p)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pb.box[p]), "l"(flag) : "memory");
+        }
+    }
+}
+// add every OTHER rank's block into this rank's counters (saturating); a counter that crosses ci_min joins present[].
+// recv + w * stride_words = block of rank w.  epoch != 0: the blocks were stored by the peers themselves -- wait for word 0
+// of each to carry this epoch (bounded by timeout_ns).  If any rank had more entries than a block holds, NOTHING is merged
+// and status[0] = the largest count (the caller repeats the exchange with larger blocks); status[1] = 1 on a timeout.
+__global__ void k_merge_exchange(unsigned char* cnt8, const unsigned long long* recv, unsigned long long stride_words, uint32_t world,
+                                 uint32_t rank, unsigned long long cap, uint32_t nd, uint32_t ci_min, uint32_t* present, uint32_t* touched,
+                                 unsigned long long* cursors, unsigned long long* status, unsigned long long epoch,
+                                 unsigned long long timeout_ns) {
+    __shared__ unsigned long long s_cnt[MLG_MAX_RANKS];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const uint32_t w = threadIdx.x;
+        unsigned long long v = 0;
+        if (w != rank) {
+            const unsigned long long* fp = recv + (unsigned long long)w * stride_words;
+            if (epoch) {
+                unsigned long long t0, t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(fp) : "memory");
+                    if ((v >> 40) == epoch) break;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > timeout_ns) { s_bad = 2; v = 0; break; }
+                    __nanosleep(200);
+                }
+            } else {
+                v = __ldcg(fp);
+            }
+            v &= XCNT_MASK;
+            if (v > cap) atomicMax(&s_bad, 1);
+        }
+        s_cnt[w] = v;
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long mx = 0;
+            for (uint32_t w = 0; w < world; ++w) mx = s_cnt[w] > mx ? s_cnt[w] : mx;
+            if (s_bad == 2) status[1] = 1; else status[0] = mx;
+        }
+        return;
+    }
+    const unsigned long long total = (unsigned long long)world * cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t w = (uint32_t)(i / cap);
+        const unsigned long long k = i - (unsigned long long)w * cap;
+        if (k >= s_cnt[w]) continue;                      // s_cnt[rank] == 0: the own block is skipped
+        const unsigned long long en = __ldcg(recv + (unsigned long long)w * stride_words + 2ull + k);
+        const uint32_t e = (uint32_t)en, c = (uint32_t)(en >> 32);
+        if (c == 0u || e >= nd) continue;
+        uint32_t* wp = reinterpret_cast<uint32_t*>(cnt8) + (e >> 2);
+        const uint32_t sh = (e & 3u) * 8u;
+        uint32_t old = *reinterpret_cast<volatile uint32_t*>(wp);
+        for (;;) {
+            const uint32_t before = (old >> sh) & 0xFFu;
+            const uint32_t after = before + c > 255u ? 255u : before + c;
+            if (after == before) break;
+            const uint32_t assumed = old;
+            old = atomicCAS(wp, assumed, (assumed & ~(0xFFu << sh)) | (after << sh));
+            if (old == assumed) {
+                if (before == 0u) touched[atomicAdd(cursors + 1, 1ull)] = e;
+                if (before < ci_min && after >= ci_min) present[atomicAdd(cursors, 1ull)] = e;
+                break;
+            }
+        }
+    }
+}
 // present[] = indices of the counters >= ci_min; 16 counters per thread and step (the table is almost all zeros)
 __global__ void k_compact_present(const uint4* __restrict__ cnt16, uint32_t nd, uint32_t ci_min, uint32_t* out, unsigned long long* cursor) {
     const unsigned long long nvec = ((unsigned long long)nd + 15ull) / 16ull;       // the table is padded to 16 bytes with zeros
@@ -303,6 +414,32 @@ int launch_merge_sparse(unsigned char* cnt8, const unsigned long long* entries, 
     if (!n) return MLG_OK;
     unsigned long long want = (n + 255) / 256;
     k_merge_sparse<<<(unsigned)(want < 148ull * 8ull ? want : 148ull * 8ull), 256, 0, st>>>(cnt8, entries, n, nd, ci_min, present, touched, d_cursors);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_pack_exchange(const unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min,
+                         unsigned long long* out, unsigned long long cap, cudaStream_t st) {
+    k_pack_exchange<<<148u * 2u, 256, 0, st>>>(cnt8, touched, d_n_touched, ci_min, out, cap);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_push_peers(const unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, uint32_t ci_min,
+                      unsigned long long* const* boxes, uint32_t n_peers, unsigned long long cap, unsigned long long epoch,
+                      unsigned int* done_ctas, cudaStream_t st) {
+    PeerBoxes pb{};
+    pb.n = n_peers;
+    for (uint32_t p = 0; p < n_peers && p < MLG_MAX_RANKS; ++p) pb.box[p] = boxes[p];
+    k_push_peers<<<148u, 256, 0, st>>>(cnt8, touched, d_n_touched, ci_min, pb, cap, epoch, done_ctas);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_merge_exchange(unsigned char* cnt8, const unsigned long long* recv, unsigned long long stride_words, uint32_t world, uint32_t rank,
+                          unsigned long long cap, uint32_t nd, uint32_t ci_min, uint32_t* present, uint32_t* touched,
+                          unsigned long long* d_cursors, unsigned long long* d_status, unsigned long long epoch,
+                          unsigned long long timeout_ns, cudaStream_t st) {
+    static_assert(MLG_MAX_RANKS <= 256, "one thread per rank reads the block headers");
+    k_merge_exchange<<<148u * 4u, 256, 0, st>>>(cnt8, recv, stride_words, world, rank, cap, nd, ci_min, present, touched, d_cursors,
+                                              d_status, epoch, timeout_ns);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }

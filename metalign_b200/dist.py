@@ -97,59 +97,102 @@ def allgather_sparse(entries, group=None):
     return recv, sizes
 
 
+EXCHANGE_MODES = ("sparse", "dense", "p2p")
+
+
 def exchange_mode() -> str:
     m = os.environ.get("MLG_EXCHANGE", "sparse")
-    if m not in ("sparse", "dense"):
-        raise ValueError("MLG_EXCHANGE must be 'sparse' or 'dense'")
+    if m not in EXCHANGE_MODES:
+        raise ValueError("MLG_EXCHANGE must be one of %s" % (EXCHANGE_MODES,))
     return m
 
 
+def describe_exchange(mode: str, world: int) -> str:
+    """what bench.py prints in config.parallelism"""
+    return {"sparse": "1 NCCL all-gather of the non-zero per-k-mer counters (fixed-size blocks, no host round trip)",
+            "dense": "1 NCCL uint8 sum all-reduce of the whole per-k-mer counter table",
+            "p2p": "non-zero per-k-mer counters stored straight into the peers' NVLink-mapped mailboxes by a kernel "
+                   "(system-scope release/acquire flags, no NCCL call, no host round trip)"}[mode]
+
+
+_EXCHANGES = {}          # (id(ctx), world, rank, mode in ('p2p', 'gather')) -> (Exchange, torch views)
+_DEFAULT_CAP = 1 << 20   # entries per rank: 8 MiB blocks; grown on demand (MLG_ERR_RETRY)
+
+
+def _comp_stream(ctx, device):
+    import torch
+    return torch.cuda.ExternalStream(ctx.streams()[0], device=device)
+
+
+def _get_exchange(ctx, device: int, group, p2p: bool, cap: int = 0):
+    """the persistent exchange of this context (created collectively on first use; re-created with larger blocks when
+    `cap` asks for more)"""
+    import torch
+    import torch.distributed as dist
+    from .api import Exchange
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    key = (id(ctx), world, rank)
+    cur = _EXCHANGES.get(key)
+    if cur is not None and cur["ex"].cap >= max(cap, 1) and (cur["connected"] or not p2p):
+        return cur
+    if cur is not None and cur["ex"].cap < cap:
+        cur["ex"].close()
+        cur = None
+    if cur is None:
+        ex = Exchange(ctx, world, rank, max(cap, int(os.environ.get("MLG_EXCHANGE_CAP", _DEFAULT_CAP))))
+        send = device_view_i64(ex.send_ptr, ex.block_words, device)
+        recv = device_view_i64(ex.recv_ptr, ex.block_words * world, device)
+        cur = dict(ex=ex, send=send, recv=recv, connected=False)
+        _EXCHANGES[key] = cur
+    if p2p and not cur["connected"]:
+        mine = torch.frombuffer(bytearray(cur["ex"].local_handle()), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            mine = mine.to("cuda:%d" % device)
+        allh = torch.empty(64 * world, dtype=torch.uint8, device=mine.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        cur["ex"].connect(bytes(allh.cpu().numpy().tobytes()))
+        cur["connected"] = True
+    return cur
+
+
 def reduce_query(query, device: int = 0, group=None, mode: str = None) -> None:
-    """The exchange step for a live GPU Query (see the module docstring for the two forms)."""
+    """The exchange step for a live GPU Query (see the module docstring).  Nothing here synchronises the host: every
+    kernel and the collective are queued on the library's compute stream, and `query.finish()` is the join.  If some
+    rank had more non-zero counters than the persistent blocks hold, finish() comes back asking for a repeat, and the
+    closure left in `query._exchange_retry` redoes the exchange with larger blocks (collectively: every rank sees the
+    same gathered counts)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):
         return
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world = dist.get_world_size(group)
     check_reducible(query_ci_min(query), world)
     mode = mode or exchange_mode()
+    ctx = query.db.ctx
     if mode == "dense":
-        ptr, n = query.counts_export()          # joins the library's streams
-        t = device_view_u8(ptr, n, device)
-        allreduce_counts(t, group)
-        torch.cuda.synchronize(device)          # NCCL ran on torch's stream; the library uses its own
-        query.counts_import()
+        ptr, n = query.exchange_dense()
+        with torch.cuda.stream(_comp_stream(ctx, device)):
+            allreduce_counts(device_view_u8(ptr, n, device), group)
         return
-    ptr, n = query.counts_export_sparse()       # joins the library's streams
-    dev = "cuda:%d" % device
-    # ONE all-gather of fixed-capacity buffers: word 0 = this rank's entry count, then its entries, zero padding (count 0:
-    # ignored by the merge).  The capacity adapts: if some rank had more entries than fit, every rank sees that in
-    # the gathered counts and the gather is repeated with room for the largest.
-    global _SPARSE_CAP
-    while True:
-        cap = max(_SPARSE_CAP, 1024)
-        send = torch.zeros(cap + 1, dtype=torch.int64, device=dev)
-        send[0] = n
-        if 0 < n <= cap:
-            send[1:n + 1] = device_view_i64(ptr, n, device)
-        out = torch.empty(world * (cap + 1), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(out, send, group=group)
-        counts = out[::cap + 1].tolist()        # synchronises torch's stream: the gather has landed
-        if max(counts) <= cap:
-            break
-        _SPARSE_CAP = 1 << (int(max(counts)) - 1).bit_length()
-    _SPARSE_CAP = max(1024, 1 << (2 * int(max(counts))).bit_length())     # room for twice what this job needed
-    # (the count words need no masking: read as entries their count field, bits 32.., is zero, and the merge skips those)
-    torch.cuda.synchronize(device)
-    lo, hi = rank * (cap + 1), (rank + 1) * (cap + 1)
-    if lo:
-        query.counts_merge_sparse(out.data_ptr(), lo)                      # every rank before this one ...
-    if hi < out.numel():
-        query.counts_merge_sparse(out.data_ptr() + 8 * hi, out.numel() - hi)   # ... and every rank after it
-    query.sync()                                # `out` may be released after this
+
+    def run(cap=0):
+        st = _get_exchange(ctx, device, group, mode == "p2p", cap)
+        if mode == "p2p":
+            query.exchange_p2p(st["ex"])
+        else:
+            query.exchange_pack(st["ex"])
+            with torch.cuda.stream(_comp_stream(ctx, device)):
+                dist.all_gather_into_tensor(st["recv"], st["send"], group=group)
+            query.exchange_merge(st["ex"])
+
+    query._exchange_retry = lambda need: run(1 << (2 * int(need) - 1).bit_length())
+    run()
 
 
-_SPARSE_CAP = 1 << 18
+def close_exchanges():
+    for cur in _EXCHANGES.values():
+        cur["ex"].close()
+    _EXCHANGES.clear()
 
 
 def query_ci_min(query) -> int:

@@ -1,5 +1,7 @@
-"""Two real GPUs, one process each, NCCL: read-sharded probe + ONE uint8 all-reduce of the counter table, against
-the single-process CPU oracle.  Skipped when fewer than two GPUs are visible."""
+"""Two real GPUs, one process each: read-sharded probe + ONE exchange of the per-k-mer counters -- the NCCL all-gather
+of the non-zero counters, the dense uint8 all-reduce, and the direct NVLink-store form ("p2p"), each without a host
+round trip -- against the single-process CPU oracle.  "tiny" forces blocks too small for the counters, i.e. the
+repeat-with-larger-blocks path.  Skipped when fewer than two GPUs are visible."""
 import os
 import sys
 
@@ -25,6 +27,9 @@ def _worker(rank, world, port, out_dir, mode):
     import synth
     from metalign_b200 import dist as mdist
     from metalign_b200.api import Context, Database
+    if mode.endswith("-tiny"):
+        mode = mode[:-5]
+        os.environ["MLG_EXCHANGE_CAP"] = "64"
     r, w, local = mdist.init_from_env("nccl")
     p = _params()
     keys = synth.sketch_keys(p)
@@ -38,11 +43,22 @@ def _worker(rank, world, port, out_dir, mode):
     res = q.finish()
     np.save(os.path.join(out_dir, "num_%d.npy" % rank), res["num"])
     np.save(os.path.join(out_dir, "I_%d.npy" % rank), q.intersection())
-    q.close(); db.close(); ctx.close()
+    # a second query through the same persistent exchange (epochs / buffer reuse)
+    q2 = db.query()
+    q2.push_packed(bases, nmask, None, b - a, p.read_len)
+    mdist.reduce_query(q2, local, mode=mode)
+    res2 = q2.finish()
+    assert np.array_equal(res2["num"], res["num"])
+    q2.close(); q.close()
+    mdist.close_exchanges()
+    db.close(); ctx.close()
     tdist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["sparse", "dense"])
+MODES = ["sparse", "dense", "p2p", "sparse-tiny", "p2p-tiny"]
+
+
+@pytest.mark.parametrize("mode", MODES)
 def test_two_gpu_read_sharding_matches_oracle(tmp_path, mode):
     import torch
     import torch.multiprocessing as mp
@@ -51,7 +67,7 @@ def test_two_gpu_read_sharding_matches_oracle(tmp_path, mode):
     import synth
     from helpers import oracle_c_run
     world = 2
-    mp.spawn(_worker, args=(world, 29400 + os.getpid() % 500 + (7 if mode == "dense" else 0), str(tmp_path), mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29400 + os.getpid() % 500 + 7 * MODES.index(mode), str(tmp_path), mode), nprocs=world, join=True)
     p = _params()
     keys = synth.sketch_keys(p)
     bases, nmask = synth.reads_packed(p, 0, NREADS)

@@ -657,6 +657,45 @@ def test_full_size_properties(ctx):
     db.close()
 
 
+def test_headline_config_against_oracle(ctx):
+    """BASELINE.json configs[1] at FULL size -- 2e5 genomes x 1000 slots, 10 M x 150 bp reads, the workload bench.py
+    quotes its headline on -- with the complete per-genome tables and the intersection compared with the C oracle
+    (about a minute of host time: the oracle's database build dominates)."""
+    import torch
+    from oracle.oracle_c import OracleDB, OracleQuery, lib as olib
+    olib().orc_set_threads(len(os.sched_getaffinity(0)))
+    G, n, nreads, L = 200_000, 1000, 10_000_000, 150
+    p = synth.params(G=G, n=n, seed=20200529, n_present=500, read_len=L)
+    d_keys = torch.empty(G * n * 2, dtype=torch.int64, device="cuda")
+    assert synth.cuda_lib().syn_cuda_gen_sketch_keys(C.byref(p), d_keys.data_ptr(), None) == 0
+    keys = d_keys.cpu().numpy().view(np.uint64).reshape(-1, 2)
+    db = Database.from_device_keys(ctx, d_keys.data_ptr(), G, n, 60, KS)
+    del d_keys
+    nbb, nmb = synth.packed_sizes(nreads, L)
+    d_b = torch.empty(nbb, dtype=torch.uint8, device="cuda")
+    d_m = torch.empty(nmb, dtype=torch.uint8, device="cuda")
+    assert synth.cuda_lib().syn_cuda_gen_reads_packed(C.byref(p), 0, nreads, d_b.data_ptr(), d_m.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    q = db.query()
+    q.push_packed_ptr(d_b.data_ptr(), d_m.data_ptr(), None, nreads, L, device=True)
+    res = q.finish()
+    I_gpu = q.intersection()
+    q.close()
+    db.close()
+    bases, nmask = d_b.cpu().numpy(), d_m.cpu().numpy()
+    del d_b, d_m
+    torch.cuda.empty_cache()
+    odb = OracleDB(keys, G, n, 60, KS)
+    oq = OracleQuery(odb)
+    oq.push_packed(bases, nmask, None, nreads, L)
+    ref = oq.finish()
+    I_ref = oq.intersection()
+    oq.close()
+    odb.close()
+    assert ref["n_intersect"] > 10000 and (ref["num"][:, -1] > 0).sum() > 100
+    _check(res, I_gpu, ref, I_ref, "configs[1] full size")
+
+
 def test_superkmer_overfull_pairs(ctx, workload, monkeypatch):
     """mean load 7.5 per 8-slot half: most halves are full or overflowed, so most windows go through the queue and the
     exact compare (a full half is treated as overflowed; there is no flag bit in this layout)"""
