@@ -38,9 +38,11 @@ int mlgi_open(const char* path, int input_type, int threads, mlgi_reader** out);
  *   bases      cap_bases_bytes >= max_bases / 4 + 32; the used part (rounded up to 16 bytes) is written in full
  *   nruns      cap_runs (start, length) pairs of uint32; max_bases must be < 2^32
  *   off        max_reads + 1 entries
- * Returns 1 with *n_reads > 0, 0 at end of input (nothing written), < 0 on error. */
+ * Returns 1 with *n_reads > 0, 0 at end of input (nothing written), < 0 on error; 2 = like 1, but the batch has more
+ * than cap_runs N runs: *n_runs says how many, nruns was not written, and mlgi_spilled_runs() hands them over. */
 int mlgi_next(mlgi_reader* r, uint8_t* bases, uint64_t cap_bases_bytes, uint32_t* nruns, uint64_t cap_runs, uint64_t* off,
               uint64_t max_reads, uint64_t max_bases, uint64_t* n_reads, uint64_t* n_runs);
+int mlgi_spilled_runs(mlgi_reader* r, uint32_t* nruns, uint64_t cap_runs);
 /* totals so far: reads and bases delivered, compressed/raw bytes consumed from the file */
 int mlgi_stats(mlgi_reader* r, uint64_t* reads, uint64_t* bases, uint64_t* text_bytes);
 void mlgi_close(mlgi_reader* r);

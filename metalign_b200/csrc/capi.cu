@@ -298,7 +298,9 @@ MLG_API int mlg_db_from_keys(mlg_ctx* ctx, const uint64_t* keys, uint32_t G, uin
     MLG_TRY(ensure_device(ctx));
     size_t total = (size_t)G * n;
     DevBuf<key128> d; MLG_TRY(d.alloc(total));
-    CUDA_TRY(cudaMemcpy(d.p, keys, total * sizeof(key128), cudaMemcpyHostToDevice));
+    // on the stream the build runs on, then joined: the build never sees a copy still in flight
+    CUDA_TRY(cudaMemcpyAsync(d.p, keys, total * sizeof(key128), cudaMemcpyHostToDevice, ctx->s_comp));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
     return mlg_db_build_device(ctx, d.p, G, n, K, ks, nk, out);
 }
 MLG_API int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk,
@@ -309,8 +311,8 @@ MLG_API int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers, uint32_t G, uint3
     size_t total = (size_t)G * n;
     DevBuf<unsigned char> t; MLG_TRY(t.alloc(total * K));
     DevBuf<key128> d; MLG_TRY(d.alloc(total));
-    CUDA_TRY(cudaMemcpy(t.p, kmers, total * K, cudaMemcpyHostToDevice));
-    MLG_TRY(launch_ascii_to_keys(t.p, total, K, d.p, ctx->s_comp));
+    CUDA_TRY(cudaMemcpyAsync(t.p, kmers, total * K, cudaMemcpyHostToDevice, ctx->s_comp));
+    MLG_TRY(launch_ascii_to_keys(t.p, total, K, d.p, ctx->s_comp));     // joins the stream before it returns
     t.release();
     return mlg_db_build_device(ctx, d.p, G, n, K, ks, nk, out);
 }

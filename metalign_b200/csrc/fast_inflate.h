@@ -146,6 +146,8 @@ struct Inflater {
             const unsigned sym = e >> 16;
             if (sym < 16) { lens[n++] = (uint8_t)sym; continue; }
             unsigned rep, val = 0;
+            const unsigned xb = sym == 16 ? 2u : sym == 17 ? 3u : 7u;
+            if (bitcnt < xb) return false;                       // truncated inside the repeat count
             if (sym == 16) { if (n == 0) return false; val = lens[n - 1]; rep = 3 + bits(2); }
             else if (sym == 17) rep = 3 + bits(3);
             else rep = 11 + bits(7);
@@ -227,6 +229,7 @@ struct Inflater {
                     refill();
                     uint32_t e = ll[bitbuf & ((1u << LL_BITS) - 1u)];
                     if ((e & K_MASK) == K_LINK) {
+                        if (bitcnt < LL_BITS) { error = "truncated deflate stream"; return -1; }   // bitcnt is unsigned: never let it wrap
                         bitbuf >>= LL_BITS; bitcnt -= LL_BITS;
                         e = ll[(e >> 16) + (uint32_t)(bitbuf & ((1u << ((e >> 4) & 15u)) - 1u))];
                     }
@@ -251,6 +254,7 @@ struct Inflater {
                     if (bitcnt < 32) refill();
                     uint32_t d = dd[bitbuf & ((1u << D_BITS) - 1u)];
                     if ((d & K_MASK) == K_LINK) {
+                        if (bitcnt < D_BITS) { error = "truncated deflate stream"; return -1; }
                         bitbuf >>= D_BITS; bitcnt -= D_BITS;
                         d = dd[(d >> 16) + (uint32_t)(bitbuf & ((1u << ((d >> 4) & 15u)) - 1u))];
                     }

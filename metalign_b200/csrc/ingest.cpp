@@ -190,6 +190,7 @@ struct mlgi_reader {
     BoundedQueue<RawBlock> q_raw{4};
     BoundedQueue<Lines> q_lines{4};
     std::thread t_read, t_scan;
+    std::vector<uint32_t> spill;        // N runs of the last batch when they did not fit the caller's buffer
     std::string io_error;               // set by the reader thread before it finishes the queue
     std::mutex err_mu;
     // consumer state
@@ -790,19 +791,33 @@ MLGI_API int mlgi_next(mlgi_reader* r, uint8_t* bases, uint64_t cap_bases_bytes,
     }
     r->t_pack += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count();
     // N runs of the workers, in stream order; runs that touch across a worker boundary are merged
-    uint64_t nr = 0;
+    // A batch with more runs than the caller's buffer holds (very low-quality reads: KMC in the reference just skips N,
+    // select_db.py:50) is still delivered: its runs stay with the reader and are fetched with mlgi_spilled_runs().
+    uint64_t nr = 0, upper = 0;
+    for (int t = 0; t < T; ++t) upper += jobs[(size_t)t].runs.size() / 2;
+    const bool spill = upper > cap_runs || !nruns;
+    if (spill) r->spill.assign((size_t)(2 * upper + 2), 0u);
+    uint32_t* dst = spill ? r->spill.data() : nruns;
     for (int t = 0; t < T; ++t) {
         const std::vector<uint32_t>& v = jobs[(size_t)t].runs;
         for (size_t i = 0; i + 1 < v.size(); i += 2) {
-            if (nr && (uint64_t)nruns[2 * (nr - 1)] + nruns[2 * (nr - 1) + 1] == v[i]) { nruns[2 * (nr - 1) + 1] += v[i + 1]; continue; }
-            if (nr >= cap_runs || !nruns) { set_error("more than %llu N runs in one batch", (unsigned long long)cap_runs); return -2; }
-            nruns[2 * nr] = v[i]; nruns[2 * nr + 1] = v[i + 1];
+            if (nr && (uint64_t)dst[2 * (nr - 1)] + dst[2 * (nr - 1) + 1] == v[i]) { dst[2 * (nr - 1) + 1] += v[i + 1]; continue; }
+            dst[2 * nr] = v[i]; dst[2 * nr + 1] = v[i + 1];
             ++nr;
         }
     }
+    if (spill) r->spill.resize((size_t)(2 * nr));
     *n_reads = n; *n_runs = nr;
     r->tot_reads += n; r->tot_bases += nb;
-    return 1;
+    return spill && nr ? 2 : 1;
+}
+
+MLGI_API int mlgi_spilled_runs(mlgi_reader* r, uint32_t* nruns, uint64_t cap_runs) {
+    if (!r || !nruns) { set_error("null argument"); return -2; }
+    if (cap_runs * 2 < r->spill.size()) { set_error("buffer holds %llu runs, %llu are waiting", (unsigned long long)cap_runs, (unsigned long long)(r->spill.size() / 2)); return -2; }
+    if (!r->spill.empty()) memcpy(nruns, r->spill.data(), r->spill.size() * sizeof(uint32_t));
+    r->spill.clear();
+    return 0;
 }
 
 MLGI_API int mlgi_stats(mlgi_reader* r, uint64_t* reads, uint64_t* bases, uint64_t* text_bytes) {

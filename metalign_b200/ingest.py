@@ -41,6 +41,7 @@ def ingest_lib():
         L.mlgi_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.mlgi_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.mlgi_spilled_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.mlgi_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
         L.mlgi_close.argtypes = [C.c_void_p]
         L.mlgi_close.restype = None
@@ -86,6 +87,11 @@ class PackedBatches:
             raise IOError(self.L.mlgi_last_error().decode())
         if rc == 0:
             raise StopIteration
+        if rc == 2:          # more N runs than the (pinned) buffer holds: the reader kept them
+            big = np.empty(2 * nn.value, dtype=np.uint32)
+            if self.L.mlgi_spilled_runs(self.h, big.ctypes.data, nn.value) != 0:
+                raise IOError(self.L.mlgi_last_error().decode())
+            return b, big.reshape(-1, 2), o[:nr.value + 1], nr.value
         return b, r[:2 * nn.value].reshape(-1, 2), o[:nr.value + 1], nr.value
 
     def stats(self):

@@ -72,8 +72,11 @@ def main(argv=None):
         try:
             import map_and_profile as mapper      # the reference's scripts/ directory on PYTHONPATH
         except ImportError:
-            print("map_and_profile (reference alignment/profiling stage) is not importable; "
-                  "selection outputs are in " + args.temp_dir)
+            # the reference always goes on to mapper.map_main(args) (metalign.py:85): a run that cannot must not look
+            # like one that did -- no abundances file was written
+            sys.exit("Error: map_and_profile (the reference's alignment/profiling stage, scripts/ of nlapier2/Metalign) is "
+                     "not importable, so %s was not written; selection outputs are in %s (use --select_only to stop "
+                     "after database selection)" % (args.output, args.temp_dir))
     if mapper is not None:
         mapper.map_main(args)
         if not args.keep_temp_files:

@@ -74,16 +74,28 @@ def run_kmc_steps(args):
     reads that belong to the database sketch; the live query is parked on args for run_cmash_and_cutoff."""
     from . import ingest
     from .api import Context, Database, pinned_array
-    ctx = Context(args.device)
-    db = Database.load(ctx, args.db_file)
-    query = db.query(ci_min=2, gate=args.gate, count_empty_in_den=True)     # -ci2 (select_db.py:50)
-    # the native reader (its worker count = --threads, KMC's -t in the reference) fills one pinned buffer set while
-    # the previous batch is still on its way to the GPU
-    reader = ingest.PackedBatches(args.reads, args.input_type, threads=max(1, int(getattr(args, "threads", 4) or 4)),
-                                  alloc=pinned_array)
-    for bases, nruns, off, n_reads in reader:
-        query.push_packed_nruns(bases, nruns if len(nruns) else None, off, n_reads)
-    query.sync()
+    ctx = db = query = reader = None
+    try:
+        ctx = Context(args.device)
+        db = Database.load(ctx, args.db_file)
+        query = db.query(ci_min=2, gate=args.gate, count_empty_in_den=True)     # -ci2 (select_db.py:50)
+        # the native reader (its worker count = --threads, KMC's -t in the reference) fills one pinned buffer set while
+        # the previous batch is still on its way to the GPU
+        reader = ingest.PackedBatches(args.reads, args.input_type, threads=max(1, int(getattr(args, "threads", 4) or 4)),
+                                      alloc=pinned_array)
+        for bases, nruns, off, n_reads in reader:
+            query.push_packed_nruns(bases, nruns if len(nruns) else None, off, n_reads)
+        query.sync()
+    except BaseException:
+        # a corrupt reads file, a failed push: give the device and pinned memory back before the error travels on
+        # (a caller looping over samples would otherwise accumulate them)
+        for obj in (reader, query, db, ctx):
+            if obj is not None:
+                try:
+                    obj.close()
+                except Exception:  # noqa: BLE001
+                    pass
+        raise
     reader.close()
     args._mlg = (ctx, db, query)
 

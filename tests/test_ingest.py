@@ -187,6 +187,22 @@ def test_limits_and_errors(tmp_path):
     assert len(got) == 50 and nb == 5
 
 
+def test_more_n_runs_than_the_buffer_holds(tmp_path):
+    """low-quality reads: more separate N runs in a batch than the caller's run buffer -- KMC in the reference just skips
+    N (scripts/select_db.py:50), so the batch must still come through (the reader keeps the runs and hands them over)"""
+    p = tmp_path / "n.fq"
+    read = "ACGNTTNACNGG" * 12                       # 36 N runs per 144-base read
+    _write(p, "".join("@r%d\n%s\n+\n%s\n" % (i, read, "I" * len(read)) for i in range(400)))
+    rd = ingest.PackedBatches(str(p), "fastq", reads_per_batch=1000, bases_per_batch=100000, max_runs=64)
+    bases, runs, off, n = next(rd)
+    assert n == 400 and runs.shape == (400 * 36, 2) and (runs[:, 1] == 1).all()
+    want = np.array([i for i, c in enumerate(read * 400) if c == "N"], dtype=np.uint32)
+    assert np.array_equal(runs[:, 0], want)
+    with pytest.raises(StopIteration):
+        next(rd)
+    rd.close()
+
+
 def test_large_parallel_pack_matches_codec(tmp_path):
     """~6 Mbases through 8 workers: the packed stream and the run list equal codec.pack_reads exactly"""
     rng = np.random.default_rng(5)
@@ -276,3 +292,38 @@ def test_fast_inflate_against_zlib():
     rc, _ = inflate(bytes(blob[:len(blob) // 2]), len(data), 1 << 16)
     assert rc != 0
     assert cases > 200
+
+
+def test_fast_inflate_truncated_at_every_byte():
+    """A gzip stream cut at ANY byte must fail cleanly -- never run past the output cap, never hang.  The data are chosen
+    for long codes: Z_HUFFMAN_ONLY over a skewed alphabet gives literal codes beyond the 11-bit primary table, and a
+    level-9 stream over far-apart repeats gives distance codes beyond the 8-bit one (the second-level paths, where the
+    unsigned bit counter once wrapped on a truncated tail)."""
+    import ctypes as C
+    import zlib
+    L = ingest.ingest_lib()
+    L.mlgi_test_inflate.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+    rng = random.Random(77)
+
+    def gz(data, level, strategy):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+        body = co.compress(data) + co.flush()
+        return (b"\x1f\x8b\x08\0\0\0\0\0\0\xff" + body + (zlib.crc32(data) & 0xFFFFFFFF).to_bytes(4, "little")
+                + (len(data) & 0xFFFFFFFF).to_bytes(4, "little"))
+
+    # skewed alphabet: byte value b with probability ~ 2^-(b/8)
+    skew = bytes(min(255, int(rng.expovariate(0.09))) for _ in range(40000))
+    chunks = [bytes(rng.randrange(256) for _ in range(rng.randint(20, 200))) for _ in range(300)]
+    far = b"".join(rng.choice(chunks) for _ in range(1500))[:90000]
+    total = 0
+    for data, level, strategy in ((skew, 6, zlib.Z_HUFFMAN_ONLY), (far, 9, zlib.Z_DEFAULT_STRATEGY)):
+        blob = gz(data, level, strategy)
+        out = np.empty(len(data) + 3 * 4096, dtype=np.uint8)
+        n = C.c_uint64()
+        assert L.mlgi_test_inflate(blob, len(blob), out.ctypes.data, out.size, 4096, C.byref(n)) == 0
+        assert out[:n.value].tobytes() == data
+        for cut in range(1, len(blob)):          # (an empty file is a valid gzip stream of zero members)
+            rc = L.mlgi_test_inflate(blob[:cut], cut, out.ctypes.data, out.size, 4096, C.byref(n))
+            assert rc in (-1, -3), (level, cut, rc)
+            total += 1
+    assert total > 50000
