@@ -752,7 +752,7 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     if (db->hoff.p) {
         // replay the precomputed hit lists; touched[] is dead by now and serves as the list of k-mers without one
         MLG_TRY(launch_apply_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p,
-                                  db->hoff.p, db->hits.p, q->touched.p, q->d_scalar.p + 2, st));
+                                  db->hoff.p, db->hbase.p, db->hits.p, q->touched.p, q->d_scalar.p + 2, st));
         q->st.gpu_launches += 1;
     } else {
         MLG_TRY(launch_expand_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p, st));

@@ -476,39 +476,47 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             }
         }
     }
-    // 6. hit lists: what a present k-mer of D contributes to the per-genome table is a static function of the
-    //    database, so it is expanded once here (same code as the on-the-fly kernel) and replayed per query.
-    //    MLG_PRECOMPUTE_HITS=0 skips this; k-mers that do not fit (buffer or list too small) stay on the fly.
+    // 6. hit records: what a present k-mer of D contributes to the per-genome table is a static function of the
+    //    database, so it is expanded once here (same code as the on-the-fly kernel) and replayed per query.  Two passes:
+    //    tally (sizes; the common one-slot records are complete after it) -> offsets -> fill.  Afterwards P, its bucket
+    //    index and the class representatives -- 60 % of the database's footprint -- have no reader left and are released.
+    //    MLG_PRECOMPUTE_HITS=0 skips all this (every query expands on the fly); MLG_HIT_CAP_WORDS=n drops the records
+    //    beyond word n (their k-mers are expanded on the fly: the mixed path, for tests); MLG_KEEP_P=1 keeps P regardless.
     {
         const char* pe = getenv("MLG_PRECOMPUTE_HITS");
         if (nd && (!pe || atoi(pe) != 0)) {
+            unsigned long long drop_from = ~0ull;
+            if (const char* s = getenv("MLG_HIT_CAP_WORDS")) { unsigned long long x = strtoull(s, nullptr, 10); if (x >= 16) drop_from = x; }
+            const unsigned long long groups = ((unsigned long long)nd + (1ull << MLG_HGROUP_SHIFT) - 1) >> MLG_HGROUP_SHIFT;
+            DevBuf<uint32_t> summary;
+            MLG_TRY(summary.alloc(2ull * nd)); MLG_TRY(db->hoff.alloc(nd)); MLG_TRY(db->hbase.alloc(groups + 1));
+            MLG_TRY(launch_tally_hits(v, summary.p, st));
+            CUDA_TRY(cudaMemsetAsync(db->hbase.p, 0, (groups + 1) * 8, st));
+            MLG_TRY(launch_hit_group_sums(summary.p, nd, db->hbase.p, st));
+            {
+                void* tmp = nullptr; size_t tb = 0;
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tb, db->hbase.p, db->hbase.p, (int)(groups + 1), st));
+                CUDA_TRY(cudaMalloc(&tmp, tb ? tb : 1));
+                cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, db->hbase.p, db->hbase.p, (int)(groups + 1), st);
+                cudaStreamSynchronize(st); cudaFree(tmp);
+                if (e != cudaSuccess) { mlg_set_error("DeviceScan failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
+            }
+            MLG_TRY(launch_hit_offsets(summary.p, nd, db->hoff.p, st));
+            unsigned long long total_words = 0;
+            CUDA_TRY(cudaMemcpyAsync(&total_words, db->hbase.p + groups, 8, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            size_t free_b = 0, total_b = 0;
-            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-            unsigned long long cap = (unsigned long long)nd * 12ull;                 // words; ~5-7 are used per k-mer
-            const unsigned long long lim = (unsigned long long)(free_b * 0.4) / 4ull;
-            if (cap > lim) cap = lim;
-            if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
-            if (const char* s = getenv("MLG_HIT_CAP_WORDS")) { unsigned long long x = strtoull(s, nullptr, 10); if (x >= 16 && x < cap) cap = x; }   // tests: force the fallback
-            if (cap >= 16 && db->hoff.alloc(nd) == MLG_OK) {
-                DevBuf<uint32_t> big;
-                if (big.alloc(cap) == MLG_OK) {
-                    MLG_TRY(launch_collect_hits(v, db->hoff.p, big.p, cap, d_cnt.p, st));
-                    unsigned long long used = 0;
-                    CUDA_TRY(cudaMemcpyAsync(&used, d_cnt.p, 8, cudaMemcpyDeviceToHost, st));
-                    CUDA_TRY(cudaStreamSynchronize(st));
-                    CUDA_TRY(cudaGetLastError());
-                    if (used > cap) used = cap;
-                    if (used == 0) used = 1;
-                    MLG_TRY(db->hits.alloc(used));
-                    CUDA_TRY(cudaMemcpyAsync(db->hits.p, big.p, used * 4ull, cudaMemcpyDeviceToDevice, st));
-                    CUDA_TRY(cudaStreamSynchronize(st));
-                    db->hit_words = used;
-                } else {
-                    db->hoff.release();
-                }
-            } else {
-                db->hoff.release();
+            CUDA_TRY(cudaGetLastError());
+            const unsigned long long keep_words = total_words < drop_from ? total_words : drop_from;
+            MLG_TRY(db->hits.alloc(keep_words + 2 + MLG_MAX_KS));
+            MLG_TRY(launch_fill_hits(v, summary.p, db->hoff.p, db->hbase.p, db->hits.p, drop_from, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaGetLastError());
+            db->hit_words = keep_words;
+            const char* kp = getenv("MLG_KEEP_P");
+            if (drop_from == ~0ull && !(kp && atoi(kp) != 0)) {
+                db->P_key.release(); db->P_slot.release(); db->pidx.release(); db->rep.release();
+                v.P_key = nullptr; v.P_slot = nullptr; v.pidx = nullptr; v.rep = nullptr;
+                db->p_dropped = true;
             }
         }
     }

@@ -107,8 +107,10 @@ struct mlg_db {
     DevBuf<unsigned long long> alias_z;
     DevBuf<uint32_t> alias_i, alias_bloom;
     DevBuf<key128> D_key;
-    DevBuf<uint32_t> hoff, hits;     // precomputed hit lists per k-mer of D (hoff.p == nullptr: not built)
+    DevBuf<uint32_t> hoff, hits;     // precomputed hit records per k-mer of D (hoff.p == nullptr: not built)
+    DevBuf<unsigned long long> hbase; // 64-bit word offset of every group of 2^MLG_HGROUP_SHIFT k-mers' records
     unsigned long long hit_words = 0;
+    bool p_dropped = false;          // P / pidx / rep were released after the hit records were built
     DevBuf<long long> den_real;      // G*nk
     DevBuf<unsigned char> has_empty; // G
     double build_ms = 0;
@@ -161,9 +163,15 @@ int launch_expand_hits(const DbView& db, const uint32_t* present, const unsigned
 #define HOFF_NONE 0xFFFFFFFFu
 int launch_apply_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,
                       uint32_t* hitbits, unsigned long long words_per_k, unsigned long long* num, const uint32_t* hoff,
-                      const uint32_t* hits, uint32_t* fallback, unsigned long long* d_n_fallback, cudaStream_t st);
-int launch_collect_hits(const DbView& db, uint32_t* hoff, uint32_t* hits, unsigned long long cap_words, unsigned long long* d_cursor,
-                        cudaStream_t st);
+                      const unsigned long long* hbase, const uint32_t* hits, uint32_t* fallback, unsigned long long* d_n_fallback,
+                      cudaStream_t st);
+// hit-record build (db.cu): tally -> sizes -> offsets (32-bit, relative to a 64-bit base per MLG_HGROUP k-mers) -> fill
+#define MLG_HGROUP_SHIFT 16
+int launch_tally_hits(const DbView& db, uint32_t* summary, cudaStream_t st);
+int launch_hit_group_sums(const uint32_t* summary, uint32_t nd, unsigned long long* gsum, cudaStream_t st);
+int launch_hit_offsets(const uint32_t* summary, uint32_t nd, uint32_t* hoff, cudaStream_t st);
+int launch_fill_hits(const DbView& db, const uint32_t* summary, uint32_t* hoff, const unsigned long long* hbase,
+                     uint32_t* hits, unsigned long long drop_from, cudaStream_t st);
 int launch_scatter_nruns(const uint32_t* d_runs, unsigned long long n_runs, unsigned long long nbases, unsigned char* nmask,
                          cudaStream_t st);
 int launch_finalize(const unsigned long long* num, const long long* den_real, const unsigned char* has_empty, uint32_t G,

@@ -38,6 +38,19 @@ struct MzShared {
 };
 constexpr uint32_t MZ_ROW = RT * 4;           // byte stride between rows of wm[] / seq[]
 
+// The L2::64B qualifier matters: without a prefetch-size qualifier a miss on this part moves 128 bytes from HBM for
+// every random 4-byte access (3.8 sectors per request, whatever the load's width or cache policy); with it, 64
+// (profiles/r3a_ubench_gather.md).  MZ_L2_FETCH=0 builds the kernel without it (A/B measurements).
+#ifndef MZ_L2_FETCH
+#define MZ_L2_FETCH 64
+#endif
+#if MZ_L2_FETCH == 64
+#define MZ_L2Q ".L2::64B"
+#elif MZ_L2_FETCH == 128
+#define MZ_L2Q ".L2::128B"
+#else
+#define MZ_L2Q ""
+#endif
 __device__ __forceinline__ uint32_t ldg_bitmap_if(bool p, const uint32_t* ptr) {
     uint32_t r;
     asm volatile(
@@ -45,9 +58,20 @@ __device__ __forceinline__ uint32_t ldg_bitmap_if(bool p, const uint32_t* ptr) {
         ".reg .pred q;\n"
         "setp.ne.u32 q, %1, 0;\n"
         "mov.u32 %0, 0;\n"
-        "@q ld.global.nc.L1::no_allocate.b32 %0, [%2];\n"
+        "@q ld.global.nc.L1::no_allocate" MZ_L2Q ".b32 %0, [%2];\n"
         "}\n" : "=r"(r) : "r"((uint32_t)p), "l"(ptr));
     return r;
+}
+// the exact path's random reads of database arrays, same fetch size
+__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* ptr) {
+    uint32_t r;
+    asm volatile("ld.global.nc" MZ_L2Q ".b32 %0, [%1];" : "=r"(r) : "l"(ptr));
+    return r;
+}
+__device__ __forceinline__ key128 ldg_key(const key128* ptr) {
+    key128 k;
+    asm volatile("ld.global.nc" MZ_L2Q ".v2.u64 {%0, %1}, [%2];" : "=l"(k.hi), "=l"(k.lo) : "l"(ptr));
+    return k;
 }
 // (order << 6 | position) of the 32-mer at position 16j+i of the current block: first half = bases [16j+i, +16) of
 // loc[], reverse complement of the second half = the 16-mer at 16(j+1)+i seen through rcl[] (see sk_mmer)
@@ -91,11 +115,11 @@ __device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long
     const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
     if (untested) {               // a run beyond the fourth of its block: its level-1 word was not fetched ahead
         const unsigned long long idx = mz_bit_index(((unsigned long long)zhi << 32) | zlo, db.fbits);
-        const uint32_t f = db.F[idx >> 5];
+        const uint32_t f = ldg_u32(db.F + (idx >> 5));
         if (!((f >> (zlo & 31u)) & (f >> mz_bit2(zhi)) & 1u)) return;
     }
     const uint32_t bucket = zhi >> (32u - db.bbits);
-    w.s = db.bstart[bucket]; w.e = db.bstart[bucket + 1];
+    w.s = ldg_u32(db.bstart + bucket); w.e = ldg_u32(db.bstart + bucket + 1);
     // K-mers filed under a second identity (order ties) are rare: a 2^16-bit array says whether to look at all
     if (db.n_alias && ((db.alias_bloom[(zlo & 0xFFFFu) >> 5] >> (zlo & 31u)) & 1u)) {
         const unsigned long long z = ((unsigned long long)zhi << 32) | zlo;
@@ -109,15 +133,15 @@ __device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long
     F = key_shr(F, 128 - 2 * SK_K);                                 // the 60-mer, bottom-aligned
     const key128 G = key_rc(F, SK_K);
     w.cn = key_lt(G, F) ? G : F;
-    if (w.s < w.e) w.d0 = db.D_key[w.s];
-    if (w.s + 1u < w.e) w.d1 = db.D_key[w.s + 1u];
+    if (w.s < w.e) w.d0 = ldg_key(db.D_key + w.s);
+    if (w.s + 1u < w.e) w.d1 = ldg_key(db.D_key + w.s + 1u);
 }
 // stage 2: compare with the database k-mers filed under the identity, count a match
 __device__ __forceinline__ void mz_window_end(const MzWin& w, const DbView& db, const CountSink& cs) {
     if (w.s < w.e && w.d0.hi == w.cn.hi && w.d0.lo == w.cn.lo) { bump_counter(cs, w.s); return; }
     if (w.s + 1u < w.e && w.d1.hi == w.cn.hi && w.d1.lo == w.cn.lo) { bump_counter(cs, w.s + 1u); return; }
     for (uint32_t i = w.s + 2u; i < w.e; ++i) {
-        const key128 d = db.D_key[i];
+        const key128 d = ldg_key(db.D_key + i);
         if (d.hi == w.cn.hi && d.lo == w.cn.lo) { bump_counter(cs, i); return; }
     }
     for (uint32_t j = w.j0; j < w.j1; ++j) {

@@ -53,9 +53,32 @@ struct HitSink {
 };
 // (b) database build: the hits of a database k-mer are a static function of the database, so they are expanded
 //     ONCE for every k-mer of D (gate = none, each hit flagged with whether the exact gate would also let it
-//     through) and kept as a list per k-mer; a query then only replays the lists of the k-mers it found.
-constexpr unsigned HCAP = 96;          // hits collected per k-mer before the list is given up (-> on-the-fly expansion)
+//     through) and kept as a record per k-mer; a query then only replays the records of the k-mers it found.
+//     Record formats (word 0 = header; a hit word = representative slot | HIT_EXACT):
+//       short      (header & 15) != 15: one 4-bit count per k (<= 14 each), then the hits grouped by k
+//       same slot  header = 0xF | 1 << 4 | present-k mask << 8 | exact-k mask << 16, word 1 = the slot every hit names
+//                  (the usual case: a k-mer of one genome whose prefixes are their own class representatives)
+//       long       header = 0xF | 2 << 4, words 1..nk = count per k, then the hits grouped by k (k-mers shared by many genomes)
+constexpr unsigned HCAP = 112;         // hits a short record can hold: 8 k values x 14
 constexpr uint32_t HIT_EXACT = 0x80000000u;
+constexpr uint32_t HREC_ESC = 15u, HREC_SAME = 1u, HREC_LONG = 2u;
+constexpr unsigned HGROUP_SHIFT = MLG_HGROUP_SHIFT;  // record offsets are 32-bit words relative to a 64-bit base per 2^16 k-mers
+// pass-1 summary word of a k-mer -> size of its record in words
+__device__ __forceinline__ uint32_t hrec_size(uint32_t su) { return (su >> 30) == 1u ? 2u : (su & 0x3FFFFFFFu); }
+// pass-1 sink: per-k counts, OR of the exact flags per k, smallest / largest slot named (all per warp, shared memory)
+struct TallySink {
+    uint32_t* cnt;                // [MLG_MAX_KS]
+    uint32_t* ex;                 // bit k: some hit at k passes the exact gate
+    uint32_t* rmin; uint32_t* rmax;
+    __device__ __forceinline__ void mark(const DbView& db, uint32_t ki, uint32_t e, bool also_under_exact_gate) const {
+        const unsigned long long total = (unsigned long long)db.G * db.n;
+        const uint32_t r = db.rep[(unsigned long long)ki * total + db.P_slot[e]];
+        atomicAdd(&cnt[ki], 1u);
+        if (also_under_exact_gate) atomicOr(ex, 1u << ki);
+        atomicMin(rmin, r); atomicMax(rmax, r);
+    }
+};
+// pass-2 sinks: a short record is collected in shared memory, a long one is scattered straight into its place
 struct CollectSink {
     uint32_t* val;                // [HCAP] per warp, shared memory: representative slot | HIT_EXACT
     unsigned char* kis;           // [HCAP]
@@ -65,6 +88,15 @@ struct CollectSink {
         const uint32_t r = db.rep[(unsigned long long)ki * total + db.P_slot[e]];
         const unsigned i = atomicAdd(n, 1u);
         if (i < HCAP) { val[i] = r | (also_under_exact_gate ? HIT_EXACT : 0u); kis[i] = (unsigned char)ki; }
+    }
+};
+struct ScatterSink {
+    uint32_t* dst;                // first hit word of the record
+    uint32_t* cursor;             // [MLG_MAX_KS] per warp, shared memory: next free position per k
+    __device__ __forceinline__ void mark(const DbView& db, uint32_t ki, uint32_t e, bool also_under_exact_gate) const {
+        const unsigned long long total = (unsigned long long)db.G * db.n;
+        const uint32_t r = db.rep[(unsigned long long)ki * total + db.P_slot[e]];
+        dst[atomicAdd(&cursor[ki], 1u)] = r | (also_under_exact_gate ? HIT_EXACT : 0u);
     }
 };
 
@@ -123,67 +155,156 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_expand_hits(DbView db, c
         expand_one(db, db.D_key[present[xi]], gate_none, hs, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
 }
 
-// database build: hit list of every k-mer of D.  Record layout in hits[]: header word (count per k, 4 bits each),
-// then the hits grouped by k, each = representative slot | HIT_EXACT.  hoff[e] = word offset of the record, or
-// HOFF_NONE when the k-mer has too many hits / the buffer is full (such k-mers are expanded on the fly).
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_collect_hits(DbView db, uint32_t* hoff, uint32_t* hits,
-                                                                     unsigned long long cap_words, unsigned long long* cursor) {
+// database build, pass 1: tally the hits of every k-mer of D.  summary[2e] = kind << 30 | the record's size in words
+// (kind 0 short, 2 long), or for kind 1 (same slot: always 2 words) 1 << 30 | the record's finished header with
+// summary[2e + 1] = its slot -- such a record is complete after this pass.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_tally_hits(DbView db, uint32_t* summary) {
+    __shared__ uint32_t s_flo[WARPS_PER_CTA][MAX_OFF], s_fcnt[WARPS_PER_CTA][MAX_OFF];
+    __shared__ uint32_t s_rlo[WARPS_PER_CTA][MAX_OFF], s_rcnt[WARPS_PER_CTA][MAX_OFF];
+    __shared__ uint32_t s_cnt[WARPS_PER_CTA][MLG_MAX_KS], s_ex[WARPS_PER_CTA], s_min[WARPS_PER_CTA], s_max[WARPS_PER_CTA];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS_PER_CTA + warp; e < db.nd;
+         e += (unsigned long long)gridDim.x * WARPS_PER_CTA) {
+        if (lane < MLG_MAX_KS) s_cnt[warp][lane] = 0;
+        if (lane == 0) { s_ex[warp] = 0; s_min[warp] = 0xFFFFFFFFu; s_max[warp] = 0; }
+        __syncwarp();
+        TallySink sink{s_cnt[warp], &s_ex[warp], &s_min[warp], &s_max[warp]};
+        expand_one(db, db.D_key[e], 1, sink, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
+        if (lane == 0) {
+            uint32_t n = 0, present = 0; bool fits = true;
+            for (unsigned k = 0; k < MLG_MAX_KS; ++k) { const uint32_t c = s_cnt[warp][k]; n += c; if (c) present |= 1u << k; if (c > 14u) fits = false; }
+            static_assert(MLG_MAX_KS <= 8, "the same-slot header has 8 bits per mask");
+            if (n && s_min[warp] == s_max[warp]) {
+                summary[2 * e] = (HREC_SAME << 30) | HREC_ESC | (HREC_SAME << 4) | (present << 8) | (s_ex[warp] << 16);
+                summary[2 * e + 1] = s_min[warp];
+            } else {
+                summary[2 * e] = fits ? (1u + n) : ((HREC_LONG << 30) | (1u + db.nk + n));
+                summary[2 * e + 1] = 0;
+            }
+        }
+        __syncwarp();
+    }
+}
+// record sizes -> offsets: sum per group of 2^HGROUP_SHIFT k-mers (one CTA per group), then -- after the group sums have
+// been scanned into 64-bit bases -- the exclusive scan inside every group
+__global__ void __launch_bounds__(256) k_hit_group_sums(const uint32_t* __restrict__ summary, uint32_t nd, unsigned long long* gsum) {
+    __shared__ unsigned long long s_part[256];
+    const unsigned long long g0 = (unsigned long long)blockIdx.x << HGROUP_SHIFT;
+    unsigned long long acc = 0;
+    for (unsigned long long i = g0 + threadIdx.x; i < g0 + (1ull << HGROUP_SHIFT) && i < nd; i += 256) acc += hrec_size(summary[2 * i]);
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned o = 128; o; o >>= 1) { if (threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) gsum[blockIdx.x] = s_part[0];
+}
+__global__ void __launch_bounds__(256) k_hit_offsets(const uint32_t* __restrict__ summary, uint32_t nd, uint32_t* hoff) {
+    // every thread owns 256 consecutive k-mers of the group: local sums, a scan over the 256 threads, then the offsets
+    __shared__ uint32_t s_tot[256];
+    const unsigned long long g0 = (unsigned long long)blockIdx.x << HGROUP_SHIFT;
+    const unsigned long long a = g0 + (unsigned long long)threadIdx.x * 256ull;
+    uint32_t acc = 0;
+    for (unsigned long long i = a; i < a + 256ull && i < nd; ++i) acc += hrec_size(summary[2 * i]);
+    s_tot[threadIdx.x] = acc;
+    __syncthreads();
+    for (unsigned o = 1; o < 256; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? s_tot[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_tot[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t off = s_tot[threadIdx.x] - acc;
+    for (unsigned long long i = a; i < a + 256ull && i < nd; ++i) { hoff[i] = off; off += hrec_size(summary[2 * i]); }
+}
+// database build, pass 2: write the records.  Same-slot records come straight from the summary; the others are expanded
+// again (short: collected in shared memory; long: tallied for the per-k counts, then scattered into place).  drop_from:
+// records that start at or beyond this word are not written and their k-mer is marked HOFF_NONE (tests of the
+// on-the-fly path).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_fill_hits(DbView db, const uint32_t* __restrict__ summary, uint32_t* hoff,
+                                                                  const unsigned long long* __restrict__ hbase, uint32_t* hits,
+                                                                  unsigned long long drop_from) {
     __shared__ uint32_t s_flo[WARPS_PER_CTA][MAX_OFF], s_fcnt[WARPS_PER_CTA][MAX_OFF];
     __shared__ uint32_t s_rlo[WARPS_PER_CTA][MAX_OFF], s_rcnt[WARPS_PER_CTA][MAX_OFF];
     __shared__ uint32_t s_val[WARPS_PER_CTA][HCAP];
     __shared__ unsigned char s_ki[WARPS_PER_CTA][HCAP];
     __shared__ unsigned s_n[WARPS_PER_CTA];
+    __shared__ uint32_t s_cnt[WARPS_PER_CTA][MLG_MAX_KS], s_ex[WARPS_PER_CTA], s_min[WARPS_PER_CTA], s_max[WARPS_PER_CTA];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS_PER_CTA + warp; e < db.nd;
          e += (unsigned long long)gridDim.x * WARPS_PER_CTA) {
-        if (lane == 0) s_n[warp] = 0;
-        __syncwarp();
-        CollectSink sink{s_val[warp], s_ki[warp], &s_n[warp]};
-        expand_one(db, db.D_key[e], 1, sink, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
-        if (lane == 0) {
-            const unsigned n = s_n[warp];
-            uint32_t off = HOFF_NONE;
-            unsigned cnt[MLG_MAX_KS];
-            for (unsigned k = 0; k < MLG_MAX_KS; ++k) cnt[k] = 0;
-            bool ok = n <= HCAP;
-            if (ok) {
+        const uint32_t su = summary[2 * e], kind = su >> 30;
+        const unsigned long long at = hbase[e >> HGROUP_SHIFT] + hoff[e];
+        if (at >= drop_from) { if (lane == 0) hoff[e] = HOFF_NONE; continue; }
+        uint32_t* rec = hits + at;
+        if (kind == HREC_SAME) {
+            if (lane == 0) { rec[0] = su & 0x3FFFFFFFu; rec[1] = summary[2 * e + 1]; }
+            continue;
+        }
+        const key128 x = db.D_key[e];
+        if (kind == 0) {
+            if (lane == 0) s_n[warp] = 0;
+            __syncwarp();
+            CollectSink sink{s_val[warp], s_ki[warp], &s_n[warp]};
+            expand_one(db, x, 1, sink, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
+            if (lane == 0) {
+                const unsigned n = s_n[warp] < HCAP ? s_n[warp] : HCAP;      // == the tally of pass 1
+                unsigned cnt[MLG_MAX_KS], start[MLG_MAX_KS], acc = 0;
+                for (unsigned k = 0; k < MLG_MAX_KS; ++k) cnt[k] = 0;
                 for (unsigned i = 0; i < n; ++i) cnt[s_ki[warp][i]]++;
-                for (unsigned k = 0; k < MLG_MAX_KS; ++k) ok = ok && cnt[k] <= 15u;
+                uint32_t hdr = 0;
+                for (unsigned k = 0; k < MLG_MAX_KS; ++k) { hdr |= cnt[k] << (4 * k); start[k] = acc; acc += cnt[k]; }
+                rec[0] = hdr;
+                for (unsigned i = 0; i < n; ++i) rec[1 + start[s_ki[warp][i]]++] = s_val[warp][i];
             }
-            if (ok) {
-                const unsigned long long base = atomicAdd(cursor, (unsigned long long)n + 1ull);
-                if (base + n + 1ull <= cap_words && base + n + 1ull < (unsigned long long)HOFF_NONE) {
-                    uint32_t hdr = 0; unsigned start[MLG_MAX_KS]; unsigned acc = 0;
-                    for (unsigned k = 0; k < MLG_MAX_KS; ++k) { hdr |= cnt[k] << (4 * k); start[k] = acc; acc += cnt[k]; }
-                    hits[base] = hdr;
-                    for (unsigned i = 0; i < n; ++i) hits[base + 1 + start[s_ki[warp][i]]++] = s_val[warp][i];
-                    off = (uint32_t)base;
-                }
+        } else {
+            if (lane < MLG_MAX_KS) s_cnt[warp][lane] = 0;
+            if (lane == 0) { s_ex[warp] = 0; s_min[warp] = 0xFFFFFFFFu; s_max[warp] = 0; }
+            __syncwarp();
+            TallySink tally{s_cnt[warp], &s_ex[warp], &s_min[warp], &s_max[warp]};
+            expand_one(db, x, 1, tally, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
+            if (lane == 0) {
+                rec[0] = HREC_ESC | (HREC_LONG << 4);
+                uint32_t acc = 0;
+                for (unsigned k = 0; k < db.nk; ++k) { const uint32_t c = s_cnt[warp][k]; rec[1 + k] = c; s_cnt[warp][k] = acc; acc += c; }
             }
-            hoff[e] = off;
+            __syncwarp();
+            ScatterSink sc{rec + 1 + db.nk, s_cnt[warp]};
+            expand_one(db, x, 1, sc, lane, s_flo[warp], s_fcnt[warp], s_rlo[warp], s_rcnt[warp]);
         }
         __syncwarp();
     }
 }
 
-// query time: replay the precomputed hit lists of the present k-mers; k-mers without a list are queued for
-// the on-the-fly kernel
+// query time: replay the precomputed records of the present k-mers; k-mers without one are queued for the on-the-fly kernel
 __global__ void k_apply_hits(DbView db, const uint32_t* __restrict__ present, const unsigned long long* __restrict__ d_n_present,
-                             int gate_none, HitSink hs, const uint32_t* __restrict__ hoff, const uint32_t* __restrict__ hits,
-                             uint32_t* fallback, unsigned long long* n_fallback) {
+                             int gate_none, HitSink hs, const uint32_t* __restrict__ hoff, const unsigned long long* __restrict__ hbase,
+                             const uint32_t* __restrict__ hits, uint32_t* fallback, unsigned long long* n_fallback) {
     const unsigned long long n_present = *d_n_present;
     for (unsigned long long xi = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; xi < n_present;
          xi += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t e = present[xi];
         const uint32_t off = hoff[e];
         if (off == HOFF_NONE) { fallback[atomicAdd(n_fallback, 1ull)] = e; continue; }
-        uint32_t hdr = hits[off];
-        const uint32_t* hp = hits + off + 1;
-        for (uint32_t ki = 0; ki < db.nk; ++ki, hdr >>= 4)
-            for (uint32_t c = hdr & 15u; c; --c) {
-                const uint32_t v = *hp++;
-                if (gate_none || (v & HIT_EXACT)) hs.set(db, ki, v & ~HIT_EXACT);
-            }
+        const uint32_t* hp = hits + hbase[e >> HGROUP_SHIFT] + off;
+        uint32_t hdr = *hp++;
+        if ((hdr & 15u) != HREC_ESC) {
+            for (uint32_t ki = 0; ki < db.nk; ++ki, hdr >>= 4)
+                for (uint32_t c = hdr & 15u; c; --c) {
+                    const uint32_t v = *hp++;
+                    if (gate_none || (v & HIT_EXACT)) hs.set(db, ki, v & ~HIT_EXACT);
+                }
+        } else if (((hdr >> 4) & 15u) == HREC_SAME) {
+            const uint32_t r = *hp;
+            const uint32_t take = gate_none ? (hdr >> 8) & 0xFFu : (hdr >> 8) & (hdr >> 16) & 0xFFu;
+            for (uint32_t ki = 0; ki < db.nk; ++ki) if ((take >> ki) & 1u) hs.set(db, ki, r);
+        } else {
+            const uint32_t* cp = hp;
+            hp += db.nk;
+            for (uint32_t ki = 0; ki < db.nk; ++ki)
+                for (uint32_t c = cp[ki]; c; --c) {
+                    const uint32_t v = *hp++;
+                    if (gate_none || (v & HIT_EXACT)) hs.set(db, ki, v & ~HIT_EXACT);
+                }
+        }
     }
 }
 
@@ -461,21 +582,44 @@ int launch_expand_hits(const DbView& db, const uint32_t* present, const unsigned
 }
 int launch_apply_hits(const DbView& db, const uint32_t* present, const unsigned long long* d_n_present, int gate_none,
                       uint32_t* hitbits, unsigned long long words_per_k, unsigned long long* num, const uint32_t* hoff,
-                      const uint32_t* hits, uint32_t* fallback, unsigned long long* d_n_fallback, cudaStream_t st) {
+                      const unsigned long long* hbase, const uint32_t* hits, uint32_t* fallback, unsigned long long* d_n_fallback,
+                      cudaStream_t st) {
     HitSink hs{hitbits, words_per_k, num};
     CUDA_TRY(cudaMemsetAsync(d_n_fallback, 0, 8, st));
-    k_apply_hits<<<148u * 4u, 256, 0, st>>>(db, present, d_n_present, gate_none, hs, hoff, hits, fallback, d_n_fallback);
+    k_apply_hits<<<148u * 4u, 256, 0, st>>>(db, present, d_n_present, gate_none, hs, hoff, hbase, hits, fallback, d_n_fallback);
     CUDA_TRY(cudaGetLastError());
-    // whatever had no list (none, usually) is expanded on the fly
-    k_expand_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, fallback, d_n_fallback, gate_none, hs);
+    // whatever had no record is expanded on the fly (only databases that kept P can have such k-mers)
+    if (db.P_key) {
+        k_expand_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, fallback, d_n_fallback, gate_none, hs);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return MLG_OK;
+}
+int launch_tally_hits(const DbView& db, uint32_t* summary, cudaStream_t st) {
+    if (!db.nd) return MLG_OK;
+    k_tally_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, summary);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }
-int launch_collect_hits(const DbView& db, uint32_t* hoff, uint32_t* hits, unsigned long long cap_words, unsigned long long* d_cursor,
-                        cudaStream_t st) {
-    CUDA_TRY(cudaMemsetAsync(d_cursor, 0, 8, st));
+int launch_hit_group_sums(const uint32_t* summary, uint32_t nd, unsigned long long* gsum, cudaStream_t st) {
+    const unsigned groups = (unsigned)(((unsigned long long)nd + (1ull << HGROUP_SHIFT) - 1) >> HGROUP_SHIFT);
+    if (!groups) return MLG_OK;
+    k_hit_group_sums<<<groups, 256, 0, st>>>(summary, nd, gsum);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_hit_offsets(const uint32_t* summary, uint32_t nd, uint32_t* hoff, cudaStream_t st) {
+    const unsigned groups = (unsigned)(((unsigned long long)nd + (1ull << HGROUP_SHIFT) - 1) >> HGROUP_SHIFT);
+    if (!groups) return MLG_OK;
+    static_assert((1u << HGROUP_SHIFT) == 256u * 256u, "k_hit_offsets: 256 threads x 256 k-mers per group");
+    k_hit_offsets<<<groups, 256, 0, st>>>(summary, nd, hoff);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_fill_hits(const DbView& db, const uint32_t* summary, uint32_t* hoff, const unsigned long long* hbase,
+                     uint32_t* hits, unsigned long long drop_from, cudaStream_t st) {
     if (!db.nd) return MLG_OK;
-    k_collect_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, hoff, hits, cap_words, d_cursor);
+    k_fill_hits<<<148u * 16u, WARPS_PER_CTA * 32, 0, st>>>(db, summary, hoff, hbase, hits, drop_from);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }
