@@ -102,7 +102,11 @@ int mlg_db_from_keys_device(mlg_ctx* ctx, const uint64_t* d_keys /* device, 16-b
                             uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db** out);
 int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers /* host, G*n*K chars; a slot starting with NUL is empty */,
                       uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db** out);
+/* .mlgdb file: the source form (sketch keys; the device structures are built on load) or the built form written by
+ * mlg_db_save (the device structures themselves: loading is a file read).  names = the '\n'-joined genome names the
+ * file's head carries for the host side (metalign_b200/dbformat.py). */
 int mlg_db_load(mlg_ctx* ctx, const char* path /* .mlgdb file */, mlg_db** out);
+int mlg_db_save(const mlg_db* db, const char* path, const char* names, uint64_t names_bytes);
 int mlg_db_info(const mlg_db* db, uint32_t* G, uint32_t* n, uint32_t* K, uint32_t* nk, uint32_t* ks /* 8 */,
                 uint64_t* n_entries, uint64_t* n_distinct);
 /* static denominators: distinct k-prefixes per genome (+1 for '' where the genome has an empty slot) */

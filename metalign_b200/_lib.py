@@ -61,6 +61,7 @@ SIGNATURES = {
     "mlg_db_from_keys_device": (C.c_int, [_vp, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _pp]),
     "mlg_db_from_ascii": (C.c_int, [_vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _pp]),
     "mlg_db_load": (C.c_int, [_vp, C.c_char_p, _pp]),
+    "mlg_db_save": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_uint64]),
     "mlg_db_info": (C.c_int, [_vp] + [C.POINTER(C.c_uint32)] * 4 + [C.POINTER(C.c_uint32 * 8)] + [C.POINTER(C.c_uint64)] * 2),
     "mlg_db_denominators": (C.c_int, [_vp, C.c_int, _i64p]),
     "mlg_db_free": (C.c_int, [_vp]),

@@ -123,6 +123,14 @@ class Database:
         check(_lib.lib().mlg_db_load(ctx._h, path.encode(), C.byref(h)))
         return cls(ctx, h, names)
 
+    def save(self, path: str) -> None:
+        """Write the BUILT form of the database (the device structures): `Database.load` of such a file is a file read,
+        not a rebuild.  Needs the genome names (a database made by `load` or given `names=`)."""
+        blob = "\n".join(self.names or []).encode()
+        if self.names is None or len(self.names) != self.G:
+            raise ValueError("saving needs one name per genome")
+        check(_lib.lib().mlg_db_save(self._h, path.encode(), blob, len(blob)))
+
     # -- queries ------------------------------------------------------------------------------
     def denominators(self, count_empty_in_den: bool = True) -> np.ndarray:
         den = np.zeros((self.G, len(self.ks)), dtype=np.int64)

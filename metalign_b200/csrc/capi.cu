@@ -317,33 +317,17 @@ MLG_API int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers, uint32_t G, uint3
     return mlg_db_build_device(ctx, d.p, G, n, K, ks, nk, out);
 }
 
-// .mlgdb: "MLGDB001", u32 K, u32 n, u64 G, u32 nk, u32 ks[8], u64 names_bytes, names, pad to 16, keys (G*n * 16 bytes)
+// .mlgdb files, source form (version 1: the sketch keys; everything else is rebuilt here) or built form (version 2: the
+// device structures as mlg_db_save wrote them): csrc/dbfile.cu
 MLG_API int mlg_db_load(mlg_ctx* ctx, const char* path, mlg_db** out) {
     if (!ctx || !path || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
     MLG_TRY(ensure_device(ctx));
-    FILE* f = fopen(path, "rb");
-    if (!f) { mlg_set_error("cannot open %s", path); return MLG_ERR_IO; }
-    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
-    char magic[8]; uint32_t K, n, nk, ks[8]; uint64_t G, names_bytes;
-    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "MLGDB001", 8) != 0) { mlg_set_error("%s: not a .mlgdb file", path); return MLG_ERR_IO; }
-    if (fread(&K, 4, 1, f) != 1 || fread(&n, 4, 1, f) != 1 || fread(&G, 8, 1, f) != 1 || fread(&nk, 4, 1, f) != 1 ||
-        fread(ks, 4, 8, f) != 8 || fread(&names_bytes, 8, 1, f) != 1) { mlg_set_error("%s: truncated header", path); return MLG_ERR_IO; }
-    if (G == 0 || G > 0xFFFFFFFFull || nk < 1 || nk > 8) { mlg_set_error("%s: bad header", path); return MLG_ERR_IO; }
-    uint64_t pos = 8 + 4 + 4 + 8 + 4 + 32 + 8 + names_bytes;
-    pos = round_up(pos, 16);
-    if (fseek(f, (long)pos, SEEK_SET) != 0) { mlg_set_error("%s: truncated", path); return MLG_ERR_IO; }
-    size_t total = (size_t)G * n;
-    DevBuf<key128> d; MLG_TRY(d.alloc(total));
-    const size_t CH = (size_t)1 << 22;   // keys per staging chunk (64 MiB)
-    void* h = nullptr;
-    CUDA_TRY(cudaMallocHost(&h, std::min(CH, total ? total : 1) * sizeof(key128)));
-    struct HFree { void* p; ~HFree() { cudaFreeHost(p); } } hfree{h};
-    for (size_t o = 0; o < total; o += CH) {
-        size_t m = std::min(CH, total - o);
-        if (fread(h, sizeof(key128), m, f) != m) { mlg_set_error("%s: truncated key block", path); return MLG_ERR_IO; }
-        CUDA_TRY(cudaMemcpy(d.p + o, h, m * sizeof(key128), cudaMemcpyHostToDevice));
-    }
-    return mlg_db_build_device(ctx, d.p, (uint32_t)G, n, K, ks, nk, out);
+    return mlg_db_load_file(ctx, path, out);
+}
+MLG_API int mlg_db_save(const mlg_db* db, const char* path, const char* names, uint64_t names_bytes) {
+    if (!db || !path || (names_bytes && !names)) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(db->ctx));
+    return mlg_db_save_file(db, path, names, names_bytes);
 }
 MLG_API int mlg_db_info(const mlg_db* db, uint32_t* G, uint32_t* n, uint32_t* K, uint32_t* nk, uint32_t* ks, uint64_t* n_entries,
                 uint64_t* n_distinct) {

@@ -211,16 +211,22 @@ MLG_HD unsigned long long key_hash_sk(const key128& x, unsigned K, unsigned bbit
 #define MLG_MZ_M 32u
 #define MLG_MZ_ORD_MULT 0x9E3779B1u
 MLG_HD unsigned mz_order(unsigned a, unsigned b) { return ((a + b) * MLG_MZ_ORD_MULT) & 0x03FFFFFFu; }
-MLG_HD unsigned mz_mix(unsigned t) { t ^= t >> 16; t *= 0x7FEB352Du; t ^= t >> 15; return t; }
 // low word: bit index inside the level-1 array (plus the low bits of the high word for arrays above 2^32 bits);
-// high word: bucket of the exact-compare index (its top bbits bits)
+// high word: bucket of the exact-compare index (its top bbits bits) and the second bit position (its top 5 bits).
+// Both words are multiply-add hashes of the ordered pair (min, max) with one xor-shift each (10 instructions for the two;
+// the round-2 version, with a multiply-xorshift finisher per word, took 17, four times per block of 16 windows).  Both
+// words are used from their low bits up as well as from the top, hence the xor-shifts.  (A version hashing a + b and
+// a ^ b instead of min / max lost a bit -- both products are even or odd together -- and with it half of the array:
+// K1 went from 2.32 to 2.59 ms on four times the false positives.)
 MLG_HD unsigned mz_ident_lo(unsigned a, unsigned b) {
     const unsigned lo = a < b ? a : b, hi = a < b ? b : a;
-    return mz_mix(lo * 0x9E3779B1u + hi * 0x85EBCA6Bu);
+    const unsigned t = lo * 0x85EBCA6Bu + hi * 0xC2B2AE35u;
+    return t ^ (t >> 15);
 }
 MLG_HD unsigned mz_ident_hi(unsigned a, unsigned b) {
     const unsigned lo = a < b ? a : b, hi = a < b ? b : a;
-    return mz_mix(lo * 0xC2B2AE35u + hi * 0x27D4EB2Fu + 0x165667B1u);
+    const unsigned u = lo * 0x27D4EB2Fu + hi * 0x165667B1u + 0x9E3779B9u;
+    return u ^ (u >> 16);       // arrays above 2^32 bits take index bits from the LOW end of this word as well
 }
 MLG_HD unsigned long long mz_ident(unsigned a, unsigned b) { return ((unsigned long long)mz_ident_hi(a, b) << 32) | mz_ident_lo(a, b); }
 // every identity sets TWO bits of its 32-bit word (blocked Bloom filter: one DRAM access, false positives ~ density^2):

@@ -118,6 +118,9 @@ struct mlg_db {
 
 int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t n, uint32_t K,
                         const uint32_t* ks, uint32_t nk, mlg_db** out);
+// .mlgdb files (dbfile.cu): version 1 = source keys (built on load), version 2 = the built structures
+int mlg_db_load_file(mlg_ctx* ctx, const char* path, mlg_db** out);
+int mlg_db_save_file(const mlg_db* db, const char* path, const char* names, uint64_t names_bytes);
 
 // ---- kernels' host launchers (probe.cu / query.cu) ----
 struct ProbeArgs {

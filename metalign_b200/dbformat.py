@@ -22,6 +22,7 @@ import struct
 import numpy as np
 
 MAGIC = b"MLGDB001"
+MAGIC_BUILT = b"MLGDB002"     # same head; behind it the built device structures (csrc/dbfile.cu) instead of the keys
 _HDR = struct.Struct("<8sIIQI8IQ")
 
 
@@ -45,12 +46,12 @@ def write(path: str, keys: np.ndarray, names, G: int, n: int, K: int, ks) -> Non
 def read_header(path: str):
     with open(path, "rb") as f:
         raw = f.read(_HDR.size)
-        if len(raw) != _HDR.size or raw[:8] != MAGIC:
+        if len(raw) != _HDR.size or raw[:8] not in (MAGIC, MAGIC_BUILT):
             raise ValueError("%s is not a .mlgdb file" % path)
         vals = _HDR.unpack(raw)
     _, K, n, G, nk = vals[:5]
     ks = list(vals[5:13])[:nk]
-    return dict(K=K, n=n, G=G, ks=ks, names_bytes=vals[13], header_bytes=_HDR.size)
+    return dict(K=K, n=n, G=G, ks=ks, names_bytes=vals[13], header_bytes=_HDR.size, built=(raw[:8] == MAGIC_BUILT))
 
 
 def read_names(path: str):
@@ -66,6 +67,8 @@ def read_names(path: str):
 
 def read_keys(path: str) -> np.ndarray:
     h = read_header(path)
+    if h["built"]:
+        raise ValueError("%s is a built database: it does not carry the source keys" % path)
     pos = h["header_bytes"] + h["names_bytes"]
     pos += (-pos) % 16
     return np.fromfile(path, dtype="<u8", offset=pos, count=2 * h["G"] * h["n"]).reshape(-1, 2)

@@ -24,6 +24,20 @@ HEADER_LINES = ("Accesion\tLength\tTaxID\tLineage\tTaxID_Lineage\n",          # 
                 "Unmapped\t0\tUnmapped\t|||||||Unmapped\t|||||||Unmapped\n")
 
 
+_T0 = None
+
+
+def _tick(label):
+    """MLG_TIMING=1: stage times on stderr (seconds since the module was imported)"""
+    if os.environ.get("MLG_TIMING"):
+        import time
+        global _T0
+        now = time.perf_counter()
+        if _T0 is None:
+            _T0 = now
+        sys.stderr.write("[mlg %7.3f s] %s\n" % (now - _T0, label))
+
+
 def select_parseargs(argv=None):
     p = argparse.ArgumentParser(description="Score every database genome against the reads (containment min-hash, "
                                             "k=30..60) and write the reduced database to align to.")
@@ -76,16 +90,39 @@ def run_kmc_steps(args):
     from .api import Context, Database, pinned_array
     ctx = db = query = reader = None
     try:
+        # pandas (the CSV tail) takes a good part of a second to import: do it while the GPU works
+        import threading
+        threading.Thread(target=lambda: __import__("pandas"), daemon=True).start()
+        _tick("imports done")
         ctx = Context(args.device)
-        db = Database.load(ctx, args.db_file)
+        _tick("CUDA context")
+        # the native reader (its worker count = --threads, KMC's -t in the reference) is set up -- pinned buffers, file
+        # mapped, parser threads started -- by a helper thread while this one reads the database file (both are C calls
+        # that release the interpreter lock); it then cuts the first batches while the database is still loading, and
+        # later fills one pinned buffer set while the previous batch is on its way to the GPU
+        box = {}
+
+        def open_reader():
+            try:
+                box["reader"] = ingest.PackedBatches(args.reads, args.input_type, alloc=pinned_array,
+                                                     threads=max(1, int(getattr(args, "threads", 4) or 4)))
+            except BaseException as e:  # noqa: BLE001
+                box["error"] = e
+        th = threading.Thread(target=open_reader)
+        th.start()
+        try:
+            db = Database.load(ctx, args.db_file)
+        finally:
+            th.join()
+            reader = box.get("reader")
+        if "error" in box:
+            raise box["error"]
+        _tick("database loaded, reader started")
         query = db.query(ci_min=2, gate=args.gate, count_empty_in_den=True)     # -ci2 (select_db.py:50)
-        # the native reader (its worker count = --threads, KMC's -t in the reference) fills one pinned buffer set while
-        # the previous batch is still on its way to the GPU
-        reader = ingest.PackedBatches(args.reads, args.input_type, threads=max(1, int(getattr(args, "threads", 4) or 4)),
-                                      alloc=pinned_array)
         for bases, nruns, off, n_reads in reader:
             query.push_packed_nruns(bases, nruns if len(nruns) else None, off, n_reads)
         query.sync()
+        _tick("reads pushed and probed")
     except BaseException:
         # a corrupt reads file, a failed push: give the device and pinned memory back before the error travels on
         # (a caller looping over samples would otherwise accumulate them)
@@ -97,6 +134,7 @@ def run_kmc_steps(args):
                     pass
         raise
     reader.close()
+    _tick("reader closed")
     args._mlg = (ctx, db, query)
 
 
@@ -108,13 +146,17 @@ def run_cmash_and_cutoff(args, taxid2info):
         ctx, db, query = args._mlg
         cmash_out = args.temp_dir + "cmash_query_results.csv"
         res = query.finish()
+        _tick("containment table")
         cmash_tail.write_results_csv(cmash_out, db.names, db.ks, res["ci"], 0.0)      # '-c 0'
+        _tick("csv written")
         if args.keep_temp_files:
             with open(args.temp_dir + "60mers_intersection_dump", "w") as fh:
                 for hi, lo in query.intersection():
                     fh.write(codec.key_to_kmer(hi, lo, db.K) + "\n")
-        query.close(); db.close(); ctx.close()
+        if not getattr(args, "_mlg_leave_open", False):     # the command-line script exits right after: no point in freeing GBs first
+            query.close(); db.close(); ctx.close()
         del args._mlg
+        _tick("GPU objects closed")
     else:
         cmash_out = args.cmash_results
 
@@ -202,11 +244,33 @@ def select_main(args=None):
         print("Error: args.cutoff must be between 0 and 1, inclusive.")
         sys.exit()
     _normalise(args)
-    taxid2info = read_dbinfo(args)
+    _tick("start")
     if args.cmash_results == "NONE":
-        run_kmc_steps(args)
+        # db_info.txt has a line per accession of the full database: parsed beside the GPU stage, needed after it
+        import threading
+        box = {}
+
+        def load_info():
+            try:
+                box["info"] = read_dbinfo(args)
+            except BaseException as e:  # noqa: BLE001
+                box["error"] = e
+        th = threading.Thread(target=load_info)
+        th.start()
+        try:
+            run_kmc_steps(args)
+        finally:
+            th.join()
+        if "error" in box:
+            raise box["error"]
+        taxid2info = box["info"]
+    else:
+        taxid2info = read_dbinfo(args)
+    _tick("db_info read")
     organisms_to_include = run_cmash_and_cutoff(args, taxid2info)
+    _tick("selection done")
     make_db_and_dbinfo(args, organisms_to_include, taxid2info)
+    _tick("subset files written")
     return organisms_to_include
 
 

@@ -203,6 +203,48 @@ def test_mlgdb_roundtrip(ctx, workload, tmp_path):
     db.close()
 
 
+def test_built_database_file(ctx, workload, tmp_path, monkeypatch):
+    """the built form of a database (mlg_db_save: the device structures themselves) loads to the same answers for both
+    gates, keeps the names, refuses a file of another build tag, and cannot be written from a database that kept P"""
+    w = workload
+    p = w["p"]
+    names = ["taxid_%d_genomic.fna.gz" % g for g in range(p.G)]
+    src = str(tmp_path / "src.mlgdb")
+    dbformat.write(src, w["keys"], names, p.G, p.n, 60, KS)
+    db = Database.load(ctx, src)
+    built = str(tmp_path / "built.mlgdb")
+    db.save(built)
+    db.close()
+    assert dbformat.read_header(built)["built"] and dbformat.read_names(built) == names
+    with pytest.raises(ValueError):
+        dbformat.read_keys(built)
+    db2 = Database.load(ctx, built)
+    assert db2.names == names and (db2.G, db2.n, db2.K, db2.ks) == (p.G, p.n, 60, KS)
+    assert np.array_equal(db2.denominators(True), w["refs"]["exact"][0]["den"])
+    for gate in ("exact", "none"):
+        q = db2.query(2, gate, True)
+        q.push_packed(w["bases"], w["nmask"], None, w["nreads"], p.read_len)
+        res = q.finish()
+        _check(res, q.intersection(), *w["refs"][gate], tag=("built", gate))
+        q.close()
+    db2.close()
+    raw = bytearray(open(built, "rb").read())
+    head = (68 + len("\n".join(names).encode()) + 15) // 16 * 16
+    raw[head] ^= 0xFF                                   # the build tag
+    bad = str(tmp_path / "stale.mlgdb")
+    open(bad, "wb").write(raw)
+    with pytest.raises(MlgError):
+        Database.load(ctx, bad)
+    open(bad, "wb").write(raw[: len(raw) // 2])          # truncated
+    with pytest.raises(MlgError):
+        Database.load(ctx, bad)
+    monkeypatch.setenv("MLG_KEEP_P", "1")
+    db3 = Database.from_keys(ctx, w["keys"], p.G, p.n, 60, KS, names=names)
+    with pytest.raises(MlgError):
+        db3.save(str(tmp_path / "no.mlgdb"))
+    db3.close()
+
+
 def test_sixteen_byte_buckets(ctx, workload, monkeypatch):
     w = workload
     monkeypatch.setenv("MLG_BUCKET_SLOTS", "4")
