@@ -239,7 +239,8 @@ def run_native(args):
     from metalign_b200 import codec
     from metalign_b200 import dist as mdist
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line on stdout: whatever NCCL has to say (its version banner, with NCCL_DEBUG set) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = mdist.init_from_env("nccl")
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -301,6 +302,10 @@ def run_native(args):
     h_num = torch.empty(G * nk, dtype=torch.int64, pin_memory=True)
     h_den = torch.empty(G * nk, dtype=torch.int64, pin_memory=True)
     h_ci = torch.empty(G * nk, dtype=torch.float64, pin_memory=True)
+    ROW_CAP = min(G, 1 << 16)
+    h_rows_g = torch.empty(ROW_CAP, dtype=torch.int32, pin_memory=True)
+    h_rows_ci = torch.empty(ROW_CAP * nk, dtype=torch.float64, pin_memory=True)
+    rows = [0]
     torch.cuda.synchronize()
 
     def step(host_leg: bool, readback_all: bool = False):
@@ -320,8 +325,12 @@ def run_native(args):
         # (static) denominators stay on the device unless asked for
         if readback_all or os.environ.get("MLG_BENCH_READBACK_ALL"):
             ni = q.finish_into(h_num.data_ptr(), h_den.data_ptr(), h_ci.data_ptr())
-        else:
+        elif os.environ.get("MLG_BENCH_DENSE_RESULT"):
             ni = q.finish_into(None, None, h_ci.data_ptr())
+        else:
+            # rows of the genomes with a hit (mlg_query_finish_sparse): everything CMash's CSV can hold, a few KB instead
+            # of the 6.4 MB dense table
+            ni, rows[0] = q.finish_sparse_into(h_rows_g.data_ptr(), None, None, h_rows_ci.data_ptr(), ROW_CAP)
         st = q.stats()
         q.close()
         return ni, st
@@ -418,6 +427,7 @@ def run_native(args):
                       tr.get("warps_active_pct", 0), tr.get("source", "")))
     else:
         limiter = "random 32-byte DRAM sectors (one per k-mer behind an L2 prefilter)" if layout == 0 else "see profiles/"
+    xmode_eff = mdist.effective_mode(ctx, xmode)
     line = None
     if rank == 0:
         l1_bytes = st_dev[-1]["filter_words"] * 4 if layout == 2 else st_dev[-1]["n_buckets"] * (32 if layout == 1 else bucket_bytes)
@@ -430,7 +440,9 @@ def run_native(args):
                 "workload": desc, "workload_name": args.workload,
                 "genomes": G, "sketch_slots": 1000, "reads_total": total_reads, "reads_rank0": reads_rank, "pushes_per_step": len(batches),
                 "read_len": READ_LEN, "db_distinct_kmers": st_dev[-1]["n_db_distinct"], "intersect": ni,
-                "parallelism": ("reads sharded x%d, DB replicated, ONE exchange per job: %s (MLG_EXCHANGE=%s)" % (world, mdist.describe_exchange(xmode, world), xmode)) if world > 1 else "single GPU",
+                "result": ("dense containment table" if os.environ.get("MLG_BENCH_DENSE_RESULT") or os.environ.get("MLG_BENCH_READBACK_ALL")
+                           else "containment rows of the %d genomes with a hit (mlg_query_finish_sparse)" % rows[0]),
+                "parallelism": ("reads sharded x%d, DB replicated, ONE exchange per job: %s (MLG_EXCHANGE=%s)" % (world, mdist.describe_exchange(xmode_eff, world), xmode_eff)) if world > 1 else "single GPU",
                 "l2_policy": "inputs (%.2f GB packed reads per GPU) and level-1 table (%.2f GB) both exceed the 126 MB L2; no flush needed" % (in_bytes / 1e9, l1_bytes / 1e9),
                 "db_build_s": round(t_db, 3),
             },

@@ -166,6 +166,12 @@ int mlg_query_exchange_p2p(mlg_query* q, mlg_exchange* ex);
 int mlg_query_exchange_dense(mlg_query* q, uint8_t** d_counts, uint64_t* n_counts);
 /* num/den: int64 [G*nk]; ci: double [G*nk] (num/den where num > 0, else 0.0); any pointer may be NULL */
 int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect);
+/* the same result in sparse form: one row per genome with a hit at any k (in no particular order) -- genome index, and
+ * nk values each of num / den / ci per row; any output pointer may be NULL.  *n_rows = the number of rows; if it exceeds
+ * cap_rows the call fails with MLG_ERR_ARG and can be repeated with larger buffers.  Everything select_db.py keeps is in
+ * these rows: CMash's tail drops the genomes whose containment at the largest k is 0. */
+int mlg_query_finish_sparse(mlg_query* q, uint32_t* genomes, int64_t* num, int64_t* den, double* ci, uint64_t cap_rows,
+                            uint64_t* n_rows, uint64_t* n_intersect);
 /* after finish: I as (hi,lo) canonical keys in increasing order; writes at most cap pairs, *n = |I| */
 int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n);
 int mlg_query_stats(mlg_query* q, mlg_stats* out);

@@ -243,16 +243,22 @@ class Query:
         check(_lib.lib().mlg_query_exchange_dense(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def _finish_call(self, num_ptr, den_ptr, ci_ptr):
-        """mlg_query_finish; an exchange whose blocks turned out too small is repeated once with larger ones
-        (self._exchange_retry is set by metalign_b200.dist.reduce_query)"""
+    def _finish_call(self, num_ptr, den_ptr, ci_ptr, sparse=None):
+        """mlg_query_finish (or, with sparse = (genomes, cap, n_rows byref), mlg_query_finish_sparse); an exchange whose
+        blocks turned out too small is repeated once with larger ones (self._exchange_retry is set by
+        metalign_b200.dist.reduce_query)"""
         ni = C.c_uint64()
-        rc = _lib.lib().mlg_query_finish(self._h, num_ptr, den_ptr, ci_ptr, C.byref(ni))
+
+        def call():
+            if sparse is None:
+                return _lib.lib().mlg_query_finish(self._h, num_ptr, den_ptr, ci_ptr, C.byref(ni))
+            return _lib.lib().mlg_query_finish_sparse(self._h, sparse[0], num_ptr, den_ptr, ci_ptr, sparse[1], sparse[2], C.byref(ni))
+        rc = call()
         retry = getattr(self, "_exchange_retry", None)
         if rc == _lib.MLG_ERR_RETRY and retry is not None:
             msg = _lib.lib().mlg_last_error().decode(errors="replace")
             retry(int(msg.split(":")[-1].split()[0]))
-            rc = _lib.lib().mlg_query_finish(self._h, num_ptr, den_ptr, ci_ptr, C.byref(ni))
+            rc = call()
         check(rc)
         return ni.value
 
@@ -271,6 +277,37 @@ class Query:
         ni = self._finish_call(num_ptr, den_ptr, ci_ptr)
         self._keep = []
         return ni
+
+    def finish_sparse(self, cap_rows: int = 1 << 16):
+        """The result as rows for the genomes with a hit at any k, sorted by genome index:
+        dict(genomes uint32[m], num / den int64[m, nk], ci float64[m, nk], n_intersect, n_kmers, stats)."""
+        nk = len(self.db.ks)
+        while True:
+            g = np.empty(cap_rows, dtype=np.uint32)
+            num = np.empty((cap_rows, nk), dtype=np.int64)
+            den = np.empty((cap_rows, nk), dtype=np.int64)
+            ci = np.empty((cap_rows, nk), dtype=np.float64)
+            n = C.c_uint64()
+            try:
+                ni = self._finish_call(num.ctypes.data, den.ctypes.data, ci.ctypes.data, (g.ctypes.data, cap_rows, C.byref(n)))
+                break
+            except MlgError:
+                if n.value <= cap_rows:
+                    raise
+                cap_rows = int(n.value)           # more rows than room: the call can simply be repeated
+        self._keep = []
+        m = n.value
+        order = np.argsort(g[:m], kind="stable")
+        st = self.stats()
+        return dict(genomes=g[:m][order], num=num[:m][order], den=den[:m][order], ci=ci[:m][order], n_intersect=ni,
+                    n_kmers=st["n_kmers"], stats=st)
+
+    def finish_sparse_into(self, genomes_ptr: int, num_ptr, den_ptr, ci_ptr, cap_rows: int):
+        """finish_sparse() into caller-provided (pinned) host buffers, rows in no particular order; returns (|I|, rows)"""
+        n = C.c_uint64()
+        ni = self._finish_call(num_ptr, den_ptr, ci_ptr, (genomes_ptr, int(cap_rows), C.byref(n)))
+        self._keep = []
+        return ni, n.value
 
     def intersection(self) -> np.ndarray:
         n = C.c_uint64()

@@ -30,3 +30,18 @@ def write_results_csv(path: str, names: Sequence[str], ks: Sequence[int], ci: np
     out = filter_and_sort(containment_frame(names, ks, ci), coverage_threshold)
     out.to_csv(path, index=True, encoding="utf-8")
     return out
+
+
+def write_results_csv_sparse(path: str, names: Sequence[str], ks: Sequence[int], genomes: np.ndarray, ci_rows: np.ndarray,
+                             coverage_threshold: float = 0.0) -> pd.DataFrame:
+    """The same file from the sparse form of the result (Query.finish_sparse: rows only for genomes with a hit, in genome
+    order).  CMash filters BEFORE it sorts, so the sort sees exactly the rows above the threshold in genome order either
+    way, and with a threshold >= 0 every such row has a hit: the two forms give the same bytes (tests/test_select_db.py)."""
+    if coverage_threshold < 0.0:
+        raise ValueError("the sparse form only holds genomes with a hit: it cannot serve a negative threshold")
+    ci_rows = np.asarray(ci_rows, dtype=np.float64).reshape(-1, len(ks))
+    data = {"k=%d" % k: ci_rows[:, i] for i, k in enumerate(ks)}
+    df = pd.DataFrame(data, index=[names[int(g)] for g in genomes])
+    out = filter_and_sort(df, coverage_threshold)
+    out.to_csv(path, index=True, encoding="utf-8")
+    return out

@@ -139,6 +139,8 @@ struct mlg_query {
     mlg_stats st{};
     bool finished = false, reduced = false, merged = false;
     mlg_exchange* ex_pending = nullptr;            // exchange whose status words mlg_query_finish has to look at
+    DevBuf<uint32_t> fallback;                     // k-mers without a hit record (databases that kept P only)
+    DevBuf<unsigned long long> d_rows;             // sparse finish: row counter
     DevBuf<unsigned long long> sparse;             // this rank's non-zero counters as index | count << 32
     unsigned long long chunk_words = CHUNK_WORDS;   // 64-base words per host->device copy chunk
     // results kept for mlg_query_intersection
@@ -366,9 +368,13 @@ MLG_API int mlg_query_begin(mlg_ctx* ctx, mlg_db* db, int ci_min, int gate_mode,
     struct Guard { mlg_query* q; ~Guard() { if (q) mlg_query_free(q); } } guard{q};
     q->ctx = ctx; q->db = db; q->ci_min = ci_min; q->gate = gate_mode; q->count_empty = count_empty_in_den ? 1 : 0;
     size_t cbytes = round_up((size_t)db->v.nd + 4, 16);
-    MLG_TRY(q->cnt8.alloc(cbytes));
+    if (db->clean_cnt8.p && db->clean_cnt8.n >= cbytes) {        // left all-zero by the query before (mlg_query_free)
+        std::swap(q->cnt8.p, db->clean_cnt8.p); std::swap(q->cnt8.n, db->clean_cnt8.n);
+    } else {
+        MLG_TRY(q->cnt8.alloc(cbytes));
+        CUDA_TRY(cudaMemsetAsync(q->cnt8.p, 0, cbytes, ctx->s_comp));
+    }
     MLG_TRY(q->d_nkmers.alloc(2)); MLG_TRY(q->d_scalar.alloc(4));
-    CUDA_TRY(cudaMemsetAsync(q->cnt8.p, 0, cbytes, ctx->s_comp));
     CUDA_TRY(cudaMemsetAsync(q->d_nkmers.p, 0, 16, ctx->s_comp));
     CUDA_TRY(cudaMemsetAsync(q->d_scalar.p, 0, 32, ctx->s_comp));
     CUDA_TRY(cudaEventCreate(&q->ev_q0)); CUDA_TRY(cudaEventCreate(&q->ev_q1));
@@ -708,7 +714,9 @@ MLG_API int mlg_query_exchange_dense(mlg_query* q, uint8_t** d_counts, uint64_t*
     return MLG_OK;
 }
 
-MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect) {
+// the finish stage, shared by the dense and the sparse form of the result
+struct SparseOut { uint32_t* genomes; int64_t* num; int64_t* den; double* ci; uint64_t cap; uint64_t* n_rows; };
+static int finish_impl(mlg_query* q, int64_t* num, int64_t* den, double* ci, const SparseOut* sp, uint64_t* n_intersect) {
     if (!q) { mlg_set_error("null query"); return MLG_ERR_ARG; }
     if (q->finished) { mlg_set_error("query already finished"); return MLG_ERR_STATE; }
     mlg_ctx* ctx = q->ctx; mlg_db* db = q->db; const DbView& v = db->v;
@@ -730,23 +738,43 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     CUDA_TRY(cudaMemsetAsync(hitbits.p, 0, words_per_k * v.nk * 4, st));
     const size_t cells = (size_t)v.G * v.nk;
     DevBuf<unsigned long long> d_num; MLG_TRY(d_num.alloc(cells));
-    DevBuf<long long> o_num, o_den; DevBuf<double> o_ci;
-    MLG_TRY(o_num.alloc(cells)); MLG_TRY(o_den.alloc(cells)); MLG_TRY(o_ci.alloc(cells));
     CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
     if (db->hoff.p) {
-        // replay the precomputed hit lists; touched[] is dead by now and serves as the list of k-mers without one
+        // replay the precomputed hit records; k-mers without one (only a database that kept P has any) are listed and
+        // expanded on the fly
+        if (v.P_key && !q->fallback.p) MLG_TRY(q->fallback.alloc((size_t)v.nd + 1));
         MLG_TRY(launch_apply_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p,
-                                  db->hoff.p, db->hbase.p, db->hits.p, q->touched.p, q->d_scalar.p + 2, st));
+                                  db->hoff.p, db->hbase.p, db->hits.p, q->fallback.p, q->d_scalar.p + 2, st));
         q->st.gpu_launches += 1;
     } else {
         MLG_TRY(launch_expand_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p, st));
     }
-    MLG_TRY(launch_finalize(d_num.p, db->den_real.p, db->has_empty.p, v.G, v.nk, q->count_empty, o_num.p, o_den.p, o_ci.p, st));
     q->st.gpu_launches += 2;
-    CUDA_TRY(cudaEventRecord(q->ev_q1, st));
-    if (num) { CUDA_TRY(cudaMemcpyAsync(num, o_num.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
-    if (den) { CUDA_TRY(cudaMemcpyAsync(den, o_den.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
-    if (ci) { CUDA_TRY(cudaMemcpyAsync(ci, o_ci.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
+    DevBuf<long long> o_num, o_den; DevBuf<double> o_ci; DevBuf<uint32_t> o_g;
+    unsigned long long nrows = 0;
+    const uint64_t first = sp ? std::min<uint64_t>(sp->cap, 4096) : 0;     // rows copied back before their number is known
+    if (!sp) {
+        MLG_TRY(o_num.alloc(cells)); MLG_TRY(o_den.alloc(cells)); MLG_TRY(o_ci.alloc(cells));
+        MLG_TRY(launch_finalize(d_num.p, db->den_real.p, db->has_empty.p, v.G, v.nk, q->count_empty, o_num.p, o_den.p, o_ci.p, st));
+        CUDA_TRY(cudaEventRecord(q->ev_q1, st));
+        if (num) { CUDA_TRY(cudaMemcpyAsync(num, o_num.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
+        if (den) { CUDA_TRY(cudaMemcpyAsync(den, o_den.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
+        if (ci) { CUDA_TRY(cudaMemcpyAsync(ci, o_ci.p, cells * 8, cudaMemcpyDeviceToHost, st)); q->st.d2h_bytes += cells * 8; }
+    } else {
+        const size_t rc = (size_t)std::max<uint64_t>(sp->cap, 1);
+        MLG_TRY(o_g.alloc(rc)); MLG_TRY(o_num.alloc(rc * v.nk)); MLG_TRY(o_den.alloc(rc * v.nk)); MLG_TRY(o_ci.alloc(rc * v.nk));
+        if (!q->d_rows.p) MLG_TRY(q->d_rows.alloc(1));
+        MLG_TRY(launch_finalize_sparse(d_num.p, db->den_real.p, db->has_empty.p, v.G, v.nk, q->count_empty, o_g.p, o_num.p, o_den.p,
+                                       o_ci.p, sp->cap, q->d_rows.p, st));
+        CUDA_TRY(cudaEventRecord(q->ev_q1, st));
+        CUDA_TRY(cudaMemcpyAsync(&nrows, q->d_rows.p, 8, cudaMemcpyDeviceToHost, st));
+        if (first) {
+            if (sp->genomes) CUDA_TRY(cudaMemcpyAsync(sp->genomes, o_g.p, first * 4, cudaMemcpyDeviceToHost, st));
+            if (sp->num) CUDA_TRY(cudaMemcpyAsync(sp->num, o_num.p, first * v.nk * 8, cudaMemcpyDeviceToHost, st));
+            if (sp->den) CUDA_TRY(cudaMemcpyAsync(sp->den, o_den.p, first * v.nk * 8, cudaMemcpyDeviceToHost, st));
+            if (sp->ci) CUDA_TRY(cudaMemcpyAsync(sp->ci, o_ci.p, first * v.nk * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
     unsigned long long nk_host2[2] = {0, 0}, ni = 0;
     unsigned long long& nk_host = nk_host2[0];
     CUDA_TRY(cudaMemcpyAsync(nk_host2, q->d_nkmers.p, 16, cudaMemcpyDeviceToHost, st));
@@ -763,6 +791,20 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
         mlg_set_error("exchange blocks too small: %llu entries needed", xstat[0]);
         return MLG_ERR_RETRY;
     }
+    if (sp) {
+        if (sp->n_rows) *sp->n_rows = nrows;
+        if (nrows > sp->cap) { mlg_set_error("result has %llu rows, the buffers hold %llu", nrows, (unsigned long long)sp->cap); return MLG_ERR_ARG; }
+        if (nrows > first) {                          // (rare) more rows than were copied ahead
+            const size_t m = (size_t)(nrows - first);
+            if (sp->genomes) CUDA_TRY(cudaMemcpyAsync(sp->genomes + first, o_g.p + first, m * 4, cudaMemcpyDeviceToHost, st));
+            if (sp->num) CUDA_TRY(cudaMemcpyAsync(sp->num + first * v.nk, o_num.p + first * v.nk, m * v.nk * 8, cudaMemcpyDeviceToHost, st));
+            if (sp->den) CUDA_TRY(cudaMemcpyAsync(sp->den + first * v.nk, o_den.p + first * v.nk, m * v.nk * 8, cudaMemcpyDeviceToHost, st));
+            if (sp->ci) CUDA_TRY(cudaMemcpyAsync(sp->ci + first * v.nk, o_ci.p + first * v.nk, m * v.nk * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        const uint64_t copied = std::max<uint64_t>(first, nrows);
+        q->st.d2h_bytes += 8 + copied * ((sp->genomes ? 4 : 0) + ((sp->num ? 8 : 0) + (sp->den ? 8 : 0) + (sp->ci ? 8 : 0)) * v.nk);
+    }
     q->n_present = (uint32_t)ni;
     q->st.n_kmers = nk_host; q->st.n_intersect = ni;
     q->st.n_bucket_fetches = v.layout >= 1 ? nk_host2[1] : nk_host;
@@ -775,6 +817,15 @@ MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* c
     if (n_intersect) *n_intersect = ni;
     q->finished = true;
     return MLG_OK;
+}
+MLG_API int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint64_t* n_intersect) {
+    return finish_impl(q, num, den, ci, nullptr, n_intersect);
+}
+MLG_API int mlg_query_finish_sparse(mlg_query* q, uint32_t* genomes, int64_t* num, int64_t* den, double* ci, uint64_t cap_rows,
+                                    uint64_t* n_rows, uint64_t* n_intersect) {
+    if (!n_rows) { mlg_set_error("null n_rows"); return MLG_ERR_ARG; }
+    SparseOut sp{genomes, num, den, ci, cap_rows, n_rows};
+    return finish_impl(q, nullptr, nullptr, nullptr, &sp, n_intersect);
 }
 
 MLG_API int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n) {
@@ -805,6 +856,16 @@ MLG_API int mlg_query_free(mlg_query* q) {
     cudaSetDevice(q->ctx->device);
     cudaStreamSynchronize(q->ctx->s_copy);
     cudaStreamSynchronize(q->ctx->s_comp);
+    // The counter table goes to the next query of this database all-zero: only the counters this query touched are
+    // visited (a dense all-reduce writes counters that are on no list, so that table is dropped instead).
+    if (q->db && q->cnt8.p && !q->reduced && !q->db->clean_cnt8.p) {
+        bool ok = true;
+        if (q->touched.p) {
+            ok = launch_clear_touched(q->cnt8.p, q->touched.p, q->d_scalar.p + 1, q->ctx->s_comp) == MLG_OK &&
+                 cudaStreamSynchronize(q->ctx->s_comp) == cudaSuccess;
+        }
+        if (ok) { std::swap(q->cnt8.p, q->db->clean_cnt8.p); std::swap(q->cnt8.n, q->db->clean_cnt8.n); }
+    }
     for (auto& pe : q->probe_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     for (auto& e : q->chunk_events) cudaEventDestroy(e);
     for (auto& s : q->stg) if (s.done) cudaEventDestroy(s.done);

@@ -104,7 +104,7 @@ struct MzWin {
     key128 cn, d0, d1;           // canonical key of the window; first two k-mers of the bucket
     uint32_t s, e, j0, j1;       // bucket range in D, alias range
 };
-__device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long long p, unsigned long long pm, bool untested,
+__device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long long p, unsigned long long pm,
                                                 const unsigned long long* bsrc, unsigned long long base_words, const DbView& db) {
     w.s = w.e = w.j0 = w.j1 = 0;
     w.cn.hi = w.cn.lo = 0; w.d0 = w.cn; w.d1 = w.cn;
@@ -113,11 +113,6 @@ __device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long
     mz_bases64(bsrc, base_words, pm, mh, ml);
     const uint32_t ha = (uint32_t)(mh >> 32), hb = rev2_32(~(uint32_t)mh);
     const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
-    if (untested) {               // a run beyond the fourth of its block: its level-1 word was not fetched ahead
-        const unsigned long long idx = mz_bit_index(((unsigned long long)zhi << 32) | zlo, db.fbits);
-        const uint32_t f = ldg_u32(db.F + (idx >> 5));
-        if (!((f >> (zlo & 31u)) & (f >> mz_bit2(zhi)) & 1u)) return;
-    }
     const uint32_t bucket = zhi >> (32u - db.bbits);
     w.s = ldg_u32(db.bstart + bucket); w.e = ldg_u32(db.bstart + bucket + 1);
     // K-mers filed under a second identity (order ties) are rare: a 2^16-bit array says whether to look at all
@@ -151,7 +146,7 @@ __device__ __forceinline__ void mz_window_end(const MzWin& w, const DbView& db, 
     }
 }
 // exact compare of every window of every waiting item of one warp, one WINDOW per lane (items have 1..16 windows)
-__device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const uint32_t* qc, const uint32_t* qb, uint32_t* qoff,
+__device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const uint32_t* qc, uint32_t* qb, uint32_t* qoff,
                                       const unsigned long long* bsrc, unsigned long long base_words, const DbView& db, const CountSink& cs) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
@@ -159,7 +154,25 @@ __device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const ui
     const uint32_t n = *qn;
     for (uint32_t base = 0; base < n; base += 32u) {
         const uint32_t i = base + lane;
-        const uint32_t cnt = i < n ? (uint32_t)__popc(qb[i] & 0xFFFFu) : 0u;
+        uint32_t kb0 = i < n ? qb[i] : 0u;
+        // Items of runs beyond the fourth of their block arrive untested (bit 31).  Their level-1 bits are looked at here,
+        // once per ITEM and 32 items at a time, before the items are spread over the lanes window by window: 99.6 % of
+        // them fail, and used to cost every one of their ~11 windows a lookup of its own.
+        if (__any_sync(FULL, (kb0 >> 31) != 0u)) {
+            if (kb0 >> 31) {
+                const unsigned long long pb = ((unsigned long long)qc[i] << 32) | qa[i];
+                unsigned long long mh, ml;
+                mz_bases64(bsrc, base_words, pb + ((kb0 >> 16) & 63u), mh, ml);
+                const uint32_t ha = (uint32_t)(mh >> 32), hb = rev2_32(~(uint32_t)mh);
+                const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
+                const unsigned long long idx = mz_bit_index(((unsigned long long)zhi << 32) | zlo, db.fbits);
+                const uint32_t f = ldg_u32(db.F + (idx >> 5));
+                kb0 = ((f >> (zlo & 31u)) & (f >> mz_bit2(zhi)) & 1u) ? (kb0 & 0x7FFFFFFFu) : 0u;
+                qb[i] = kb0;
+            }
+            __syncwarp();
+        }
+        const uint32_t cnt = (uint32_t)__popc(kb0 & 0xFFFFu);
         uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += u; }
@@ -174,7 +187,7 @@ __device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const ui
             const uint32_t tt = __fns(kb & 0xFFFFu, 0u, (int)(w - qoff[j]) + 1);
             const unsigned long long pb = ((unsigned long long)qc[base + j] << 32) | qa[base + j];
             MzWin win;
-            mz_window_begin(win, true, pb + tt, pb + ((kb >> 16) & 63u), (kb >> 31) != 0u, bsrc, base_words, db);
+            mz_window_begin(win, true, pb + tt, pb + ((kb >> 16) & 63u), bsrc, base_words, db);
             mz_window_end(win, db, cs);
         }
         __syncwarp();
@@ -475,368 +488,20 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
     if (lane == 0 && my_fetch) atomicAdd(a.n_kmers + 1, (unsigned long long)my_fetch);
 }
 
-// ======================================================================================================
-// K1, run-queue form of the same kernel (MLG_PROBE_MZ=q; database structures unchanged).  One lane per read walks its
-// windows as above, but the LOOKUPS are no longer tied to the lane that found the run: a lane has 0..16 runs per block
-// of 16 windows (1.4 on average) and a warp executes what its busiest lane needs, so four lookup slots per lane ran at a
-// third of their capacity, and runs beyond the fourth went to the exact path untested.  Here every run that needs its own
-// lookup becomes a 32-bit entry in a per-warp queue (warp prefix sum + a short loop); the queue is consumed 32 entries per
-// round, any lane serving any lane's run (the minimizer's halves come from the owner's segment copy in shared memory).
-// Two blocks of 16 windows are walked per pass: the level-1 words of a pass's runs are loaded at the START of the next
-// pass and looked at after its two walks, inside one loop body like before.
-//   entry / meta word: lane 0-4 | first window of the run in its block 5-8 | block 9-11 | minimizer base in the segment 12-19 |
-//                      run reaches the end of its block 20 | bit positions of the two level-1 bits 21-25, 26-30 | valid 31
-// A run that crosses into the next block is not looked up again: its owner lane inherits the verdict (lastpass[block][lane])
-// once the pass that carries it has been resolved.
-constexpr unsigned MQ_RQCAP = 640;             // queued lookups per warp; a block adds at most 16 x 32, the rest is flushed before
-constexpr unsigned MQ_QCAP = MZ_QDRAIN + 128;  // items: every round of verdicts and every continuation step adds at most 32 and is followed by a drain check
-constexpr unsigned MQ_ROUNDS = 4;              // lookup rounds whose words stay in registers across a pass
-constexpr unsigned MQ_BLOCKS = WMAX / 16;
-struct MqShared {
-    SkStage stg;
-    uint32_t wm[MZ_LIST][RT];                 // [r][thread]: value of the r-th run start of the current block (row 0 = window 0's)
-    uint32_t seq[SEGW + 1][RT];               // [word][thread]: the lane's current segment
-    uint32_t cv[MQ_BLOCKS][RT];               // [block][thread]: valid windows (bits 0-15) | windows where a run with its own lookup starts << 16
-    uint32_t r0lo[RT], r0hi[RT];              // stream position of the lane's read
-    unsigned char lastpass[MQ_BLOCKS][RT];    // verdict of the run that reaches the end of (block, lane)
-    unsigned char pos0[MQ_BLOCKS][RT];        // minimizer base of window 0's run, relative to the block
-    uint32_t rq[WARPS][MQ_RQCAP];
-    uint32_t qa[WARPS][MQ_QCAP], qc[WARPS][MQ_QCAP], qb[WARPS][MQ_QCAP];
-    uint32_t qoff[WARPS][32];
-    uint32_t qn[WARPS];
-};
-
-template <bool HAS_NMASK>
-__global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe_q(ProbeArgs a, DbView db) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    MqShared& sm = *reinterpret_cast<MqShared*>(smem_raw);
-    SkStage& stg = sm.stg;
-    __shared__ __align__(8) unsigned long long mbar[WARPS][2];
-    __shared__ unsigned long long s_bw0[WARPS][2], s_mw0[WARPS][2];
-    __shared__ unsigned s_staged[WARPS][2];
-
-    const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-    constexpr unsigned K = SK_K;
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    const unsigned long long nreads = a.r_end - a.r_begin;
-    const unsigned long long ntiles = (nreads + 31) / 32;
-    auto next_tile = [&]() -> unsigned long long {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
-        return __shfl_sync(FULL, t, 0);
-    };
-    const unsigned long long pol_stream = policy_evict_first();
-    const CountSink sink{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
-    const uint32_t wm_base = smem_u32(&sm.wm[0][tid]), seq_base = smem_u32(&sm.seq[0][tid]);
-    const uint32_t seq_warp = smem_u32(&sm.seq[0][warp * 32u]);
-    const uint32_t* const MB = db.F;
-    const uint32_t fmask_lo = db.fbits >= 32u ? 0xFFFFFFFFu : ((1u << db.fbits) - 1u);
-    const uint32_t fmask_hi = db.fbits > 32u ? ((1u << (db.fbits - 32u)) - 1u) : 0u;
-
-    if (lane == 0) {
-        mbar_init(&mbar[warp][0], 1);
-        mbar_init(&mbar[warp][1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](unsigned stage, unsigned long long t) {
-        const unsigned long long r0 = a.r_begin + t * 32ull;
-        const unsigned long long r1 = (r0 + 32 < a.r_end) ? r0 + 32 : a.r_end;
-        const unsigned long long p0 = a.off ? a.off[r0] : r0 * (unsigned long long)a.read_len;
-        const unsigned long long p1 = a.off ? a.off[r1] : r1 * (unsigned long long)a.read_len;
-        unsigned long long bw0 = (p0 >> 5) & ~1ull;
-        unsigned long long bw1 = ((p1 + 31) >> 5) + 6;
-        if (bw1 > a.base_words) bw1 = a.base_words;
-        bw1 = (bw1 + 1) & ~1ull;
-        unsigned long long mw0 = (p0 >> 6) & ~1ull;
-        unsigned long long mw1 = ((p1 + 63) >> 6) + 4;
-        if (HAS_NMASK) { if (mw1 > a.nmask_words) mw1 = a.nmask_words; mw1 = (mw1 + 1) & ~1ull; }
-        const unsigned long long bytes_b = (bw1 - bw0) * 8ull, bytes_m = HAS_NMASK ? (mw1 - mw0) * 8ull : 0ull;
-        const bool fits = bw1 > bw0 && bytes_b <= WSTAGE_B && bytes_m <= WSTAGE_M;
-        s_bw0[warp][stage] = bw0; s_mw0[warp][stage] = mw0; s_staged[warp][stage] = fits ? 1u : 0u;
-        if (fits) {
-            mbar_expect_tx(&mbar[warp][stage], (uint32_t)(bytes_b + bytes_m));
-            bulk_g2s(&stg.b[warp][stage][0], a.bases + bw0, (uint32_t)bytes_b, &mbar[warp][stage], pol_stream);
-            if (HAS_NMASK && bytes_m) bulk_g2s(&stg.m[warp][stage][0], a.nmask + mw0, (uint32_t)bytes_m, &mbar[warp][stage], pol_stream);
-        } else {
-            mbar_arrive(&mbar[warp][stage]);
-        }
-    };
-
-    unsigned long long my_valid = 0;
-    unsigned my_fetch = 0;
-    const unsigned long long* bsrc = a.bases;
-    if (lane == 0) sm.qn[warp] = 0;
-    __syncwarp();
-
-    auto drain = [&]() {
-        mz_drain(&sm.qn[warp], &sm.qa[warp][0], &sm.qc[warp][0], &sm.qb[warp][0], &sm.qoff[warp][0], a.bases, a.base_words, db, sink);
-    };
-    auto push = [&](bool p, unsigned long long pb, uint32_t ik, uint32_t rel) {
-        if (p) {
-            const uint32_t i = atomicAdd(&sm.qn[warp], 1u);
-            sm.qa[warp][i] = (uint32_t)pb; sm.qc[warp][i] = (uint32_t)(pb >> 32); sm.qb[warp][i] = ik | (rel << 16);
-        }
-    };
-    auto drain_if_full = [&]() {
-        __syncwarp();
-        if (sm.qn[warp] >= MZ_QDRAIN) drain();
-    };
-
-    unsigned it = 0;
-    unsigned long long t = next_tile(), t_ahead = next_tile();
-    if (lane == 0) {
-        if (t < ntiles) issue(0, t);
-        if (t_ahead < ntiles) issue(1, t_ahead);
-    }
-    for (; t < ntiles; ++it) {
-        const unsigned stage = it & 1u, parity = (it >> 1) & 1u;
-        __syncwarp();
-        mbar_wait(&mbar[warp][stage], parity);
-
-        const unsigned long long r = a.r_begin + t * 32ull + lane;
-        const bool active = r < a.r_end;
-        unsigned long long R0 = 0, R1 = 0;
-        if (active) {
-            R0 = a.off ? a.off[r] : r * (unsigned long long)a.read_len;
-            R1 = a.off ? a.off[r + 1] : R0 + a.read_len;
-        }
-        const unsigned long long len = R1 - R0;
-        const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
-        const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
-        const unsigned max_seg = __reduce_max_sync(FULL, nseg);
-        const bool staged = s_staged[warp][stage] != 0;
-        bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[warp][stage][0]) - s_bw0[warp][stage] : a.bases;
-        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[warp][stage][0]) - s_mw0[warp][stage] : a.nmask;
-        sm.r0lo[tid] = (uint32_t)R0; sm.r0hi[tid] = (uint32_t)(R0 >> 32);
-        __syncwarp();
-
-        for (unsigned seg = 0; seg < max_seg; ++seg) {
-            const unsigned c = seg < nseg ? (unsigned)((nw - (unsigned long long)seg * WMAX) < WMAX ? (nw - (unsigned long long)seg * WMAX) : WMAX) : 0u;
-            const unsigned long long s = R0 + (unsigned long long)seg * WMAX;
-            const uint32_t segw = seg * WMAX;
-
-            uint32_t loc[SEGW];
-            uint32_t nl[5];
-            segment_load<HAS_NMASK>(loc, nl, c, s, bsrc, msrc, a.base_words, a.nmask_words);
-            uint32_t v0, v1, v2;
-            segment_valid<HAS_NMASK>(nl, c, K, v0, v1, v2);
-            my_valid += __popc(v0) + __popc(v1) + __popc(v2);
-            if (__all_sync(FULL, (v0 | v1 | v2) == 0u)) continue;
-
-#pragma unroll
-            for (int k = 0; k < (int)SEGW; ++k) sts32(seq_base + (uint32_t)k * MZ_ROW, loc[k]);
-            sts32(seq_base + SEGW * MZ_ROW, 0u);
-            uint32_t rcl[SEGW];
-            segment_rc60(loc, rcl);
-            uint32_t P = 0xFFFFFFFFu;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) P = min(P, mz_val(loc, rcl, 1, i));
-
-            // one lookup: entry -> the owner's minimizer halves -> identity -> level-1 word index and bit positions
-            auto locate = [&](bool on, uint32_t ent, uint32_t& meta) -> uint32_t {
-                const uint32_t L = ent & 31u, Pm = (ent >> 12) & 255u;
-                const uint32_t ad = seq_warp + L * 4u + (Pm >> 4) * MZ_ROW;
-                const uint32_t w0 = lds32(ad), w1 = lds32(ad + MZ_ROW), w2 = lds32(ad + 2u * MZ_ROW);
-                const unsigned sh = 2u * (Pm & 15u);
-                const uint32_t ha = fsl(w0, w1, sh), hb = rev2_32(~fsl(w1, w2, sh));
-                const uint32_t zlo = mz_ident_lo(ha, hb) & fmask_lo, zhi = mz_ident_hi(ha, hb);
-                meta = (ent & 0x1FFFFFu) | ((zlo & 31u) << 21) | (mz_bit2(zhi) << 26) | (on ? 0x80000000u : 0u);
-                return (zlo >> 5) | ((zhi & fmask_hi) << 27);
-            };
-            // verdict of one lookup: note it for a run that goes on into the next block; a passing run becomes an item
-            auto settle = [&](uint32_t f, uint32_t meta) {
-                const bool on = (meta >> 31) != 0u;
-                const bool pass = on && (((f >> ((meta >> 21) & 31u)) & (f >> ((meta >> 26) & 31u)) & 1u) != 0u);
-                const uint32_t L = meta & 31u, tt = (meta >> 5) & 15u, be = (meta >> 9) & 7u;
-                if (on && ((meta >> 20) & 1u)) sm.lastpass[be][warp * 32u + L] = pass ? 1 : 0;
-                if (__any_sync(FULL, pass)) {
-                    uint32_t mask = 0;
-                    unsigned long long ia = 0;
-                    if (pass) {
-                        const uint32_t cvw = sm.cv[be][warp * 32u + L];
-                        const uint32_t above = (cvw >> 16) & ~((2u << tt) - 1u);
-                        const uint32_t nxt = above ? (above & (0u - above)) : 0x10000u;
-                        mask = (nxt - (1u << tt)) & cvw & 0xFFFFu;
-                        ia = (((unsigned long long)sm.r0hi[warp * 32u + L] << 32) | sm.r0lo[warp * 32u + L]) + segw + be * 16u;
-                    }
-                    push(mask != 0u, ia, mask, ((meta >> 12) & 255u) - be * 16u);
-                    drain_if_full();
-                }
-            };
-            // window 0's run of block b goes on from block b - 1 (no lookup of its own): inherit the verdict
-            auto resolve = [&](uint32_t b) {
-                const uint32_t cvw = sm.cv[b][tid], starts = cvw >> 16;
-                bool go = false;
-                uint32_t m0 = 0;
-                if (!(starts & 1u)) {
-                    const bool p0 = sm.lastpass[b - 1u][tid] != 0;
-                    const uint32_t nxt = starts ? (starts & (0u - starts)) : 0x10000u;
-                    m0 = (nxt - 1u) & cvw & 0xFFFFu;
-                    go = p0 && m0 != 0u;
-                    if (starts == 0u) sm.lastpass[b][tid] = p0 ? 1 : 0;
-                }
-                if (__any_sync(FULL, go)) {
-                    push(go, R0 + segw + b * 16u, m0, sm.pos0[b][tid]);
-                    drain_if_full();
-                }
-            };
-
-            uint32_t rqn = 0;                               // lookups queued by the pass before (warp-uniform)
-            uint32_t held_wm = 0xFFFFFFFFu;                 // value of the run the lane is in, re-based to the coming block
-            bool more = true;
-#pragma unroll 1
-            for (uint32_t pass_i = 0;; ++pass_i) {
-                // ---- the level-1 words of the lookups queued by the previous pass: up to MQ_ROUNDS rounds stay in registers
-                const uint32_t n_pend = rqn, nr = (n_pend + 31u) >> 5;
-                uint32_t F0 = 0, F1 = 0, F2 = 0, F3 = 0, M0 = 0, M1 = 0, M2 = 0, M3 = 0;
-                if (nr > 0u) { const uint32_t i = lane;       const bool on = i < n_pend; F0 = ldg_bitmap_if(on, MB + locate(on, on ? sm.rq[warp][i] : 0u, M0)); my_fetch += on ? 1u : 0u; }
-                if (nr > 1u) { const uint32_t i = 32u + lane; const bool on = i < n_pend; F1 = ldg_bitmap_if(on, MB + locate(on, on ? sm.rq[warp][i] : 0u, M1)); my_fetch += on ? 1u : 0u; }
-                if (nr > 2u) { const uint32_t i = 64u + lane; const bool on = i < n_pend; F2 = ldg_bitmap_if(on, MB + locate(on, on ? sm.rq[warp][i] : 0u, M2)); my_fetch += on ? 1u : 0u; }
-                if (nr > 3u) { const uint32_t i = 96u + lane; const bool on = i < n_pend; F3 = ldg_bitmap_if(on, MB + locate(on, on ? sm.rq[warp][i] : 0u, M3)); my_fetch += on ? 1u : 0u; }
-#pragma unroll 1
-                for (uint32_t j = MQ_ROUNDS; j < nr; ++j) {  // more rounds than registers (rare): looked at on the spot
-                    const uint32_t i = j * 32u + lane;
-                    const bool on = i < n_pend;
-                    uint32_t Mx;
-                    const uint32_t Fx = ldg_bitmap_if(on, MB + locate(on, on ? sm.rq[warp][i] : 0u, Mx));
-                    my_fetch += on ? 1u : 0u;
-                    settle(Fx, Mx);
-                }
-                rqn = 0;
-                __syncwarp();                                // every lane has read its entries: the queue may be refilled
-                // ---- walk two blocks of 16 windows; their runs are queued for the next pass
-                if (more) {
-#pragma unroll 1
-                    for (uint32_t sub = 0; sub < 2u; ++sub) {
-                        const uint32_t blk = 2u * pass_i + sub, blk16 = blk * 16u;
-                        const uint32_t vb = v0 & 0xFFFF0000u;
-                        v0 = fsl(v0, v1, 16); v1 = fsl(v1, v2, 16); v2 <<= 16;
-                        uint32_t chgraw = 0, wm_first = 0;
-                        {
-                            uint32_t Suf[16];
-                            {
-                                uint32_t smn = 0xFFFFFFFFu;
-#pragma unroll
-                                for (int i = 15; i >= 0; --i) { smn = min(smn, mz_val(loc, rcl, 0, i)); Suf[i] = smn; }
-                            }
-                            uint32_t A1 = 0, pw = 0;
-                            uint32_t lst = wm_base + MZ_ROW;
-#pragma unroll
-                            for (int tt = 0; tt < 16; ++tt) {
-                                uint32_t wm;
-                                if (tt < 4) {
-                                    P = min(P, mz_val(loc, rcl, 1, 12 + tt));
-                                    wm = min(Suf[tt], P);
-                                    if (tt == 3) { A1 = P; P = 0xFFFFFFFFu; }
-                                } else {
-                                    P = min(P, mz_val(loc, rcl, 2, tt - 4));
-                                    wm = min(min(Suf[tt], A1), P);
-                                }
-                                if (tt == 0) wm_first = wm;
-                                else if (wm != pw) {
-                                    sts32(lst, wm);
-                                    lst += MZ_ROW;
-                                    chgraw |= 1u << tt;
-                                }
-                                pw = wm;
-                            }
-                            P -= 16u;
-                            // the run that reaches the end of this block, re-based to the next one
-                            const uint32_t lastv = pw;
-                            const uint32_t vwin = __brev(vb) & 0xFFFFu;
-                            const bool new0 = wm_first != held_wm;
-                            held_wm = vwin ? lastv - 16u : 0xFFFFFFFFu;   // nothing valid here: the next block starts afresh
-                            const uint32_t starts = vwin ? (chgraw | (new0 ? 1u : 0u)) : 0u;
-                            sm.cv[blk][tid] = vwin | (starts << 16);
-                            sm.pos0[blk][tid] = (unsigned char)(wm_first & 63u);
-                            sts32(wm_base, wm_first);
-                            // queue positions: exclusive prefix sum of the lanes' counts
-                            const uint32_t cnt = __popc(starts);
-                            uint32_t inc = cnt;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += u; }
-                            const uint32_t tot = __shfl_sync(FULL, inc, 31);
-                            if (rqn + tot > MQ_RQCAP) {       // (rare) no room: look the queued ones up now
-                                __syncwarp();
-#pragma unroll 1
-                                for (uint32_t j = 0; j * 32u < rqn; ++j) {
-                                    const uint32_t i = j * 32u + lane;
-                                    const bool on = i < rqn;
-                                    uint32_t Mx;
-                                    const uint32_t Fx = ldg_bitmap_if(on, MB + locate(on, on ? sm.rq[warp][i] : 0u, Mx));
-                                    my_fetch += on ? 1u : 0u;
-                                    settle(Fx, Mx);
-                                }
-                                rqn = 0;
-                                __syncwarp();
-                            }
-                            uint32_t at = rqn + inc - cnt, rest = starts, row = new0 ? 0u : 1u;
-                            const uint32_t maxc = __reduce_max_sync(FULL, cnt);
-                            for (uint32_t k = 0; k < maxc; ++k) {
-                                if (rest) {
-                                    const uint32_t low = rest & (0u - rest);
-                                    rest ^= low;
-                                    const uint32_t tt = 31u - (uint32_t)__clz(low);
-                                    const uint32_t w = lds32(wm_base + row * MZ_ROW);
-                                    ++row;
-                                    sm.rq[warp][at++] = lane | (tt << 5) | (blk << 9) | ((blk16 + (w & 63u)) << 12) | (rest ? 0u : (1u << 20));
-                                }
-                            }
-                            rqn += tot;
-                        }
-                        // slide the register windows by one word
-#pragma unroll
-                        for (int k = 0; k < (int)SEGW - 1; ++k) loc[k] = loc[k + 1];
-#pragma unroll
-                        for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
-                    }
-                }
-                // ---- the previous pass's words have had two walks to arrive
-                if (nr > 0u) settle(F0, M0);
-                if (nr > 1u) settle(F1, M1);
-                if (nr > 2u) settle(F2, M2);
-                if (nr > 3u) settle(F3, M3);
-                __syncwarp();                                // verdicts written by other lanes are visible to their owners
-                if (pass_i >= 1u) {
-                    resolve(2u * pass_i - 1u);
-                    if (more) resolve(2u * pass_i);
-                }
-                if (!more) break;
-                more = pass_i + 1u < MQ_BLOCKS / 2u && !__all_sync(FULL, (v0 | v1 | v2) == 0u);
-                __syncwarp();                                // queue entries written above are visible to every lane
-            }
-        }
-        __syncwarp();
-        const unsigned long long t_new = next_tile();
-        if (lane == 0 && t_new < ntiles) issue(stage, t_new);
-        t = t_ahead; t_ahead = t_new;
-    }
-
-    drain();
-    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(FULL, my_valid, o);
-    my_fetch = __reduce_add_sync(FULL, my_fetch);
-    if (lane == 0 && my_valid) atomicAdd(a.n_kmers, my_valid);
-    if (lane == 0 && my_fetch) atomicAdd(a.n_kmers + 1, (unsigned long long)my_fetch);
-}
-constexpr size_t K1MQ_SMEM = sizeof(MqShared);
-
 constexpr size_t K1MZ_SMEM = sizeof(MzShared);
 
-template <bool HAS_NMASK, bool QUEUE>
+template <bool HAS_NMASK>
 int launch_mz_t(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned grid) {
-    auto kern = QUEUE ? k1_minimizer_probe_q<HAS_NMASK> : k1_minimizer_probe<HAS_NMASK>;
-    const size_t smem = QUEUE ? K1MQ_SMEM : K1MZ_SMEM;
+    auto kern = k1_minimizer_probe<HAS_NMASK>;
     static bool done[64] = {};          // the attribute is per device
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !done[dev]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1MZ_SMEM));
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
     CUDA_TRY(cudaMemsetAsync(a.tile_counter, 0, 8, st));
-    kern<<<grid, RT, smem, st>>>(a, db);
+    kern<<<grid, RT, K1MZ_SMEM, st>>>(a, db);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }
@@ -852,8 +517,5 @@ int launch_probe_mz(const DbView& db, const ProbeArgs& a, cudaStream_t st, int s
     if (const char* e = getenv("MLG_PROBE_CTAS_PER_SM")) { int x = atoi(e); if (x >= 1 && x <= 64) per_sm = x; }
     const unsigned long long res = (unsigned long long)sm_count * (unsigned)per_sm;
     const unsigned grid = (unsigned)(need < res ? need : res);
-    static int queue_form = -1;         // MLG_PROBE_MZ=q: the run-queue form of the kernel; classic: the round-2 form
-    if (queue_form < 0) { const char* e = getenv("MLG_PROBE_MZ"); queue_form = (e && e[0] == 'q') ? 1 : 0; }
-    if (queue_form) return a.nmask ? launch_mz_t<true, true>(db, a, st, grid) : launch_mz_t<false, true>(db, a, st, grid);
-    return a.nmask ? launch_mz_t<true, false>(db, a, st, grid) : launch_mz_t<false, false>(db, a, st, grid);
+    return a.nmask ? launch_mz_t<true>(db, a, st, grid) : launch_mz_t<false>(db, a, st, grid);
 }

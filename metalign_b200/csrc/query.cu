@@ -319,6 +319,31 @@ __global__ void k_finalize(const unsigned long long* num, const long long* den_r
     out_ci[c] = nu > 0 ? (double)nu / (double)de : 0.0;
 }
 
+// sparse form of the result: one row per genome with a hit at any k (unordered; the caller sorts the few rows by genome)
+__global__ void k_finalize_sparse(const unsigned long long* num, const long long* den_real, const unsigned char* has_empty, uint32_t G,
+                                  uint32_t nk, int count_empty, uint32_t* out_g, long long* out_num, long long* out_den, double* out_ci,
+                                  unsigned long long cap, unsigned long long* counter) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    unsigned long long any = 0;
+    for (uint32_t k = 0; k < nk; ++k) any |= num[(size_t)g * nk + k];
+    if (!any) return;
+    const unsigned long long r = atomicAdd(counter, 1ull);
+    if (r >= cap) return;
+    out_g[r] = g;
+    const long long extra = (count_empty && has_empty[g]) ? 1 : 0;
+    for (uint32_t k = 0; k < nk; ++k) {
+        const long long nu = (long long)num[(size_t)g * nk + k], de = den_real[(size_t)g * nk + k] + extra;
+        out_num[r * nk + k] = nu; out_den[r * nk + k] = de;
+        out_ci[r * nk + k] = nu > 0 ? (double)nu / (double)de : 0.0;
+    }
+}
+// put a query's counter table back to all zeros by visiting only the counters it touched (the table is >99.9 % zeros)
+__global__ void k_clear_touched(unsigned char* cnt8, const uint32_t* __restrict__ touched, const unsigned long long* __restrict__ d_n) {
+    const unsigned long long n = *d_n;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        cnt8[touched[i]] = 0;
+}
 // clamp the counters that are non-zero (listed in touched[]) to ci_min: what a rank contributes to the cross-rank sum
 __global__ void k_clamp_counts(unsigned char* cnt8, const uint32_t* __restrict__ touched, const unsigned long long* __restrict__ d_n,
                                uint32_t ci_min) {
@@ -634,6 +659,19 @@ int launch_finalize(const unsigned long long* num, const long long* den_real, co
                     uint32_t nk, int count_empty, long long* out_num, long long* out_den, double* out_ci, cudaStream_t st) {
     unsigned long long cells = (unsigned long long)G * nk;
     k_finalize<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(num, den_real, has_empty, G, nk, count_empty, out_num, out_den, out_ci);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_finalize_sparse(const unsigned long long* num, const long long* den_real, const unsigned char* has_empty, uint32_t G, uint32_t nk,
+                           int count_empty, uint32_t* out_g, long long* out_num, long long* out_den, double* out_ci, unsigned long long cap,
+                           unsigned long long* d_counter, cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(d_counter, 0, 8, st));
+    k_finalize_sparse<<<(G + 255) / 256, 256, 0, st>>>(num, den_real, has_empty, G, nk, count_empty, out_g, out_num, out_den, out_ci, cap, d_counter);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_clear_touched(unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, cudaStream_t st) {
+    k_clear_touched<<<148u * 2u, 256, 0, st>>>(cnt8, touched, d_n_touched);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }

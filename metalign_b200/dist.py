@@ -101,10 +101,20 @@ EXCHANGE_MODES = ("sparse", "dense", "p2p")
 
 
 def exchange_mode() -> str:
-    m = os.environ.get("MLG_EXCHANGE", "sparse")
+    """MLG_EXCHANGE, default "p2p" (the direct NVLink-store form; if the ranks cannot map each other's memory it falls
+    back to "sparse", the NCCL all-gather of the same blocks)"""
+    m = os.environ.get("MLG_EXCHANGE", "p2p")
     if m not in EXCHANGE_MODES:
         raise ValueError("MLG_EXCHANGE must be one of %s" % (EXCHANGE_MODES,))
     return m
+
+
+def effective_mode(ctx, mode: str) -> str:
+    """the form the exchange of this context really takes ("p2p" degrades to "sparse" when peer mapping failed)"""
+    for key, cur in _EXCHANGES.items():
+        if key[0] == id(ctx) and mode == "p2p" and cur.get("p2p_failed"):
+            return "sparse"
+    return mode
 
 
 def describe_exchange(mode: str, world: int) -> str:
@@ -144,14 +154,24 @@ def _get_exchange(ctx, device: int, group, p2p: bool, cap: int = 0):
         recv = device_view_i64(ex.recv_ptr, ex.block_words * world, device)
         cur = dict(ex=ex, send=send, recv=recv, connected=False)
         _EXCHANGES[key] = cur
-    if p2p and not cur["connected"]:
+    if p2p and not cur["connected"] and not cur.get("p2p_failed"):
         mine = torch.frombuffer(bytearray(cur["ex"].local_handle()), dtype=torch.uint8)
-        if dist.get_backend(group) == "nccl":
+        on_gpu = dist.get_backend(group) == "nccl"
+        if on_gpu:
             mine = mine.to("cuda:%d" % device)
         allh = torch.empty(64 * world, dtype=torch.uint8, device=mine.device)
         dist.all_gather_into_tensor(allh, mine, group=group)
-        cur["ex"].connect(bytes(allh.cpu().numpy().tobytes()))
-        cur["connected"] = True
+        ok = 1
+        try:
+            cur["ex"].connect(bytes(allh.cpu().numpy().tobytes()))
+        except Exception as e:  # noqa: BLE001  (no peer access / IPC not permitted in this container)
+            ok, cur["p2p_error"] = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=mine.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)       # every rank takes the same path
+        if int(flag.item()):
+            cur["connected"] = True
+        else:
+            cur["p2p_failed"] = True
     return cur
 
 
@@ -177,7 +197,7 @@ def reduce_query(query, device: int = 0, group=None, mode: str = None) -> None:
 
     def run(cap=0):
         st = _get_exchange(ctx, device, group, mode == "p2p", cap)
-        if mode == "p2p":
+        if mode == "p2p" and st["connected"]:
             query.exchange_p2p(st["ex"])
         else:
             query.exchange_pack(st["ex"])

@@ -145,9 +145,9 @@ def run_cmash_and_cutoff(args, taxid2info):
         from . import cmash_tail, codec
         ctx, db, query = args._mlg
         cmash_out = args.temp_dir + "cmash_query_results.csv"
-        res = query.finish()
+        res = query.finish_sparse()                       # rows for the genomes with a hit: all the CSV can hold
         _tick("containment table")
-        cmash_tail.write_results_csv(cmash_out, db.names, db.ks, res["ci"], 0.0)      # '-c 0'
+        cmash_tail.write_results_csv_sparse(cmash_out, db.names, db.ks, res["genomes"], res["ci"], 0.0)      # '-c 0'
         _tick("csv written")
         if args.keep_temp_files:
             with open(args.temp_dir + "60mers_intersection_dump", "w") as fh:

@@ -203,6 +203,27 @@ def test_mlgdb_roundtrip(ctx, workload, tmp_path):
     db.close()
 
 
+def test_sparse_result_and_table_reuse(ctx, workload):
+    """finish_sparse: the rows of the genomes with a hit at any k, equal to the dense table's non-zero rows -- also with
+    room for fewer rows than there are (the call is repeated), and for several queries in a row on one database (the
+    counter table is handed on, cleared entry by entry, instead of being zeroed as a whole)"""
+    w = workload
+    p = w["p"]
+    db = Database.from_keys(ctx, w["keys"], p.G, p.n, 60, KS)
+    for rep, (gate, cap) in enumerate((("exact", 1 << 16), ("none", 3), ("exact", 1 << 16))):
+        ref, I_ref = w["refs"][gate]
+        q = db.query(2, gate, True)
+        q.push_packed(w["bases"], w["nmask"], None, w["nreads"], p.read_len)
+        res = q.finish_sparse(cap)
+        rows = np.flatnonzero(ref["num"].sum(axis=1) > 0)
+        assert rows.size > 3 and np.array_equal(res["genomes"], rows.astype(np.uint32)), (rep, gate)
+        assert np.array_equal(res["num"], ref["num"][rows]) and np.array_equal(res["den"], ref["den"][rows])
+        assert np.array_equal(res["ci"], ref["ci"][rows]) and res["n_intersect"] == ref["n_intersect"]
+        assert np.array_equal(q.intersection(), I_ref)
+        q.close()
+    db.close()
+
+
 def test_built_database_file(ctx, workload, tmp_path, monkeypatch):
     """the built form of a database (mlg_db_save: the device structures themselves) loads to the same answers for both
     gates, keeps the names, refuses a file of another build tag, and cannot be written from a database that kept P"""

@@ -74,6 +74,25 @@ def test_cmash_tail_csv_format(tmp_path):
     assert np.array_equal(back.values, out.values)
 
 
+def test_cmash_tail_sparse_rows_give_the_same_bytes(tmp_path):
+    """the tail fed with rows of the genomes that have a hit (Query.finish_sparse) == the tail fed with the dense table,
+    byte for byte, ties in the sort column included (CMash filters before it sorts, so the sort input is identical)"""
+    rng = np.random.default_rng(11)
+    G = 5000
+    names = ["taxid_%d_genomic.fna.gz" % i for i in range(G)]
+    ci = np.zeros((G, 4))
+    hit = np.sort(rng.choice(G, 900, replace=False))
+    ci[hit, 0] = rng.integers(1, 40, hit.size) / 1000.0                      # k=30 hits ...
+    top = hit[rng.random(hit.size) < 0.6]
+    ci[top, 3] = rng.integers(1, 12, top.size) / 1000.0                      # ... some with k=60 hits, full of ties
+    ci[top, 1] = ci[top, 2] = ci[top, 3]
+    dense, sparse = str(tmp_path / "dense.csv"), str(tmp_path / "sparse.csv")
+    cmash_tail.write_results_csv(dense, names, (30, 40, 50, 60), ci)
+    cmash_tail.write_results_csv_sparse(sparse, names, (30, 40, 50, 60), hit.astype(np.uint32), ci[hit])
+    assert open(dense, "rb").read() == open(sparse, "rb").read()
+    assert len(open(dense).read().splitlines()) == 1 + top.size
+
+
 def _write(path, text, gz=False):
     if gz:
         with gzip.open(path, "wt") as f:
