@@ -47,6 +47,16 @@ int mlgi_spilled_runs(mlgi_reader* r, uint32_t* nruns, uint64_t cap_runs);
 int mlgi_stats(mlgi_reader* r, uint64_t* reads, uint64_t* bases, uint64_t* text_bytes);
 void mlgi_close(mlgi_reader* r);
 
+/* KMC k-mer databases (<prefix>.kmc_pre / .kmc_suf, both layouts) -- the artefacts scripts/select_db.py:44,50-56 of the
+ * reference hands between kmc, kmc_tools and kmc_dump.  keys: total x (hi, lo) 2k-bit integers, first base most significant
+ * (the key form of include/metalign_b200.h), in file order; k <= 63.  UNPINNED against files made by a real kmc. */
+typedef struct mlgi_kmcdb mlgi_kmcdb;
+int mlgi_kmc_open(const char* prefix, mlgi_kmcdb** out);
+int mlgi_kmc_info(mlgi_kmcdb* d, uint32_t* k, uint64_t* total, uint32_t* counter_size, uint32_t* min_count, uint64_t* max_count,
+                  int* canonical, uint32_t* version);
+int mlgi_kmc_read(mlgi_kmcdb* d, uint64_t* keys, uint32_t* counts_or_null);
+void mlgi_kmc_close(mlgi_kmcdb* d);
+
 #ifdef __cplusplus
 }
 #endif

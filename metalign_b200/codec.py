@@ -153,3 +153,33 @@ def _pad16(a: np.ndarray) -> np.ndarray:
     if pad or a.size == 0:
         a = np.concatenate([a, np.zeros(pad if a.size else 16, dtype=np.uint8)])
     return np.ascontiguousarray(a)
+
+
+def _rev2_64(x: np.ndarray) -> np.ndarray:
+    """reverse the order of the 32 two-bit groups of every uint64"""
+    x = x.astype(np.uint64)
+    for sh, m in ((2, 0x3333333333333333), (4, 0x0F0F0F0F0F0F0F0F), (8, 0x00FF00FF00FF00FF), (16, 0x0000FFFF0000FFFF)):
+        m = np.uint64(m)
+        x = ((x >> np.uint64(sh)) & m) | ((x & m) << np.uint64(sh))
+    return (x >> np.uint64(32)) | (x << np.uint64(32))
+
+
+def canonical_keys(keys: np.ndarray, K: int) -> np.ndarray:
+    """(n, 2) uint64 (hi, lo) keys of K-mers -> their canonical forms (the smaller of k-mer and reverse complement),
+    vectorised; same arithmetic as key_canon in csrc/kmer.cuh"""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1, 2)
+    hi, lo = keys[:, 0], keys[:, 1]
+    fhi, flo = _rev2_64(~lo), _rev2_64(~hi)              # all 64 groups of the complemented value, reversed
+    s = 128 - 2 * K                                      # drop the groups that came from the zero padding
+    if s >= 64:
+        rlo, rhi = fhi >> np.uint64(s - 64), np.zeros_like(fhi)
+    elif s == 0:
+        rlo, rhi = flo, fhi
+    else:
+        rlo = (flo >> np.uint64(s)) | (fhi << np.uint64(64 - s))
+        rhi = fhi >> np.uint64(s)
+    take_rc = (rhi < hi) | ((rhi == hi) & (rlo < lo))
+    out = keys.copy()
+    out[take_rc, 0] = rhi[take_rc]
+    out[take_rc, 1] = rlo[take_rc]
+    return out

@@ -42,6 +42,7 @@
 #include <chrono>
 #include "../../include/metalign_b200_ingest.h"
 #include "fast_inflate.h"
+#include "kmcdb.h"
 
 #define MLGI_API __attribute__((visibility("default")))
 
@@ -849,6 +850,35 @@ MLGI_API int mlgi_test_inflate(const uint8_t* in, uint64_t n, uint8_t* out, uint
     *out_n = (uint64_t)(o - out);
     return 0;
 }
+
+// ---- KMC database reader (kmcdb.h) ----
+struct mlgi_kmcdb { kmcdb::Reader r; };
+MLGI_API int mlgi_kmc_open(const char* prefix, mlgi_kmcdb** out) {
+    if (!prefix || !out) { set_error("null argument"); return -2; }
+    std::unique_ptr<mlgi_kmcdb> d(new mlgi_kmcdb());
+    if (!d->r.open(prefix)) { set_error("%s", d->r.error.c_str()); return -3; }
+    *out = d.release();
+    return 0;
+}
+MLGI_API int mlgi_kmc_info(mlgi_kmcdb* d, uint32_t* k, uint64_t* total, uint32_t* counter_size, uint32_t* min_count, uint64_t* max_count,
+                           int* canonical, uint32_t* version) {
+    if (!d) { set_error("null database"); return -2; }
+    const kmcdb::Info& i = d->r.info;
+    if (k) *k = i.k;
+    if (total) *total = i.total;
+    if (counter_size) *counter_size = i.counter_size;
+    if (min_count) *min_count = i.min_count;
+    if (max_count) *max_count = i.max_count;
+    if (canonical) *canonical = i.canonical ? 1 : 0;
+    if (version) *version = i.version;
+    return 0;
+}
+MLGI_API int mlgi_kmc_read(mlgi_kmcdb* d, uint64_t* keys, uint32_t* counts_or_null) {
+    if (!d || !keys) { set_error("null argument"); return -2; }
+    if (!d->r.read_all(keys, counts_or_null)) { set_error("%s", d->r.error.c_str()); return -3; }
+    return 0;
+}
+MLGI_API void mlgi_kmc_close(mlgi_kmcdb* d) { delete d; }
 
 MLGI_API void mlgi_close(mlgi_reader* r) {
     if (!r) return;

@@ -42,6 +42,12 @@ def ingest_lib():
         L.mlgi_next.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64,
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.mlgi_spilled_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.mlgi_kmc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.mlgi_kmc_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+        L.mlgi_kmc_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mlgi_kmc_close.argtypes = [C.c_void_p]
+        L.mlgi_kmc_close.restype = None
         L.mlgi_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
         L.mlgi_close.argtypes = [C.c_void_p]
         L.mlgi_close.restype = None
@@ -171,3 +177,26 @@ def detect_input_type(reads_path: str) -> str:
     if parts[-1] in ("fa", "fna", "fasta"):
         return "fasta"
     raise SystemExit("Could not auto-determine file type. Use --input_type.")
+
+
+def read_kmc_database(prefix: str, with_counts: bool = False):
+    """The k-mers of a KMC database (<prefix>.kmc_pre / .kmc_suf; e.g. data/cmash_db_n1000_k60_dump of the reference,
+    scripts/select_db.py:44) as an (n, 2) uint64 array of (hi, lo) keys in file order, plus a dict of its header fields
+    (and the counts, if asked for)."""
+    L = ingest_lib()
+    h = C.c_void_p()
+    if L.mlgi_kmc_open(prefix.encode(), C.byref(h)) != 0:
+        raise IOError(L.mlgi_last_error().decode())
+    try:
+        k, cs, mn, ver = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        tot, mx, canon = C.c_uint64(), C.c_uint64(), C.c_int()
+        L.mlgi_kmc_info(h, C.byref(k), C.byref(tot), C.byref(cs), C.byref(mn), C.byref(mx), C.byref(canon), C.byref(ver))
+        keys = np.empty((tot.value, 2), dtype=np.uint64)
+        counts = np.empty(tot.value, dtype=np.uint32) if with_counts else None
+        if L.mlgi_kmc_read(h, keys.ctypes.data, counts.ctypes.data if with_counts else None) != 0:
+            raise IOError(L.mlgi_last_error().decode())
+    finally:
+        L.mlgi_kmc_close(h)
+    info = dict(k=k.value, total=tot.value, counter_size=cs.value, min_count=mn.value, max_count=mx.value,
+                canonical=bool(canon.value), version=ver.value)
+    return (keys, info, counts) if with_counts else (keys, info)

@@ -89,3 +89,37 @@ def test_dropin_writes_the_files_the_reference_wrote(tmp_path, tag, rfile, over)
         assert filecmp.cmp(str(tmp_path / "out" / name), os.path.join(exp, name), shallow=False), (tag, name)
     got = open(tmp_path / "out" / "60mers_intersection_dump").read().split()
     assert got == [ln.split()[0] for ln in open(os.path.join(exp, "60mers_intersection_dump"))]
+
+
+def test_native_kmc_reader_on_the_fixture_databases(tmp_path):
+    """the product's C++ reader of KMC databases (csrc/kmcdb.h) against the independent Python encoder / decoder: the three
+    databases of the reference-driven fixture (layout 0x200 written by the stub `kmc`, layout 0 by the stub `kmc_tools`),
+    random databases of other k / counter sizes, and damaged files"""
+    import random
+    from metalign_b200 import ingest
+    for prefix in (os.path.join(DATA, "cmash_db_n1000_k60_dump"), os.path.join(CASE, "expected_default", "reads_60mers"),
+                   os.path.join(CASE, "expected_default", "60mers_intersection")):
+        hdr, recs = kmcdb.read(prefix)
+        keys, info, counts = ingest.read_kmc_database(prefix, with_counts=True)
+        assert info["k"] == 60 and info["total"] == len(recs) == hdr["total"] and info["version"] == hdr["version"] and info["canonical"]
+        assert [codec.key_to_kmer(a, b, 60) for a, b in keys] == [x for x, _ in recs] and counts.tolist() == [c for _, c in recs]
+    # the shipped-database check a user would run: the k-mers of the KMC dump == the canonical k-mers of the native file
+    keys, names, h = _db()
+    dkeys, _ = ingest.read_kmc_database(os.path.join(DATA, "cmash_db_n1000_k60_dump"))
+    have = {codec.key_to_kmer(a, b, 60) for a, b in dkeys}
+    want = {oracle_py.canon(codec.key_to_kmer(a, b, 60)) for a, b in keys if a != codec.EMPTY}
+    assert have == want
+    rng = random.Random(9)
+    for version in (0, 0x200):
+        for k, csz in ((21, 2), (32, 4), (63, 1), (13, 1)):
+            kmers = {"".join(rng.choice("ACGT") for _ in range(k)): rng.randint(1, 250) for _ in range(500)}
+            p = str(tmp_path / ("db_%d_%d" % (version, k)))
+            kmcdb.write(p, kmers, k, counter_size=csz, version=version)
+            got, info, counts = ingest.read_kmc_database(p, with_counts=True)
+            assert {codec.key_to_kmer(a, b, k): int(c) for (a, b), c in zip(got, counts)} == kmers
+    raw = open(p + ".kmc_suf", "rb").read()
+    open(p + ".kmc_suf", "wb").write(raw[:-9])
+    with pytest.raises(IOError):
+        ingest.read_kmc_database(p)
+    with pytest.raises(IOError):
+        ingest.read_kmc_database(str(tmp_path / "missing"))
