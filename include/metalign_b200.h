@@ -174,6 +174,14 @@ int mlg_query_finish_sparse(mlg_query* q, uint32_t* genomes, int64_t* num, int64
                             uint64_t* n_rows, uint64_t* n_intersect);
 /* after finish: I as (hi,lo) canonical keys in increasing order; writes at most cap pairs, *n = |I| */
 int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n);
+/* after finish: `kmc_dump <temp>/60mers_intersection <temp>/60mers_intersection_dump` and the FASTA rewrite that follows it
+ * (scripts/select_db.py:58-65) as files: one "<k-mer>\t<count>" line per k-mer of I in lexicographic order, and, if asked
+ * for, the ">seq" / k-mer records of 60mers_intersection_dump.fa.  count = what `kmc_tools simple ... intersect` keeps: the
+ * smaller of the k-mer's occurrences in the reads and the number of sketch slots that hold it, both saturated at
+ * counter_max (the reference builds both KMC databases with -cs3: select_db.py:50, retrain_and_test_metalign.sh:66).
+ * Exact for a query whose reads were all pushed here; after a multi-GPU exchange the read counters are sums of per-rank
+ * counters clamped to ci_min. */
+int mlg_query_dump_intersection(mlg_query* q, const char* dump_path, const char* fasta_path_or_null, uint32_t counter_max);
 int mlg_query_stats(mlg_query* q, mlg_stats* out);
 int mlg_query_free(mlg_query* q);
 

@@ -317,6 +317,12 @@ class Query:
             check(_lib.lib().mlg_query_intersection(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
+    def dump_intersection(self, dump_path: str, fasta_path: str | None = None, counter_max: int = 3) -> None:
+        """mlg_query_dump_intersection: the files `kmc_dump` and the FASTA rewrite leave behind (select_db.py:58-65);
+        counter_max = the -cs3 of both KMC runs of the reference"""
+        check(_lib.lib().mlg_query_dump_intersection(self._h, dump_path.encode(), fasta_path.encode() if fasta_path else None,
+                                                     int(counter_max)))
+
     def stats(self) -> dict:
         s = Stats()
         check(_lib.lib().mlg_query_stats(self._h, C.byref(s)))

@@ -845,6 +845,46 @@ MLG_API int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t ca
     return MLG_OK;
 }
 
+// `kmc_dump <temp>/60mers_intersection <temp>/60mers_intersection_dump` and the FASTA rewrite after it
+// (scripts/select_db.py:58-65), straight from the query's tables
+MLG_API int mlg_query_dump_intersection(mlg_query* q, const char* dump_path, const char* fasta_path_or_null, uint32_t counter_max) {
+    if (!q || !dump_path) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (!q->finished) { mlg_set_error("call mlg_query_finish first"); return MLG_ERR_STATE; }
+    if (counter_max == 0 || counter_max > 255) { mlg_set_error("counter_max must be 1..255"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(q->ctx));
+    const uint32_t n = q->n_present, K = q->db->v.K;
+    struct Rec { key128 k; unsigned char c; };
+    std::vector<Rec> recs(n);
+    if (n) {
+        DevBuf<key128> d; MLG_TRY(d.alloc(n));
+        DevBuf<unsigned char> dc; MLG_TRY(dc.alloc(n));
+        MLG_TRY(launch_gather_keys(q->db->D_key.p, q->present.p, n, d.p, q->ctx->s_comp));
+        MLG_TRY(launch_gather_counts(q->cnt8.p, q->db->D_mult.p, q->present.p, n, counter_max, dc.p, q->ctx->s_comp));
+        std::vector<key128> hk(n); std::vector<unsigned char> hc(n);
+        CUDA_TRY(cudaMemcpyAsync(hk.data(), d.p, (size_t)n * sizeof(key128), cudaMemcpyDeviceToHost, q->ctx->s_comp));
+        CUDA_TRY(cudaMemcpyAsync(hc.data(), dc.p, n, cudaMemcpyDeviceToHost, q->ctx->s_comp));
+        CUDA_TRY(cudaStreamSynchronize(q->ctx->s_comp));
+        for (uint32_t i = 0; i < n; ++i) recs[i] = Rec{hk[i], hc[i]};
+        std::sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return key_lt(a.k, b.k); });
+    }
+    FILE* fd = fopen(dump_path, "w");
+    if (!fd) { mlg_set_error("cannot create %s", dump_path); return MLG_ERR_IO; }
+    FILE* ff = fasta_path_or_null ? fopen(fasta_path_or_null, "w") : nullptr;
+    if (fasta_path_or_null && !ff) { fclose(fd); mlg_set_error("cannot create %s", fasta_path_or_null); return MLG_ERR_IO; }
+    std::vector<char> line(K + 1);
+    bool ok = true;
+    for (uint32_t i = 0; i < n && ok; ++i) {
+        key128 k = recs[i].k;
+        for (uint32_t j = 0; j < K; ++j) { line[K - 1 - j] = "ACGT"[k.lo & 3ull]; k = key_shr(k, 2); }
+        line[K] = 0;
+        ok = fprintf(fd, "%s\t%u\n", line.data(), (unsigned)recs[i].c) > 0 && (!ff || fprintf(ff, ">seq\n%s\n", line.data()) > 0);
+    }
+    ok = (fclose(fd) == 0) && ok;
+    if (ff) ok = (fclose(ff) == 0) && ok;
+    if (!ok) { mlg_set_error("%s: short write", dump_path); return MLG_ERR_IO; }
+    return MLG_OK;
+}
+
 MLG_API int mlg_query_stats(mlg_query* q, mlg_stats* out) {
     if (!q || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
     *out = q->st;

@@ -100,6 +100,18 @@ __global__ void k_flag_heads(const key128* a, uint32_t n, unsigned char* flag) {
     if (i >= n) return;
     flag[i] = (i == 0 || !key_eq(a[i], a[i - 1])) ? 1 : 0;
 }
+// length of the run of equal keys that starts at every head, saturating at 255 (the number of sketch slots that hold the K-mer)
+__global__ void k_run_lengths(const unsigned char* head, uint32_t n, unsigned char* len) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t l = 0;
+    if (head[i]) { l = 1; while (l < 255u && i + l < n && !head[i + l]) ++l; }
+    len[i] = (unsigned char)l;
+}
+__global__ void k_gather_u8(const unsigned char* src, const uint32_t* idx, uint32_t n, unsigned char* dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
 __global__ void k_hash_keys(const key128* a, uint32_t n, uint32_t K, uint32_t layout, uint32_t bbits, unsigned long long* h) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) h[i] = layout == 2 ? key_hash_mz(a[i], K) : layout == 1 ? key_hash_sk(a[i], K, bbits) : key_hash(a[i], K);
@@ -372,7 +384,20 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         unsigned long long nd64 = 0;
         CUDA_TRY(cudaMemcpy(&nd64, d_cnt.p, 8, cudaMemcpyDeviceToHost));
         nd = (uint32_t)nd64;
-        csorted.release(); head.release();
+        csorted.release();
+        // how many sketch slots hold each distinct K-mer (what `kmc -ci0` of the sketches' dump counts)
+        DevBuf<unsigned char> multu; MLG_TRY(multu.alloc(nd));
+        {
+            DevBuf<unsigned char> runlen; MLG_TRY(runlen.alloc(np));
+            k_run_lengths<<<nblk(np), TPB, 0, st>>>(head.p, np, runlen.p);
+            void* tmp = nullptr; size_t tb = 0;
+            CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, tb, runlen.p, head.p, multu.p, d_cnt.p, (int)np, st));
+            CUDA_TRY(cudaMalloc(&tmp, tb ? tb : 1));
+            cudaError_t e = cub::DeviceSelect::Flagged(tmp, tb, runlen.p, head.p, multu.p, d_cnt.p, (int)np, st);
+            cudaStreamSynchronize(st); cudaFree(tmp);
+            if (e != cudaSuccess) { mlg_set_error("DeviceSelect failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
+        }
+        head.release();
         // order by hash
         DevBuf<unsigned long long> h; DevBuf<uint32_t> iota, perm;
         MLG_TRY(h.alloc(nd)); MLG_TRY(hsorted.alloc(nd)); MLG_TRY(iota.alloc(nd)); MLG_TRY(perm.alloc(nd));
@@ -382,6 +407,8 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
         MLG_TRY(sort_pairs_u64(h.p, hsorted.p, iota.p, perm.p, nd, 0, 64, st));
         MLG_TRY(db->D_key.alloc(nd));
         k_gather_key<<<nblk(nd), TPB, 0, st>>>(duniq.p, perm.p, nd, db->D_key.p);
+        MLG_TRY(db->D_mult.alloc(nd));
+        k_gather_u8<<<nblk(nd), TPB, 0, st>>>(multu.p, perm.p, nd, db->D_mult.p);
         CUDA_TRY(cudaStreamSynchronize(st));
     } else {
         MLG_TRY(db->D_key.alloc(1)); MLG_TRY(hsorted.alloc(1));

@@ -23,7 +23,7 @@
 namespace {
 
 constexpr uint32_t BUILD_TAG = 0x20261017u;      // minimizer identity = min/max multiply-add + xor-shift; hit records v2
-enum : uint32_t { S_DKEY = 1, S_BSTART, S_F, S_ALIAS_Z, S_ALIAS_I, S_ALIAS_BLOOM, S_HOFF, S_HBASE, S_HITS, S_DEN, S_HASEMPTY, S_T1 };
+enum : uint32_t { S_DKEY = 1, S_BSTART, S_F, S_ALIAS_Z, S_ALIAS_I, S_ALIAS_BLOOM, S_HOFF, S_HBASE, S_HITS, S_DEN, S_HASEMPTY, S_T1, S_DMULT };
 struct Section { uint32_t tag, elem; uint64_t count, offset; };
 constexpr size_t CHUNK = (size_t)32 << 20;       // staging granularity
 constexpr int NBUF = 12;                         // pinned staging buffers in flight
@@ -187,6 +187,7 @@ int mlg_db_load_file(mlg_ctx* ctx, const char* path, mlg_db** out) {
         case S_DEN: MLG_TRY(load(s, db->den_real, 0)); break;
         case S_HASEMPTY: MLG_TRY(load(s, db->has_empty, 0)); break;
         case S_T1: MLG_TRY(load(s, db->T1, 0)); break;
+        case S_DMULT: MLG_TRY(load(s, db->D_mult, 0)); break;      // optional: files written before it existed load without
         default: break;       // sections of a later minor version
         }
     }
@@ -232,6 +233,7 @@ int mlg_db_save_file(const mlg_db* db, const char* path, const char* names, uint
         {S_HOFF, 4, v.nd, db->hoff.p}, {S_HBASE, 8, groups + 1, db->hbase.p}, {S_HITS, 4, db->hit_words, db->hits.p},
         {S_DEN, 8, (uint64_t)v.G * v.nk, db->den_real.p}, {S_HASEMPTY, 1, v.G, db->has_empty.p},
     };
+    if (db->D_mult.p) src.push_back({S_DMULT, 1, v.nd, db->D_mult.p});
     if (v.layout == 2) {
         src.push_back({S_F, 4, (uint64_t)v.nfw, db->F.p});
         src.push_back({S_ALIAS_BLOOM, 4, 2048, db->alias_bloom.p});

@@ -107,6 +107,8 @@ struct mlg_db {
     DevBuf<unsigned long long> alias_z;
     DevBuf<uint32_t> alias_i, alias_bloom;
     DevBuf<key128> D_key;
+    DevBuf<unsigned char> D_mult;    // per k-mer of D: sketch slots that hold it (either strand), saturating at 255 -- its count in the KMC database
+                                     // of the sketches (retrain_and_test_metalign.sh:66); only mlg_query_dump_intersection reads it
     DevBuf<uint32_t> hoff, hits;     // precomputed hit records per k-mer of D (hoff.p == nullptr: not built)
     DevBuf<unsigned long long> hbase; // 64-bit word offset of every group of 2^MLG_HGROUP_SHIFT k-mers' records
     unsigned long long hit_words = 0;
@@ -185,3 +187,5 @@ int launch_finalize_sparse(const unsigned long long* num, const long long* den_r
                            unsigned long long* d_counter, cudaStream_t st);
 int launch_clear_touched(unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, cudaStream_t st);
 int launch_gather_keys(const key128* D_key, const uint32_t* present, uint32_t n_present, key128* out, cudaStream_t st);
+int launch_gather_counts(const unsigned char* cnt8, const unsigned char* D_mult, const uint32_t* present, uint32_t n_present, uint32_t cap,
+                         unsigned char* out, cudaStream_t st);

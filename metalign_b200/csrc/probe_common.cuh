@@ -5,7 +5,10 @@
 
 namespace {
 
-constexpr unsigned RT = 256;            // reads per tile == threads per CTA
+#ifndef MLG_RT
+#define MLG_RT 256
+#endif
+constexpr unsigned RT = MLG_RT;         // reads per tile == threads per CTA
 constexpr unsigned WARPS = RT / 32;
 constexpr unsigned WMAX = 96;           // window starts per segment
 constexpr unsigned SEGW = 10;           // 32-bit words of bases per segment (160 bases >= WMAX + 63 - 1)

@@ -1,3 +1,8 @@
+// MZ_RT: threads per CTA of this kernel alone (every warp is its own pipeline, so the CTA size only sets how the
+// register file and shared memory are cut up); the other K1 kernels keep 256
+#ifdef MZ_RT
+#define MLG_RT MZ_RT
+#endif
 #include "probe_common.cuh"
 
 namespace {
@@ -25,8 +30,22 @@ constexpr unsigned MZ_QDRAIN = 32;            // per-warp item list: drained whe
 constexpr unsigned MZ_QCAP = MZ_QDRAIN + 128; // ... and one block of 16 windows adds at most 4 x 32
 constexpr unsigned MZ_LIST = 16;              // run list rows: a block of 16 windows starts at most 15 new runs (row 0 unused)
 constexpr uint32_t MZ_M64 = MLG_MZ_ORD_MULT << 6;   // the multiplier carries the << 6 of (order << 6 | position)
+// reads per hand-out: one tile counter increment, one TMA issue and one mbarrier wait serve MZ_TILE_READS / 32 warp
+// passes.  64 halves the share of the per-tile code (~300 instructions on one lane) but doubles the staging buffers:
+// 2 x 108 KB of shared memory per SM leave 28 KB of L1 and the kernel ran 18 % SLOWER (2.56 vs 2.16 ms, r4c); 32 it is.
+#ifndef MZ_TILE_READS
+#define MZ_TILE_READS 32
+#endif
+constexpr unsigned MZ_TR = MZ_TILE_READS;
+static_assert(MZ_TR % 32 == 0 && MZ_TR >= 32 && MZ_TR <= 128, "tile = whole warp passes");
+constexpr unsigned MZ_STAGE_B = MZ_TR * 40 + 64;       // MZ_TR reads x 160 bases fit; longer reads are gathered from global
+constexpr unsigned MZ_STAGE_M = MZ_TR * 20 + 64;
+struct MzStage {
+    __align__(16) unsigned char b[WARPS][2][MZ_STAGE_B];
+    __align__(16) unsigned char m[WARPS][2][MZ_STAGE_M];
+};
 struct MzShared {
-    SkStage stg;
+    MzStage stg;
     uint32_t wm[MZ_LIST][RT];                 // [r][thread]: value of the r-th run START of the current block (r >= 1)
     uint32_t seq[SEGW + 1][RT];               // [word][thread]: the lane's current segment (160 bases, top-aligned words)
     uint32_t qa[WARPS][MZ_QCAP];              // item: stream position (in bases) of the block's first window, low / high word
@@ -72,6 +91,31 @@ __device__ __forceinline__ key128 ldg_key(const key128* ptr) {
     key128 k;
     asm volatile("ld.global.nc" MZ_L2Q ".v2.u64 {%0, %1}, [%2];" : "=l"(k.hi), "=l"(k.lo) : "l"(ptr));
     return k;
+}
+// The tile's bases and N bits as 32-bit shared loads from this warp's staging buffer (the common case: reads of up to 160
+// bases; segment_load in probe_common.cuh is the general form -- 64-bit generic loads with clamped indices -- and cost 220
+// of the ~850 instructions a read pays outside its blocks).  brel / mrel: the segment's first base relative to the first
+// staged base / mask bit; sb / sk: shared addresses of the staged bytes (or of a zero block for a lane without windows).
+template <bool HAS_NMASK>
+__device__ __forceinline__ void segment_load_staged(uint32_t (&loc)[SEGW], uint32_t (&nl)[5], uint32_t brel, uint32_t mrel, uint32_t sb, uint32_t sk) {
+    const uint32_t ab = sb + (brel >> 4) * 4u;
+    const unsigned sh = 2u * (brel & 15u);
+    uint32_t W[SEGW + 1];
+#pragma unroll
+    for (int k = 0; k <= (int)SEGW; ++k) W[k] = __byte_perm(lds32(ab + 4u * (uint32_t)k), 0, 0x0123);
+#pragma unroll
+    for (int k = 0; k < (int)SEGW; ++k) loc[k] = fsl(W[k], W[k + 1], sh);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nl[k] = 0;
+    if (HAS_NMASK) {
+        const uint32_t am = sk + (mrel >> 5) * 4u;
+        const unsigned shn = mrel & 31u;
+        uint32_t M[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) M[k] = __byte_perm(lds32(am + 4u * (uint32_t)k), 0, 0x0123);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) nl[k] = fsl(M[k], M[k + 1], shn);
+    }
 }
 // (order << 6 | position) of the 32-mer at position 16j+i of the current block: first half = bases [16j+i, +16) of
 // loc[], reverse complement of the second half = the 16-mer at 16(j+1)+i seen through rcl[] (see sk_mmer)
@@ -201,16 +245,18 @@ template <bool HAS_NMASK>
 __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a, DbView db) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MzShared& sm = *reinterpret_cast<MzShared*>(smem_raw);
-    SkStage& stg = sm.stg;
+    MzStage& stg = sm.stg;
     __shared__ __align__(8) unsigned long long mbar[WARPS][2];
     __shared__ unsigned long long s_bw0[WARPS][2], s_mw0[WARPS][2];
     __shared__ unsigned s_staged[WARPS][2];
+    __shared__ __align__(16) uint32_t s_zero[SEGW + 2];      // what a lane without windows loads instead of staged bytes
 
     const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     constexpr unsigned K = SK_K;
+    if (tid < SEGW + 2) s_zero[tid] = 0u;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned long long nreads = a.r_end - a.r_begin;
-    const unsigned long long ntiles = (nreads + 31) / 32;                 // a tile = the 32 reads of one warp pass
+    const unsigned long long ntiles = (nreads + MZ_TR - 1) / MZ_TR;       // a tile = MZ_TR reads: MZ_TR / 32 warp passes
     auto next_tile = [&]() -> unsigned long long {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
@@ -233,8 +279,8 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
     __syncthreads();
 
     auto issue = [&](unsigned stage, unsigned long long t) {
-        const unsigned long long r0 = a.r_begin + t * 32ull;
-        const unsigned long long r1 = (r0 + 32 < a.r_end) ? r0 + 32 : a.r_end;
+        const unsigned long long r0 = a.r_begin + t * (unsigned long long)MZ_TR;
+        const unsigned long long r1 = (r0 + MZ_TR < a.r_end) ? r0 + MZ_TR : a.r_end;
         const unsigned long long p0 = a.off ? a.off[r0] : r0 * (unsigned long long)a.read_len;
         const unsigned long long p1 = a.off ? a.off[r1] : r1 * (unsigned long long)a.read_len;
         unsigned long long bw0 = (p0 >> 5) & ~1ull;
@@ -245,7 +291,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         unsigned long long mw1 = ((p1 + 63) >> 6) + 4;
         if (HAS_NMASK) { if (mw1 > a.nmask_words) mw1 = a.nmask_words; mw1 = (mw1 + 1) & ~1ull; }
         const unsigned long long bytes_b = (bw1 - bw0) * 8ull, bytes_m = HAS_NMASK ? (mw1 - mw0) * 8ull : 0ull;
-        const bool fits = bw1 > bw0 && bytes_b <= WSTAGE_B && bytes_m <= WSTAGE_M;
+        const bool fits = bw1 > bw0 && bytes_b <= MZ_STAGE_B && bytes_m <= MZ_STAGE_M;
         s_bw0[warp][stage] = bw0; s_mw0[warp][stage] = mw0; s_staged[warp][stage] = fits ? 1u : 0u;
         if (fits) {
             mbar_expect_tx(&mbar[warp][stage], (uint32_t)(bytes_b + bytes_m));
@@ -258,7 +304,6 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
 
     unsigned long long my_valid = 0;
     unsigned my_fetch = 0;
-    const unsigned long long* bsrc = a.bases;
     if (lane == 0) sm.qn[warp] = 0;
     __syncwarp();
 
@@ -298,7 +343,13 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         __syncwarp();
         mbar_wait(&mbar[warp][stage], parity);
 
-        const unsigned long long r = a.r_begin + t * 32ull + lane;
+        const bool staged = s_staged[warp][stage] != 0;
+        const unsigned long long bw0_32 = s_bw0[warp][stage] * 32ull, mw0_64 = s_mw0[warp][stage] * 64ull;
+        const uint32_t sb_stage = smem_u32(&stg.b[warp][stage][0]), sk_stage = smem_u32(&stg.m[warp][stage][0]), s_zero_a = smem_u32(&s_zero[0]);
+#pragma unroll 1
+        for (unsigned half = 0; half < MZ_TR / 32u; ++half) {
+        const unsigned long long r = a.r_begin + t * (unsigned long long)MZ_TR + half * 32u + lane;
+        if (half && r - lane >= a.r_end) break;
         const bool active = r < a.r_end;
         unsigned long long R0 = 0, R1 = 0;
         if (active) {
@@ -309,9 +360,8 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         const unsigned long long nw = len >= K ? len - K + 1 : 0ull;
         const unsigned nseg = (unsigned)((nw + WMAX - 1) / WMAX);
         const unsigned max_seg = __reduce_max_sync(FULL, nseg);
-        const bool staged = s_staged[warp][stage] != 0;
-        bsrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.b[warp][stage][0]) - s_bw0[warp][stage] : a.bases;
-        const unsigned long long* msrc = staged ? reinterpret_cast<const unsigned long long*>(&stg.m[warp][stage][0]) - s_mw0[warp][stage] : a.nmask;
+        // staged (reads of up to 160 bases): 32-bit positions relative to the staged bytes; otherwise the stream itself
+        const uint32_t brel0 = (uint32_t)(R0 - bw0_32), mrel0 = (uint32_t)(R0 - mw0_64);
         __syncwarp();
 
         for (unsigned seg = 0; seg < max_seg; ++seg) {
@@ -320,7 +370,8 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
 
             uint32_t loc[SEGW];
             uint32_t nl[5];
-            segment_load<HAS_NMASK>(loc, nl, c, s, bsrc, msrc, a.base_words, a.nmask_words);
+            if (staged) segment_load_staged<HAS_NMASK>(loc, nl, c ? brel0 + seg * WMAX : 0u, c ? mrel0 + seg * WMAX : 0u, c ? sb_stage : s_zero_a, c ? sk_stage : s_zero_a);
+            else segment_load<HAS_NMASK>(loc, nl, c, s, a.bases, a.nmask, a.base_words, a.nmask_words);
             uint32_t v0, v1, v2;
             segment_valid<HAS_NMASK>(nl, c, K, v0, v1, v2);
             my_valid += __popc(v0) + __popc(v1) + __popc(v2);
@@ -475,6 +526,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                 for (int k = (int)SEGW - 1; k > 0; --k) rcl[k] = rcl[k - 1];
             }
         }
+        }
         __syncwarp();             // every lane is done with this stage's staged bases before it is refilled
         const unsigned long long t_new = next_tile();
         if (lane == 0 && t_new < ntiles) issue(stage, t_new);
@@ -511,7 +563,7 @@ int launch_mz_t(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned 
 int launch_probe_mz(const DbView& db, const ProbeArgs& a, cudaStream_t st, int sm_count) {
     if (db.K != SK_K || !db.F) { mlg_set_error("minimizer-bitmap layout needs K=60 and its bit array"); return MLG_ERR_STATE; }
     // persistent: the CTAs that fit pull 32-read tiles from a global counter
-    const unsigned long long wtiles = (a.r_end - a.r_begin + 31) / 32;
+    const unsigned long long wtiles = (a.r_end - a.r_begin + MZ_TR - 1) / MZ_TR;
     const unsigned long long need = (wtiles + WARPS - 1) / WARPS;
     int per_sm = MZ_MINCTAS;
     if (const char* e = getenv("MLG_PROBE_CTAS_PER_SM")) { int x = atoi(e); if (x >= 1 && x <= 64) per_sm = x; }

@@ -541,6 +541,17 @@ __global__ void k_gather_present_keys(const key128* D_key, const uint32_t* prese
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_present) out[i] = D_key[present[i]];
 }
+// what `kmc_tools simple <db> <reads> intersect` keeps as a k-mer's counter: the smaller of its two counters, each of
+// which saturated at `cap` (-cs) when its database was written
+__global__ void k_gather_present_counts(const unsigned char* cnt8, const unsigned char* D_mult, const uint32_t* present, uint32_t n_present,
+                                        uint32_t cap, unsigned char* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_present) return;
+    const uint32_t d = present[i];
+    uint32_t c = cnt8[d];
+    if (D_mult) c = min(c, (uint32_t)D_mult[d]);
+    out[i] = (unsigned char)min(c, cap);
+}
 
 }  // namespace
 
@@ -678,6 +689,13 @@ int launch_clear_touched(unsigned char* cnt8, const uint32_t* touched, const uns
 int launch_gather_keys(const key128* D_key, const uint32_t* present, uint32_t n_present, key128* out, cudaStream_t st) {
     if (!n_present) return MLG_OK;
     k_gather_present_keys<<<(n_present + 255) / 256, 256, 0, st>>>(D_key, present, n_present, out);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_gather_counts(const unsigned char* cnt8, const unsigned char* D_mult, const uint32_t* present, uint32_t n_present, uint32_t cap,
+                         unsigned char* out, cudaStream_t st) {
+    if (!n_present) return MLG_OK;
+    k_gather_present_counts<<<(n_present + 255) / 256, 256, 0, st>>>(cnt8, D_mult, present, n_present, cap, out);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }

@@ -150,9 +150,9 @@ def run_cmash_and_cutoff(args, taxid2info):
         cmash_tail.write_results_csv_sparse(cmash_out, db.names, db.ks, res["genomes"], res["ci"], 0.0)      # '-c 0'
         _tick("csv written")
         if args.keep_temp_files:
-            with open(args.temp_dir + "60mers_intersection_dump", "w") as fh:
-                for hi, lo in query.intersection():
-                    fh.write(codec.key_to_kmer(hi, lo, db.K) + "\n")
+            # what kmc_dump and the FASTA rewrite leave in the temp dir (select_db.py:58-65): "<k-mer>\t<count>" lines
+            # and the ">seq" records CMash is given
+            query.dump_intersection(args.temp_dir + "60mers_intersection_dump", args.temp_dir + "60mers_intersection_dump.fa")
         if not getattr(args, "_mlg_leave_open", False):     # the command-line script exits right after: no point in freeing GBs first
             query.close(); db.close(); ctx.close()
         del args._mlg

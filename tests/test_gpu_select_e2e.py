@@ -68,8 +68,9 @@ def test_select_main_end_to_end(tmp_path, gate, fmt):
     taxid2info = select_db.read_dbinfo(args)
     assert chosen == oracle_py.select_organisms(rows, taxid2info, 0.01, False) and len(chosen) > 0
     # the debug artefact: sorted canonical 60-mers of the intersection
-    dump = open(tmp / "60mers_intersection_dump").read().split()
-    assert dump == [codec.key_to_kmer(a, b, 60) for a, b in I_ref]
+    dump = [ln.split("\t") for ln in open(tmp / "60mers_intersection_dump").read().splitlines()]
+    assert [d[0] for d in dump] == [codec.key_to_kmer(a, b, 60) for a, b in I_ref]
+    assert all(len(d) == 2 and 1 <= int(d[1]) <= 3 for d in dump)
     # subset files are consistent with the selection
     info = open(tmp / "subset_db_info.txt").read().splitlines()
     assert info[0].startswith("Accesion\t") and info[1].startswith("Unmapped\t0")

@@ -87,8 +87,10 @@ def test_dropin_writes_the_files_the_reference_wrote(tmp_path, tag, rfile, over)
     exp = os.path.join(CASE, "expected_" + tag)
     for name in ("cmash_query_results.csv", "cmashed_db.fna", "subset_db_info.txt"):
         assert filecmp.cmp(str(tmp_path / "out" / name), os.path.join(exp, name), shallow=False), (tag, name)
-    got = open(tmp_path / "out" / "60mers_intersection_dump").read().split()
-    assert got == [ln.split()[0] for ln in open(os.path.join(exp, "60mers_intersection_dump"))]
+    # kmc_dump's file ("<k-mer>\t<count>", count = min of the two -cs3 counters) and the FASTA rewrite of select_db.py:61-65
+    assert filecmp.cmp(str(tmp_path / "out" / "60mers_intersection_dump"), os.path.join(exp, "60mers_intersection_dump"), shallow=False), tag
+    kmers = [ln.split()[0] for ln in open(os.path.join(exp, "60mers_intersection_dump"))]
+    assert open(tmp_path / "out" / "60mers_intersection_dump.fa").read() == "".join(">seq\n%s\n" % x for x in kmers)
 
 
 def test_native_kmc_reader_on_the_fixture_databases(tmp_path):
