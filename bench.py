@@ -119,6 +119,21 @@ def measured_traffic():
         return None
 
 
+def measured_request_ceiling():
+    """What this part sustains in independent random 4-byte reads of a 1 GiB table (scripts/ubench/gather.cu, measured on
+    the same pool: profiles/r3a_ubench_gather_rates.jsonl), for the load flavour K1 uses (ld.global.nc .L2::64B)."""
+    try:
+        best = None
+        with open(os.path.join(ROOT, "profiles", "r3a_ubench_gather_rates.jsonl")) as f:
+            for ln in f:
+                d = json.loads(ln)
+                if "L2::64B" in d.get("variant", ""):
+                    best = float(d["G_loads_per_s"])
+        return best
+    except Exception:
+        return None
+
+
 def synth_params(G, paired):
     import synth
     return synth.params(G=G, n=1000, K=K, seed=SEED, n_present=500, read_len=READ_LEN, paired=paired)
@@ -239,8 +254,12 @@ def run_native(args):
     from metalign_b200 import codec
     from metalign_b200 import dist as mdist
 
-    # rank 0 prints ONE JSON line on stdout: whatever NCCL has to say (its version banner, with NCCL_DEBUG set) goes to stderr
+    # rank 0 prints ONE JSON line on stdout: whatever NCCL has to say (its version banner, with NCCL_DEBUG set) goes to stderr.
+    # The banner is written to file descriptor 1 by the library itself, so the descriptor is pointed at stderr until the line is due.
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = mdist.init_from_env("nccl")
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
@@ -263,16 +282,30 @@ def run_native(args):
 
     # database: generated on the device, built on the device
     t0 = time.perf_counter()
-    d_keys = torch.empty(G * p.n * 2, dtype=torch.int64, device="cuda")
-    assert synth.cuda_lib().syn_cuda_gen_sketch_keys(C.byref(p), d_keys.data_ptr(), None) == 0
     keys_host = None
-    if rank == 0 and not skip_cpu and (world == 1 or want_parity):
-        keys_host = d_keys.cpu().numpy().view(np.uint64).reshape(-1, 2)
-        t0 = time.perf_counter()
-    db = Database.from_device_keys(ctx, d_keys.data_ptr(), G, p.n, K, KS)
+    need_host_keys = rank == 0 and not skip_cpu and (world == 1 or want_parity)
+    if G * p.n <= 400_000_000 or need_host_keys:
+        d_keys = torch.empty(G * p.n * 2, dtype=torch.int64, device="cuda")
+        assert synth.cuda_lib().syn_cuda_gen_sketch_keys(C.byref(p), d_keys.data_ptr(), None) == 0
+        if need_host_keys:
+            keys_host = d_keys.cpu().numpy().view(np.uint64).reshape(-1, 2)
+            t0 = time.perf_counter()
+        db = Database.from_device_keys(ctx, d_keys.data_ptr(), G, p.n, K, KS)
+        del d_keys
+    else:
+        # the 10x database (2e9 slots, 32 GB of keys): generated and handed to the builder 1e5 genomes at a time
+        step = 100_000
+        d_chunk = torch.empty(step * p.n * 2, dtype=torch.int64, device="cuda")
+
+        def chunks():
+            for g0 in range(0, G, step):
+                c = min(step, G - g0)
+                assert synth.cuda_lib().syn_cuda_gen_sketch_keys_range(C.byref(p), g0, c, d_chunk.data_ptr(), None) == 0
+                yield d_chunk.data_ptr(), g0, c
+        db = Database.from_device_chunks(ctx, chunks(), G, p.n, K, KS)
+        del d_chunk
     torch.cuda.synchronize()
     t_db = time.perf_counter() - t0
-    del d_keys
     torch.cuda.empty_cache()
 
     # this rank's reads, batch by batch: generated on the device; a pinned host copy for the end-to-end leg, which hands
@@ -427,6 +460,7 @@ def run_native(args):
                       tr.get("warps_active_pct", 0), tr.get("source", "")))
     else:
         limiter = "random 32-byte DRAM sectors (one per k-mer behind an L2 prefilter)" if layout == 0 else "see profiles/"
+    req_ceiling = measured_request_ceiling()
     xmode_eff = mdist.effective_mode(ctx, xmode)
     line = None
     if rank == 0:
@@ -460,7 +494,12 @@ def run_native(args):
                          "layout": layout, "bucket_fetches_per_step": fetches, "kmers_per_bucket_fetch": kmers_rank / max(1, fetches),
                          "algorithmic_bytes_rule": "level-1 fetches x %d B + packed bases + N mask (SURVEY.md 8d, minimizer bucketing: layout 2 = one 32-byte sector of the minimizer-identity bit array per super-k-mer, layout 1 = one 64-byte fingerprint-bucket pair per super-k-mer, layout 0 = one sector per k-mer)" % bucket_bytes,
                          "sector_per_kmer_equivalent_gbs": (kmers_rank * 32 + nbases // 4 + nbases // 8) / (probe_ms / 1e3) / 1e9,
-                         "limiter": limiter},
+                         "limiter": limiter,
+                         # the bound this kernel actually runs into besides instruction issue: random-read REQUESTS per second
+                         "request_rate": ({"achieved_g_per_s": fetches / (probe_ms / 1e3) / 1e9, "ceiling_g_per_s": req_ceiling,
+                                           "frac": fetches / (probe_ms / 1e3) / 1e9 / req_ceiling,
+                                           "source": "profiles/r3a_ubench_gather.md: independent random 4-byte ld.global.nc.L2::64B reads of a 1 GiB table top out at this rate on this part (DRAM then moves 64 B per read, 3.1 TB/s)"}
+                                          if req_ceiling and layout == 2 else None)},
             "clocks": clocks,
             "host_numa_binding_rank0": numa,
             "wall_ms_per_step": wall_dev * 1e3 / args.steps,
@@ -503,7 +542,9 @@ def run_native(args):
             line["parity"] = {"against": "oracle/oracle.c on all %d reads of the job (%d cores)" % (total_reads, r["cores"]),
                               "equal": same, "intersect": [int(ni), int(r["n_intersect"])],
                               "genomes_with_k60_hits": int((gpu_num[:, -1] > 0).sum())}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if want_parity and not line["parity_checked"]:
         raise SystemExit("PARITY FAILURE: the GPU table differs from the oracle's: %s" % line["parity"])
 

@@ -102,6 +102,17 @@ int mlg_db_from_keys_device(mlg_ctx* ctx, const uint64_t* d_keys /* device, 16-b
                             uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db** out);
 int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers /* host, G*n*K chars; a slot starting with NUL is empty */,
                       uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db** out);
+/* The same build fed in chunks of whole genomes, in order (first_genome = the number of genomes added so far): the caller
+ * never holds all G*n keys on the device, which is what lets a 2e9-slot database (BASELINE configs[4]) build inside 180 GB.
+ * mlg_db_builder_finish frees the builder when it succeeds; after a failure call mlg_db_builder_destroy.  A database whose
+ * precomputed hit records would not fit beside its other structures keeps the prefix index instead and expands every
+ * query's present k-mers on the fly (same results). */
+typedef struct mlg_db_builder mlg_db_builder;
+int mlg_db_builder_create(mlg_ctx* ctx, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db_builder** out);
+int mlg_db_builder_add_device(mlg_db_builder* b, const uint64_t* d_keys /* device, n_genomes*n (hi,lo) pairs */,
+                              uint32_t first_genome, uint32_t n_genomes);
+int mlg_db_builder_finish(mlg_db_builder* b, mlg_db** out);
+int mlg_db_builder_destroy(mlg_db_builder* b);
 /* .mlgdb file: the source form (sketch keys; the device structures are built on load) or the built form written by
  * mlg_db_save (the device structures themselves: loading is a file read).  names = the '\n'-joined genome names the
  * file's head carries for the host side (metalign_b200/dbformat.py). */

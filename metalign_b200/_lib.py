@@ -59,6 +59,10 @@ SIGNATURES = {
     "mlg_host_free": (C.c_int, [_vp]),
     "mlg_db_from_keys": (C.c_int, [_vp, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _pp]),
     "mlg_db_from_keys_device": (C.c_int, [_vp, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _pp]),
+    "mlg_db_builder_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _pp]),
+    "mlg_db_builder_add_device": (C.c_int, [_vp, _u64p, C.c_uint32, C.c_uint32]),
+    "mlg_db_builder_finish": (C.c_int, [_vp, _pp]),
+    "mlg_db_builder_destroy": (C.c_int, [_vp]),
     "mlg_db_from_ascii": (C.c_int, [_vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, C.c_uint32, _pp]),
     "mlg_db_load": (C.c_int, [_vp, C.c_char_p, _pp]),
     "mlg_db_save": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_uint64]),

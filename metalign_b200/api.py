@@ -95,6 +95,24 @@ class Database:
         return cls(ctx, h, names)
 
     @classmethod
+    def from_device_chunks(cls, ctx: Context, chunks, G: int, n: int, K: int = 60, ks: Sequence[int] = DEFAULT_KS, names=None) -> "Database":
+        """mlg_db_builder_*: `chunks` yields (device pointer, first genome, genomes) in genome order; a chunk's buffer may be
+        reused as soon as the next one is asked for.  The device never holds all G*n keys beside the structures built from
+        them (a 2e9-slot database builds inside 180 GB this way)."""
+        ksa = np.asarray(ks, dtype=np.uint32)
+        b = C.c_void_p()
+        check(_lib.lib().mlg_db_builder_create(ctx._h, G, n, K, ksa.ctypes.data, ksa.size, C.byref(b)))
+        h = C.c_void_p()
+        try:
+            for ptr, g0, count in chunks:
+                check(_lib.lib().mlg_db_builder_add_device(b, ptr, g0, count))
+            check(_lib.lib().mlg_db_builder_finish(b, C.byref(h)))
+        except BaseException:
+            _lib.lib().mlg_db_builder_destroy(b)
+            raise
+        return cls(ctx, h, names)
+
+    @classmethod
     def from_sketches(cls, ctx: Context, sketches, K: int = 60, ks: Sequence[int] = DEFAULT_KS, names=None) -> "Database":
         """sketches: list of G lists of n strings ('' for an unused slot) -- what
         local_tests/dump_kmers.py:7-14 walks (`CE._kmers`).  Goes through mlg_db_from_ascii."""

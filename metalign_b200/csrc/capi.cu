@@ -294,16 +294,39 @@ MLG_API int mlg_db_from_keys_device(mlg_ctx* ctx, const uint64_t* d_keys, uint32
     MLG_TRY(ensure_device(ctx));
     return mlg_db_build_device(ctx, reinterpret_cast<const key128*>(d_keys), G, n, K, ks, nk, out);
 }
+// chunk-fed build (csrc/db.cu): host keys are uploaded a few thousand genomes at a time, so the device never holds the
+// caller's G*n keys beside the structures built from them
+MLG_API int mlg_db_builder_create(mlg_ctx* ctx, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db_builder** out) {
+    if (!ctx || !ks || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    MLG_TRY(ensure_device(ctx));
+    return mlg_db_builder_create_impl(ctx, G, n, K, ks, nk, out);
+}
+MLG_API int mlg_db_builder_add_device(mlg_db_builder* b, const uint64_t* d_keys, uint32_t first_genome, uint32_t n_genomes) {
+    return mlg_db_builder_add_impl(b, reinterpret_cast<const key128*>(d_keys), first_genome, n_genomes);
+}
+MLG_API int mlg_db_builder_finish(mlg_db_builder* b, mlg_db** out) { return mlg_db_builder_finish_impl(b, out); }
+MLG_API int mlg_db_builder_destroy(mlg_db_builder* b) { mlg_db_builder_destroy_impl(b); return MLG_OK; }
+
 MLG_API int mlg_db_from_keys(mlg_ctx* ctx, const uint64_t* keys, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk,
                      mlg_db** out) {
     if (!ctx || !keys || !ks || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
     MLG_TRY(ensure_device(ctx));
-    size_t total = (size_t)G * n;
-    DevBuf<key128> d; MLG_TRY(d.alloc(total));
-    // on the stream the build runs on, then joined: the build never sees a copy still in flight
-    CUDA_TRY(cudaMemcpyAsync(d.p, keys, total * sizeof(key128), cudaMemcpyHostToDevice, ctx->s_comp));
-    CUDA_TRY(cudaStreamSynchronize(ctx->s_comp));
-    return mlg_db_build_device(ctx, d.p, G, n, K, ks, nk, out);
+    mlg_db_builder* b = nullptr;
+    MLG_TRY(mlg_db_builder_create_impl(ctx, G, n, K, ks, nk, &b));
+    const uint32_t step = std::max<uint32_t>(1u, (uint32_t)std::min<unsigned long long>(G, (16ull << 20) / n));   // <= 256 MB of keys per upload
+    DevBuf<key128> d;
+    int rc = d.alloc((size_t)step * n);
+    for (uint32_t g0 = 0; rc == MLG_OK && g0 < G; g0 += step) {
+        const uint32_t c = std::min<uint32_t>(step, G - g0);
+        // on the stream the build runs on, then joined: the build never sees a copy still in flight
+        if (cudaMemcpyAsync(d.p, keys + (size_t)g0 * n * 2, (size_t)c * n * sizeof(key128), cudaMemcpyHostToDevice, ctx->s_comp) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->s_comp) != cudaSuccess) { mlg_set_error("upload of the sketch keys failed: %s", cudaGetErrorString(cudaGetLastError())); rc = MLG_ERR_CUDA; break; }
+        rc = mlg_db_builder_add_impl(b, d.p, g0, c);
+    }
+    d.release();
+    if (rc == MLG_OK) rc = mlg_db_builder_finish_impl(b, out);
+    if (rc != MLG_OK) mlg_db_builder_destroy_impl(b);
+    return rc;
 }
 MLG_API int mlg_db_from_ascii(mlg_ctx* ctx, const char* kmers, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk,
                       mlg_db** out) {

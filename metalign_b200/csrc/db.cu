@@ -14,6 +14,7 @@
 // Everything runs on the device (CUB radix sorts / scans + small kernels).
 #include <cub/cub.cuh>
 #include <math.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 #include "mlg_internal.h"
@@ -265,18 +266,178 @@ void choose_buckets(DbView& v, uint32_t nd) {
     v.nbuckets = 1ull << bbits; v.bbits = bbits; v.slots = slots_per_bucket;
 }
 
+
+// ---------------------------------------------------------------- memory-lean build helpers
+// one chunk of genomes: non-empty slots flagged, emptiness noted per genome
+__global__ void k_mark_nonempty_chunk(const key128* keys, unsigned long long total, uint32_t n, uint32_t g0, unsigned char* flag,
+                                      unsigned char* has_empty) {
+    unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    bool e = key_is_empty(keys[s]);
+    flag[s] = e ? 0 : 1;
+    if (e) has_empty[g0 + s / n] = 1;
+}
+// the chunk's non-empty keys appended to the builder's split arrays; slot ids are global (g * n + j)
+__global__ void k_append_split(const key128* keys, const uint32_t* sel, uint32_t cnt, uint32_t slot0, unsigned long long* hi,
+                               unsigned long long* lo, uint32_t* slot) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const key128 k = keys[sel[i]];
+    hi[i] = k.hi; lo[i] = k.lo; slot[i] = slot0 + sel[i];
+}
+__global__ void k_canon_split2(const unsigned long long* hi, const unsigned long long* lo, uint32_t np, uint32_t K,
+                               unsigned long long* chi, unsigned long long* clo) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    key128 k; k.hi = hi[i]; k.lo = lo[i];
+    const key128 c = key_canon(k, K);
+    chi[i] = c.hi; clo[i] = c.lo;
+}
+__global__ void k_flag_heads2(const unsigned long long* hi, const unsigned long long* lo, uint32_t n, unsigned char* flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (i == 0 || hi[i] != hi[i - 1] || lo[i] != lo[i - 1]) ? 1 : 0;
+}
+__global__ void k_hash_keys2(const unsigned long long* hi, const unsigned long long* lo, uint32_t n, uint32_t K, uint32_t layout,
+                             uint32_t bbits, unsigned long long* h) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    key128 a; a.hi = hi[i]; a.lo = lo[i];
+    h[i] = layout == 2 ? key_hash_mz(a, K) : layout == 1 ? key_hash_sk(a, K, bbits) : key_hash(a, K);
+}
+__global__ void k_gather_key2(const unsigned long long* hi, const unsigned long long* lo, const uint32_t* idx, uint32_t n, key128* dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    key128 k; k.hi = hi[idx[i]]; k.lo = lo[idx[i]];
+    dst[i] = k;
+}
+
+// Two buffers a radix sort ping-pongs between (cub::DoubleBuffer): the sort then needs no scratch of the input's size,
+// which is what lets a 2e9-slot database build inside 180 GB.
+template <typename T>
+struct PingPong {
+    DevBuf<T> buf[2];
+    int sel = 0;
+    T* cur() { return buf[sel].p; }
+    T* alt() { return buf[sel ^ 1].p; }
+    int alloc_alt(size_t n) { return buf[sel ^ 1].alloc(n); }
+    void adopt(DevBuf<T>& src) { buf[0].release(); buf[0].p = src.p; buf[0].n = src.n; src.p = nullptr; src.n = 0; sel = 0; }
+    void drop_alt() { buf[sel ^ 1].release(); }
+    void drop() { buf[0].release(); buf[1].release(); }
+};
+// scratch for the CUB calls comes from the pool (which gives cached blocks back to the driver before it fails)
+template <typename KeyT, typename ValT>
+int radix_pairs(PingPong<KeyT>& k, PingPong<ValT>& v, uint32_t n, int begin_bit, int end_bit, cudaStream_t st) {
+    if (n == 0 || end_bit <= begin_bit) return MLG_OK;
+    cub::DoubleBuffer<KeyT> dk(k.cur(), k.alt());
+    cub::DoubleBuffer<ValT> dv(v.cur(), v.alt());
+    size_t tb = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)n, begin_bit, end_bit, st));
+    DevBuf<unsigned char> tmp; MLG_TRY(tmp.alloc(tb ? tb : 1));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int)n, begin_bit, end_bit, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { mlg_set_error("DeviceRadixSort failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
+    k.sel = dk.Current() == k.buf[0].p ? 0 : 1;
+    v.sel = dv.Current() == v.buf[0].p ? 0 : 1;
+    return MLG_OK;
+}
+template <typename T>
+int select_flagged(const T* in, const unsigned char* flags, T* out, unsigned long long* d_count, uint32_t n, cudaStream_t st) {
+    size_t tb = 0;
+    CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, tb, in, flags, out, d_count, (int)n, st));
+    DevBuf<unsigned char> tmp; MLG_TRY(tmp.alloc(tb ? tb : 1));
+    cudaError_t e = cub::DeviceSelect::Flagged(tmp.p, tb, in, flags, out, d_count, (int)n, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { mlg_set_error("DeviceSelect failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
+    return MLG_OK;
+}
+
 }  // namespace
 
-int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks,
-                        uint32_t nk, mlg_db** out) {
-    if (!ctx || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+// ---- the builder: genomes arrive in chunks (the caller never has to hold all G*n keys on the device), the non-empty
+// slots are kept as split (hi, lo, slot) arrays, and finish() derives the device structures from them stage by stage,
+// every stage releasing what the next one does not read.  Peak device memory for 2e9 slots: ~145 GB (the radix sorts
+// ping-pong between two buffers instead of taking scratch of the input's size, D is built before P, and the hit records
+// are only precomputed when they fit beside P and the class representatives).
+struct mlg_db_builder {
+    mlg_ctx* ctx = nullptr;
+    uint32_t G = 0, n = 0, K = 0, nk = 0, ks[MLG_MAX_KS] = {};
+    DevBuf<unsigned long long> hi, lo;
+    DevBuf<uint32_t> slot;
+    DevBuf<unsigned char> has_empty;
+    uint32_t np = 0, next_g = 0;
+};
+
+int mlg_db_builder_create_impl(mlg_ctx* ctx, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db_builder** out) {
+    if (!ctx || !out || !ks) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
     if (K < 1 || K > 63) { mlg_set_error("K=%u out of range 1..63", K); return MLG_ERR_ARG; }
     if (nk < 1 || nk > MLG_MAX_KS) { mlg_set_error("nk=%u out of range 1..%d", nk, MLG_MAX_KS); return MLG_ERR_ARG; }
     for (uint32_t i = 0; i < nk; ++i)
         if (ks[i] < 1 || ks[i] > K || (i && ks[i] <= ks[i - 1])) { mlg_set_error("ks must be ascending and within 1..K"); return MLG_ERR_ARG; }
     if (K - ks[0] + 1 > 64) { mlg_set_error("K - ks[0] + 1 must be <= 64"); return MLG_ERR_ARG; }
-    unsigned long long total = (unsigned long long)G * n;
+    const unsigned long long total = (unsigned long long)G * n;
     if (G == 0 || n == 0 || total >= 0x7FFFFFF0ull) { mlg_set_error("G*n=%llu out of range (1 .. 2^31-16)", total); return MLG_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    mlg_db_builder* b = new mlg_db_builder();
+    b->ctx = ctx; b->G = G; b->n = n; b->K = K; b->nk = nk;
+    for (uint32_t i = 0; i < nk; ++i) b->ks[i] = ks[i];
+    int rc = b->hi.alloc(total);
+    if (rc == MLG_OK) rc = b->lo.alloc(total);
+    if (rc == MLG_OK) rc = b->slot.alloc(total);
+    if (rc == MLG_OK) rc = b->has_empty.alloc(G);
+    if (rc == MLG_OK && cudaMemsetAsync(b->has_empty.p, 0, G, ctx->s_comp) != cudaSuccess) { mlg_set_error("memset failed"); rc = MLG_ERR_CUDA; }
+    if (rc != MLG_OK) { delete b; return rc; }
+    *out = b;
+    return MLG_OK;
+}
+
+int mlg_db_builder_add_impl(mlg_db_builder* b, const key128* d_keys, uint32_t g0, uint32_t count) {
+    if (!b || !d_keys) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (g0 != b->next_g || count == 0 || (unsigned long long)g0 + count > b->G) {
+        mlg_set_error("genomes must be added in order without gaps (expected genome %u, got %u..%u of %u)", b->next_g, g0, g0 + count, b->G);
+        return MLG_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->s_comp;
+    const unsigned long long total = (unsigned long long)count * b->n;
+    DevBuf<unsigned char> flag; MLG_TRY(flag.alloc(total));
+    DevBuf<uint32_t> sel; MLG_TRY(sel.alloc(total));
+    DevBuf<unsigned long long> d_cnt; MLG_TRY(d_cnt.alloc(1));
+    k_mark_nonempty_chunk<<<nblk(total), TPB, 0, st>>>(d_keys, total, b->n, g0, flag.p, b->has_empty.p);
+    {
+        cub::CountingInputIterator<uint32_t> it(0);
+        IsNonEmpty pred{flag.p};
+        size_t tb = 0;
+        CUDA_TRY(cub::DeviceSelect::If(nullptr, tb, it, sel.p, d_cnt.p, (int)total, pred, st));
+        DevBuf<unsigned char> tmp; MLG_TRY(tmp.alloc(tb ? tb : 1));
+        cudaError_t e = cub::DeviceSelect::If(tmp.p, tb, it, sel.p, d_cnt.p, (int)total, pred, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { mlg_set_error("DeviceSelect failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
+    }
+    unsigned long long c64 = 0;
+    CUDA_TRY(cudaMemcpy(&c64, d_cnt.p, 8, cudaMemcpyDeviceToHost));
+    const uint32_t c = (uint32_t)c64;
+    if (c) k_append_split<<<nblk(c), TPB, 0, st>>>(d_keys, sel.p, c, g0 * b->n, b->hi.p + b->np, b->lo.p + b->np, b->slot.p + b->np);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    b->np += c;
+    b->next_g = g0 + count;
+    return MLG_OK;
+}
+
+void mlg_db_builder_destroy_impl(mlg_db_builder* b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    delete b;
+}
+
+int mlg_db_builder_finish_impl(mlg_db_builder* b, mlg_db** out) {
+    if (!b || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (b->next_g != b->G) { mlg_set_error("only %u of %u genomes were added", b->next_g, b->G); return MLG_ERR_STATE; }
+    mlg_ctx* ctx = b->ctx;
+    const uint32_t G = b->G, n = b->n, K = b->K, nk = b->nk, np = b->np;
+    const uint32_t* ks = b->ks;
+    const unsigned long long total = (unsigned long long)G * n;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->s_comp;
     cudaEvent_t e0, e1; CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
@@ -286,130 +447,70 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
     db->ctx = ctx;
     struct Guard { mlg_db* d; ~Guard() { if (d) delete d; } } guard{db};
     DbView& v = db->v;
-    v.G = G; v.n = n; v.K = K; v.nk = nk;
+    v.G = G; v.n = n; v.K = K; v.nk = nk; v.np = np;
     // Metalign's K = 60 gets the minimizer-bitmap layout (kmer.cuh); other K keep the whole-k-mer hash layout.
     // MLG_LAYOUT=0 / 1 force the whole-k-mer hash layout / the fingerprint-pair super-k-mer layout (A/B measurements).
     v.layout = (K == 60) ? 2u : 0u;
     if (const char* s = getenv("MLG_LAYOUT")) { int x = atoi(s); if (x == 0 || (x == 1 && K == 60)) v.layout = (uint32_t)x; }
     for (uint32_t i = 0; i < MLG_MAX_KS; ++i) v.ks[i] = i < nk ? ks[i] : 0;
-
-    // 1. non-empty slots
-    DevBuf<unsigned char> flag; MLG_TRY(flag.alloc(total));
-    MLG_TRY(db->has_empty.alloc(G));
-    CUDA_TRY(cudaMemsetAsync(db->has_empty.p, 0, G, st));
-    k_mark_nonempty<<<nblk(total), TPB, 0, st>>>(d_keys, total, n, flag.p, db->has_empty.p);
-    DevBuf<uint32_t> slots; MLG_TRY(slots.alloc(total));
+    db->has_empty.p = b->has_empty.p; db->has_empty.n = b->has_empty.n; b->has_empty.p = nullptr; b->has_empty.n = 0;
     DevBuf<unsigned long long> d_cnt; MLG_TRY(d_cnt.alloc(1));
-    {
-        cub::CountingInputIterator<uint32_t> it(0);
-        IsNonEmpty pred{flag.p};
-        void* tmp = nullptr; size_t tb = 0;
-        CUDA_TRY(cub::DeviceSelect::If(nullptr, tb, it, slots.p, d_cnt.p, (int)total, pred, st));
-        CUDA_TRY(cudaMalloc(&tmp, tb ? tb : 1));
-        cudaError_t e = cub::DeviceSelect::If(tmp, tb, it, slots.p, d_cnt.p, (int)total, pred, st);
-        cudaStreamSynchronize(st); cudaFree(tmp);
-        if (e != cudaSuccess) { mlg_set_error("DeviceSelect failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
-    }
-    unsigned long long np64 = 0;
-    CUDA_TRY(cudaMemcpy(&np64, d_cnt.p, 8, cudaMemcpyDeviceToHost));
-    uint32_t np = (uint32_t)np64;
-    v.np = np;
-    flag.release();
+    const int lo_bits = (2 * K < 64) ? (int)(2 * K) : 64, hi_bits = (2 * K > 64) ? (int)(2 * K - 64) : 0;
+    const bool verbose = getenv("MLG_VERBOSE_BUILD") != nullptr;
+    auto stage = [&](const char* what) {      // MLG_VERBOSE_BUILD=1: device memory in use after every stage (stderr)
+        if (!verbose) return;
+        cudaStreamSynchronize(st);
+        mlg_pool_trim(ctx->device);
+        size_t f = 0, t = 0; cudaMemGetInfo(&f, &t);
+        fprintf(stderr, "[mlg build] %-28s in use %.1f GB of %.1f\n", what, (double)(t - f) / 1e9, (double)t / 1e9);
+    };
+    stage("builder arrays");
 
-    // 2. P: sort by key
-    MLG_TRY(db->P_key.alloc(np)); MLG_TRY(db->P_slot.alloc(np));
-    {
-        DevBuf<unsigned long long> hi, lo; MLG_TRY(hi.alloc(np)); MLG_TRY(lo.alloc(np));
-        if (np) k_gather_split<<<nblk(np), TPB, 0, st>>>(d_keys, slots.p, np, hi.p, lo.p);
-        MLG_TRY(sort_keys128(hi.p, lo.p, slots.p, np, K, db->P_key.p, db->P_slot.p, st));
-    }
-    slots.release();
-    v.P_key = db->P_key.p; v.P_slot = db->P_slot.p;
-
-    // 3. bucket index on the top pbits of the key
-    {
-        uint32_t pbits = 8;
-        while (pbits < 28 && (1ull << pbits) < np) ++pbits;
-        if (pbits > 2 * K) pbits = 2 * K;
-        v.pbits = pbits;
-        size_t m = (size_t)1 << pbits;
-        MLG_TRY(db->pidx.alloc(m + 1));
-        CUDA_TRY(cudaMemsetAsync(db->pidx.p, 0, (m + 1) * 4, st));
-        if (np) k_pbucket_hist<<<nblk(np), TPB, 0, st>>>(db->P_key.p, np, K, pbits, db->pidx.p);
-        MLG_TRY(exclusive_scan_u32(db->pidx.p, m, st));
-        v.pidx = db->pidx.p;
-    }
-
-    // 4. (genome, k-prefix) classes and denominators
-    MLG_TRY(db->rep.alloc((size_t)nk * total));
-    CUDA_TRY(cudaMemsetAsync(db->rep.p, 0xFF, (size_t)nk * total * 4, st));
-    MLG_TRY(db->den_real.alloc((size_t)G * nk));
-    CUDA_TRY(cudaMemsetAsync(db->den_real.p, 0, (size_t)G * nk * 8, st));
-    if (np) {
-        DevBuf<uint32_t> gkey, gkey_s, iota, q2p;
-        MLG_TRY(gkey.alloc(np)); MLG_TRY(gkey_s.alloc(np)); MLG_TRY(iota.alloc(np)); MLG_TRY(q2p.alloc(np));
-        k_slot_to_genome<<<nblk(np), TPB, 0, st>>>(db->P_slot.p, np, n, gkey.p);
-        k_iota<<<nblk(np), TPB, 0, st>>>(iota.p, np);
-        int gbits = 1; while (gbits < 32 && (1ull << gbits) < G) ++gbits;
-        MLG_TRY(sort_pairs_u32(gkey.p, gkey_s.p, iota.p, q2p.p, np, gbits, st));
-        for (uint32_t ki = 0; ki < nk; ++ki)
-            k_rep_classes<<<nblk(np), TPB, 0, st>>>(db->P_key.p, db->P_slot.p, q2p.p, np, n, K, ks[ki], ki, nk,
-                                                    db->rep.p + (size_t)ki * total, db->den_real.p);
-        CUDA_TRY(cudaStreamSynchronize(st));
-        CUDA_TRY(cudaGetLastError());
-    }
-    v.rep = db->rep.p;
-
-    // 5. D: distinct canonical keys, hash-ordered, with the level-1 fingerprint table
+    // 1. D first (it only reads the builder's arrays): distinct canonical keys with their multiplicities, hash-ordered
     uint32_t nd = 0;
     DevBuf<unsigned long long> hsorted;
     if (np) {
-        DevBuf<key128> csorted; MLG_TRY(csorted.alloc(np));
-        {
-            DevBuf<unsigned long long> hi, lo; MLG_TRY(hi.alloc(np)); MLG_TRY(lo.alloc(np));
-            k_canon_split<<<nblk(np), TPB, 0, st>>>(db->P_key.p, np, K, hi.p, lo.p);
-            MLG_TRY(sort_keys128(hi.p, lo.p, nullptr, np, K, csorted.p, nullptr, st));
-        }
+        PingPong<unsigned long long> chi, clo;
+        MLG_TRY(chi.buf[0].alloc(np)); MLG_TRY(clo.buf[0].alloc(np));
+        k_canon_split2<<<nblk(np), TPB, 0, st>>>(b->hi.p, b->lo.p, np, K, chi.cur(), clo.cur());
+        MLG_TRY(chi.alloc_alt(np)); MLG_TRY(clo.alloc_alt(np));
+        MLG_TRY(radix_pairs(clo, chi, np, 0, lo_bits, st));           // LSD: by the low word carrying the high one ...
+        MLG_TRY(radix_pairs(chi, clo, np, 0, hi_bits, st));           // ... then stably by the high word
+        chi.drop_alt(); clo.drop_alt();
         DevBuf<unsigned char> head; MLG_TRY(head.alloc(np));
-        k_flag_heads<<<nblk(np), TPB, 0, st>>>(csorted.p, np, head.p);
-        DevBuf<key128> duniq; MLG_TRY(duniq.alloc(np));
-        {
-            void* tmp = nullptr; size_t tb = 0;
-            CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, tb, csorted.p, head.p, duniq.p, d_cnt.p, (int)np, st));
-            CUDA_TRY(cudaMalloc(&tmp, tb ? tb : 1));
-            cudaError_t e = cub::DeviceSelect::Flagged(tmp, tb, csorted.p, head.p, duniq.p, d_cnt.p, (int)np, st);
-            cudaStreamSynchronize(st); cudaFree(tmp);
-            if (e != cudaSuccess) { mlg_set_error("DeviceSelect failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
-        }
+        k_flag_heads2<<<nblk(np), TPB, 0, st>>>(chi.cur(), clo.cur(), np, head.p);
+        // how many sketch slots hold each distinct K-mer (what `kmc -ci0` of the sketches' dump counts)
+        DevBuf<unsigned char> runlen; MLG_TRY(runlen.alloc(np));
+        k_run_lengths<<<nblk(np), TPB, 0, st>>>(head.p, np, runlen.p);
+        // upper bound of nd is np; the exact size is known after the first select, so select the smallest array first
+        DevBuf<unsigned char> multu_big; MLG_TRY(multu_big.alloc(np));
+        MLG_TRY(select_flagged(runlen.p, head.p, multu_big.p, d_cnt.p, np, st));
         unsigned long long nd64 = 0;
         CUDA_TRY(cudaMemcpy(&nd64, d_cnt.p, 8, cudaMemcpyDeviceToHost));
         nd = (uint32_t)nd64;
-        csorted.release();
-        // how many sketch slots hold each distinct K-mer (what `kmc -ci0` of the sketches' dump counts)
-        DevBuf<unsigned char> multu; MLG_TRY(multu.alloc(nd));
-        {
-            DevBuf<unsigned char> runlen; MLG_TRY(runlen.alloc(np));
-            k_run_lengths<<<nblk(np), TPB, 0, st>>>(head.p, np, runlen.p);
-            void* tmp = nullptr; size_t tb = 0;
-            CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, tb, runlen.p, head.p, multu.p, d_cnt.p, (int)np, st));
-            CUDA_TRY(cudaMalloc(&tmp, tb ? tb : 1));
-            cudaError_t e = cub::DeviceSelect::Flagged(tmp, tb, runlen.p, head.p, multu.p, d_cnt.p, (int)np, st);
-            cudaStreamSynchronize(st); cudaFree(tmp);
-            if (e != cudaSuccess) { mlg_set_error("DeviceSelect failed: %s", cudaGetErrorString(e)); return MLG_ERR_CUDA; }
-        }
+        runlen.release();
+        DevBuf<unsigned long long> dhi, dlo;
+        MLG_TRY(dhi.alloc(nd)); MLG_TRY(select_flagged(chi.cur(), head.p, dhi.p, d_cnt.p, np, st)); chi.drop();
+        MLG_TRY(dlo.alloc(nd)); MLG_TRY(select_flagged(clo.cur(), head.p, dlo.p, d_cnt.p, np, st)); clo.drop();
         head.release();
         // order by hash
-        DevBuf<unsigned long long> h; DevBuf<uint32_t> iota, perm;
-        MLG_TRY(h.alloc(nd)); MLG_TRY(hsorted.alloc(nd)); MLG_TRY(iota.alloc(nd)); MLG_TRY(perm.alloc(nd));
         choose_buckets(v, nd);
-        k_hash_keys<<<nblk(nd), TPB, 0, st>>>(duniq.p, nd, K, v.layout, v.bbits, h.p);
-        k_iota<<<nblk(nd), TPB, 0, st>>>(iota.p, nd);
-        MLG_TRY(sort_pairs_u64(h.p, hsorted.p, iota.p, perm.p, nd, 0, 64, st));
-        MLG_TRY(db->D_key.alloc(nd));
-        k_gather_key<<<nblk(nd), TPB, 0, st>>>(duniq.p, perm.p, nd, db->D_key.p);
+        PingPong<unsigned long long> h; PingPong<uint32_t> perm;
+        MLG_TRY(h.buf[0].alloc(nd)); MLG_TRY(perm.buf[0].alloc(nd));
+        k_hash_keys2<<<nblk(nd), TPB, 0, st>>>(dhi.p, dlo.p, nd, K, v.layout, v.bbits, h.cur());
+        k_iota<<<nblk(nd), TPB, 0, st>>>(perm.cur(), nd);
+        MLG_TRY(h.alloc_alt(nd)); MLG_TRY(perm.alloc_alt(nd));
+        MLG_TRY(radix_pairs(h, perm, nd, 0, 64, st));
+        h.drop_alt(); perm.drop_alt();
+        MLG_TRY(db->D_key.alloc((size_t)nd + 1));
+        CUDA_TRY(cudaMemsetAsync(db->D_key.p + nd, 0, sizeof(key128), st));
+        k_gather_key2<<<nblk(nd), TPB, 0, st>>>(dhi.p, dlo.p, perm.cur(), nd, db->D_key.p);
         MLG_TRY(db->D_mult.alloc(nd));
-        k_gather_u8<<<nblk(nd), TPB, 0, st>>>(multu.p, perm.p, nd, db->D_mult.p);
+        k_gather_u8<<<nblk(nd), TPB, 0, st>>>(multu_big.p, perm.cur(), nd, db->D_mult.p);
         CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+        // hsorted = the sorted hashes (bucket histogram and level-1 fill below)
+        hsorted.p = h.buf[h.sel].p; hsorted.n = h.buf[h.sel].n; h.buf[h.sel].p = nullptr; h.buf[h.sel].n = 0;
     } else {
         MLG_TRY(db->D_key.alloc(1)); MLG_TRY(hsorted.alloc(1));
     }
@@ -503,6 +604,98 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             }
         }
     }
+    hsorted.release();
+    mlg_pool_trim(ctx->device);
+    stage("D, level 1");
+
+    // 2. P: the non-empty slots in stored orientation sorted by key, slot id as payload
+    if (np) {
+        PingPong<unsigned long long> klo; PingPong<uint32_t> p1;
+        klo.adopt(b->lo);
+        MLG_TRY(p1.buf[0].alloc(np));
+        k_iota<<<nblk(np), TPB, 0, st>>>(p1.cur(), np);
+        MLG_TRY(klo.alloc_alt(np)); MLG_TRY(p1.alloc_alt(np));
+        MLG_TRY(radix_pairs(klo, p1, np, 0, lo_bits, st));
+        klo.drop_alt(); p1.drop_alt();                        // klo.cur() = low words sorted, p1.cur() = position -> builder index
+        if (hi_bits) {
+            PingPong<unsigned long long> khi; PingPong<uint32_t> p2;
+            MLG_TRY(khi.buf[0].alloc(np));
+            k_gather_u64<<<nblk(np), TPB, 0, st>>>(b->hi.p, p1.cur(), np, khi.cur());
+            CUDA_TRY(cudaStreamSynchronize(st));
+            b->hi.release();
+            MLG_TRY(p2.buf[0].alloc(np));
+            k_iota<<<nblk(np), TPB, 0, st>>>(p2.cur(), np);
+            MLG_TRY(khi.alloc_alt(np)); MLG_TRY(p2.alloc_alt(np));
+            MLG_TRY(radix_pairs(khi, p2, np, 0, hi_bits, st));
+            khi.drop_alt(); p2.drop_alt();                    // p2.cur() = position -> position in the low-word order
+            MLG_TRY(db->P_key.alloc(np));
+            k_zip_keys<<<nblk(np), TPB, 0, st>>>(khi.cur(), klo.cur(), p2.cur(), np, db->P_key.p);
+            CUDA_TRY(cudaStreamSynchronize(st));
+            khi.drop(); klo.drop();
+            DevBuf<uint32_t> fin; MLG_TRY(fin.alloc(np));
+            k_gather_u32<<<nblk(np), TPB, 0, st>>>(p1.cur(), p2.cur(), np, fin.p);      // builder index = p1[p2[i]]
+            CUDA_TRY(cudaStreamSynchronize(st));
+            p1.drop(); p2.drop();
+            MLG_TRY(db->P_slot.alloc(np));
+            k_gather_u32<<<nblk(np), TPB, 0, st>>>(b->slot.p, fin.p, np, db->P_slot.p);
+            CUDA_TRY(cudaStreamSynchronize(st));
+        } else {
+            b->hi.release();
+            DevBuf<unsigned long long> zero; MLG_TRY(zero.alloc(np));
+            CUDA_TRY(cudaMemsetAsync(zero.p, 0, (size_t)np * 8, st));
+            MLG_TRY(db->P_key.alloc(np));
+            k_zip_keys<<<nblk(np), TPB, 0, st>>>(zero.p, klo.cur(), nullptr, np, db->P_key.p);
+            MLG_TRY(db->P_slot.alloc(np));
+            k_gather_u32<<<nblk(np), TPB, 0, st>>>(b->slot.p, p1.cur(), np, db->P_slot.p);
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        MLG_TRY(db->P_key.alloc(1)); MLG_TRY(db->P_slot.alloc(1));
+    }
+    b->hi.release(); b->lo.release(); b->slot.release();
+    v.P_key = db->P_key.p; v.P_slot = db->P_slot.p;
+    mlg_pool_trim(ctx->device);
+    stage("P");
+
+    // 3. bucket index on the top pbits of the key
+    {
+        uint32_t pbits = 8;
+        while (pbits < 28 && (1ull << pbits) < np) ++pbits;
+        if (pbits > 2 * K) pbits = 2 * K;
+        v.pbits = pbits;
+        size_t m = (size_t)1 << pbits;
+        MLG_TRY(db->pidx.alloc(m + 1));
+        CUDA_TRY(cudaMemsetAsync(db->pidx.p, 0, (m + 1) * 4, st));
+        if (np) k_pbucket_hist<<<nblk(np), TPB, 0, st>>>(db->P_key.p, np, K, pbits, db->pidx.p);
+        MLG_TRY(exclusive_scan_u32(db->pidx.p, m, st));
+        v.pidx = db->pidx.p;
+    }
+
+    // 4. (genome, k-prefix) classes and denominators
+    MLG_TRY(db->rep.alloc((size_t)nk * total));
+    CUDA_TRY(cudaMemsetAsync(db->rep.p, 0xFF, (size_t)nk * total * 4, st));
+    MLG_TRY(db->den_real.alloc((size_t)G * nk));
+    CUDA_TRY(cudaMemsetAsync(db->den_real.p, 0, (size_t)G * nk * 8, st));
+    if (np) {
+        PingPong<uint32_t> gkey, q2p;
+        MLG_TRY(gkey.buf[0].alloc(np)); MLG_TRY(q2p.buf[0].alloc(np));
+        k_slot_to_genome<<<nblk(np), TPB, 0, st>>>(db->P_slot.p, np, n, gkey.cur());
+        k_iota<<<nblk(np), TPB, 0, st>>>(q2p.cur(), np);
+        int gbits = 1; while (gbits < 32 && (1ull << gbits) < G) ++gbits;
+        MLG_TRY(gkey.alloc_alt(np)); MLG_TRY(q2p.alloc_alt(np));
+        MLG_TRY(radix_pairs(gkey, q2p, np, 0, gbits, st));
+        gkey.drop(); q2p.drop_alt();
+        for (uint32_t ki = 0; ki < nk; ++ki)
+            k_rep_classes<<<nblk(np), TPB, 0, st>>>(db->P_key.p, db->P_slot.p, q2p.cur(), np, n, K, ks[ki], ki, nk,
+                                                    db->rep.p + (size_t)ki * total, db->den_real.p);
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaGetLastError());
+    }
+    v.rep = db->rep.p;
+    mlg_pool_trim(ctx->device);
+    stage("classes");
+
     // 6. hit records: what a present k-mer of D contributes to the per-genome table is a static function of the
     //    database, so it is expanded once here (same code as the on-the-fly kernel) and replayed per query.  Two passes:
     //    tally (sizes; the common one-slot records are complete after it) -> offsets -> fill.  Afterwards P, its bucket
@@ -534,26 +727,61 @@ int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t
             CUDA_TRY(cudaStreamSynchronize(st));
             CUDA_TRY(cudaGetLastError());
             const unsigned long long keep_words = total_words < drop_from ? total_words : drop_from;
-            MLG_TRY(db->hits.alloc(keep_words + 2 + MLG_MAX_KS));
-            MLG_TRY(launch_fill_hits(v, summary.p, db->hoff.p, db->hbase.p, db->hits.p, drop_from, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            CUDA_TRY(cudaGetLastError());
-            db->hit_words = keep_words;
-            const char* kp = getenv("MLG_KEEP_P");
-            if (drop_from == ~0ull && !(kp && atoi(kp) != 0)) {
-                db->P_key.release(); db->P_slot.release(); db->pidx.release(); db->rep.release();
-                v.P_key = nullptr; v.P_slot = nullptr; v.pidx = nullptr; v.rep = nullptr;
-                db->p_dropped = true;
+            // The records have to fit BESIDE P and the class representatives, which the fill still reads (afterwards those
+            // go, and a query's own tables take their place).  When they do not (2e9 slots: P + rep are 73 GB), the
+            // database keeps P and every query expands its present k-mers on the fly -- |I| x 240 sectors, well under a
+            // millisecond more per query -- instead of failing.  MLG_HIT_BUDGET_BYTES overrides the free-memory figure (tests).
+            mlg_pool_trim(ctx->device);
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            if (const char* s = getenv("MLG_HIT_BUDGET_BYTES")) free_b = (size_t)strtoull(s, nullptr, 10);
+            const unsigned long long need = (keep_words + 2 + MLG_MAX_KS) * 4ull + (256ull << 20);
+            if (verbose) fprintf(stderr, "[mlg build] hit records need %.1f GB, free %.1f GB\n", (double)need / 1e9, (double)free_b / 1e9);
+            if (need > free_b) {
+                summary.release(); db->hoff.release(); db->hbase.release();
+                db->hit_words = 0;
+                db->hits_skipped_bytes = need;
+            } else {
+                MLG_TRY(db->hits.alloc(keep_words + 2 + MLG_MAX_KS));
+                MLG_TRY(launch_fill_hits(v, summary.p, db->hoff.p, db->hbase.p, db->hits.p, drop_from, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                CUDA_TRY(cudaGetLastError());
+                db->hit_words = keep_words;
+                const char* kp = getenv("MLG_KEEP_P");
+                if (drop_from == ~0ull && !(kp && atoi(kp) != 0)) {
+                    db->P_key.release(); db->P_slot.release(); db->pidx.release(); db->rep.release();
+                    v.P_key = nullptr; v.P_slot = nullptr; v.pidx = nullptr; v.rep = nullptr;
+                    db->p_dropped = true;
+                }
             }
         }
     }
+    stage("hit records");
     CUDA_TRY(cudaEventRecord(e1, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); db->build_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     guard.d = nullptr;
+    delete b;
     mlg_pool_trim(ctx->device);   // the build's multi-GB temporaries should not stay cached
     *out = db;
     return MLG_OK;
+}
+
+int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks,
+                        uint32_t nk, mlg_db** out) {
+    if (!ctx || !out) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    mlg_db_builder* b = nullptr;
+    MLG_TRY(mlg_db_builder_create_impl(ctx, G, n, K, ks, nk, &b));
+    // in chunks, so that the scratch of the compaction stays small beside the caller's keys
+    const uint32_t step = std::max<uint32_t>(1u, (uint32_t)std::min<unsigned long long>(G, (256ull << 20) / n));
+    for (uint32_t g0 = 0; g0 < G; g0 += step) {
+        const uint32_t c = std::min<uint32_t>(step, G - g0);
+        int rc = mlg_db_builder_add_impl(b, d_keys + (size_t)g0 * n, g0, c);
+        if (rc != MLG_OK) { mlg_db_builder_destroy_impl(b); return rc; }
+    }
+    int rc = mlg_db_builder_finish_impl(b, out);
+    if (rc != MLG_OK) mlg_db_builder_destroy_impl(b);
+    return rc;
 }

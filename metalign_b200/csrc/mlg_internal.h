@@ -113,6 +113,7 @@ struct mlg_db {
     DevBuf<unsigned long long> hbase; // 64-bit word offset of every group of 2^MLG_HGROUP_SHIFT k-mers' records
     unsigned long long hit_words = 0;
     bool p_dropped = false;          // P / pidx / rep were released after the hit records were built
+    unsigned long long hits_skipped_bytes = 0;   // != 0: the hit records (this many bytes) did not fit beside P; queries expand on the fly
     DevBuf<unsigned char> clean_cnt8; // an all-zero counter table handed from one finished query to the next (no 0.16 GB memset per query)
     DevBuf<long long> den_real;      // G*nk
     DevBuf<unsigned char> has_empty; // G
@@ -121,6 +122,12 @@ struct mlg_db {
 
 int mlg_db_build_device(mlg_ctx* ctx, const key128* d_keys, uint32_t G, uint32_t n, uint32_t K,
                         const uint32_t* ks, uint32_t nk, mlg_db** out);
+// the same build fed chunk by chunk (db.cu): the caller never holds all G*n keys on the device
+struct mlg_db_builder;
+int mlg_db_builder_create_impl(mlg_ctx* ctx, uint32_t G, uint32_t n, uint32_t K, const uint32_t* ks, uint32_t nk, mlg_db_builder** out);
+int mlg_db_builder_add_impl(mlg_db_builder* b, const key128* d_keys, uint32_t g0, uint32_t count);
+int mlg_db_builder_finish_impl(mlg_db_builder* b, mlg_db** out);      // frees the builder on success
+void mlg_db_builder_destroy_impl(mlg_db_builder* b);
 // .mlgdb files (dbfile.cu): version 1 = source keys (built on load), version 2 = the built structures
 int mlg_db_load_file(mlg_ctx* ctx, const char* path, mlg_db** out);
 int mlg_db_save_file(const mlg_db* db, const char* path, const char* names, uint64_t names_bytes);

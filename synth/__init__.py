@@ -63,6 +63,8 @@ def cuda_lib():
         pp = C.POINTER(SynthParams)
         L.syn_cuda_gen_sketch_keys.argtypes = [pp, C.c_void_p, C.c_void_p]
         L.syn_cuda_gen_sketch_keys.restype = C.c_int
+        L.syn_cuda_gen_sketch_keys_range.argtypes = [pp, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.syn_cuda_gen_sketch_keys_range.restype = C.c_int
         L.syn_cuda_gen_reads_packed.argtypes = [pp, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.syn_cuda_gen_reads_packed.restype = C.c_int
         _CUDA = L

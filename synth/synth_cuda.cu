@@ -52,6 +52,23 @@ SYN_API int syn_cuda_gen_sketch_keys(const syn_params* p, void* d_keys, void* st
     return e == cudaSuccess ? 0 : fail("sketch_keys", e);
 }
 
+// the sketch keys of genomes [g0, g0 + count) only (a 2e9-slot database is generated and handed over chunk by chunk)
+__global__ void k_sketch_keys_range(syn_params p, uint32_t g0, uint64_t total, uint64_t* keys) {
+    uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    uint64_t hi, lo;
+    syn_sketch_key(&p, g0 + (uint32_t)(s / p.n), (uint32_t)(s % p.n), &hi, &lo);
+    keys[2 * s] = hi; keys[2 * s + 1] = lo;
+}
+SYN_API int syn_cuda_gen_sketch_keys_range(const syn_params* p, uint32_t g0, uint32_t count, void* d_keys, void* stream) {
+    uint64_t total = (uint64_t)count * p->n;
+    k_sketch_keys_range<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p, g0, total, (uint64_t*)d_keys);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("sketch_keys_range launch", e);
+    e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? 0 : fail("sketch_keys_range", e);
+}
+
 // bases: packed_sizes(nreads, L)[0] bytes, nmask: packed_sizes(...)[1] bytes (both multiples of 16, device)
 SYN_API int syn_cuda_gen_reads_packed(const syn_params* p, uint64_t r0, uint64_t nreads, void* d_bases, void* d_nmask,
                                       void* stream) {

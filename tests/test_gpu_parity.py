@@ -630,13 +630,16 @@ def test_minimizer_ties_use_the_alias_table(ctx, monkeypatch):
     db.close()
 
 
-@pytest.mark.parametrize("mode", ["off", "tiny_buffer"])
+@pytest.mark.parametrize("mode", ["off", "tiny_buffer", "no_room"])
 def test_hit_list_fallbacks(ctx, workload, monkeypatch, mode):
-    """the per-k-mer hit lists are precomputed at database build; without them (MLG_PRECOMPUTE_HITS=0), or for the
-    k-mers that did not fit the buffer, the same expansion runs on the fly at query time"""
+    """the per-k-mer hit lists are precomputed at database build; without them (MLG_PRECOMPUTE_HITS=0), for the k-mers
+    that did not fit the buffer, or when the records do not fit the device beside P (what happens at 2e9 slots; here the
+    free-memory figure is overridden), the same expansion runs on the fly at query time"""
     w = workload
     if mode == "off":
         monkeypatch.setenv("MLG_PRECOMPUTE_HITS", "0")
+    elif mode == "no_room":
+        monkeypatch.setenv("MLG_HIT_BUDGET_BYTES", "4096")
     else:
         monkeypatch.setenv("MLG_HIT_CAP_WORDS", "4000")      # room for a few hundred of the ~60000 k-mers
     db = Database.from_keys(ctx, w["keys"], w["p"].G, w["p"].n, 60, KS)
@@ -647,6 +650,36 @@ def test_hit_list_fallbacks(ctx, workload, monkeypatch, mode):
         _check(res, q.intersection(), *w["refs"][gate], tag=(mode, gate))
         q.close()
     db.close()
+
+
+def test_database_built_from_chunks(ctx, workload):
+    """mlg_db_builder_*: the database handed over a few genomes at a time (device buffers, reused) answers like the one
+    built from all keys at once; genomes out of order, a gap, or a missing tail are refused"""
+    import torch
+    w = workload
+    p = w["p"]
+    keys = torch.from_numpy(w["keys"].view(np.int64).reshape(-1)).cuda()
+    step = max(1, p.G // 7)
+    buf = torch.empty(step * p.n * 2, dtype=torch.int64, device="cuda")
+
+    def chunks(stop=p.G, first=0):
+        for g0 in range(first, stop, step):
+            c = min(step, stop - g0)
+            buf[: c * p.n * 2].copy_(keys[g0 * p.n * 2:(g0 + c) * p.n * 2])
+            torch.cuda.synchronize()
+            yield buf.data_ptr(), g0, c
+    db = Database.from_device_chunks(ctx, chunks(), p.G, p.n, 60, KS)
+    for gate in ("exact", "none"):
+        q = db.query(2, gate, True)
+        q.push_packed(w["bases"], w["nmask"], None, w["nreads"], p.read_len)
+        res = q.finish()
+        _check(res, q.intersection(), *w["refs"][gate], tag=("chunks", gate))
+        q.close()
+    db.close()
+    with pytest.raises(MlgError):
+        Database.from_device_chunks(ctx, chunks(stop=p.G - 1), p.G, p.n, 60, KS)         # a genome short
+    with pytest.raises(MlgError):
+        Database.from_device_chunks(ctx, chunks(first=step), p.G, p.n, 60, KS)           # does not start at genome 0
 
 
 def test_full_size_properties(ctx):
