@@ -753,6 +753,67 @@ def test_full_size_properties(ctx):
     db.close()
 
 
+def test_ten_x_database_on_one_gpu(ctx):
+    """BASELINE.json configs[4]'s database at FULL size -- 2e6 genomes x 1000 slots (2e9 slots, 1.6e9 distinct k-mers) --
+    built through the chunk-fed builder on one GPU.  The oracle cannot hold this database, so the check is a round trip
+    that exercises the high end of every index: the sketches of 48 genomes spread over the whole range (the last genome
+    included) become reads -- every sketch k-mer twice, in a random orientation, with random flanks -- and
+      (a) the intersection is exactly the canonical forms of those k-mers,
+      (b) for the sampled genomes num / den / ci at every k equal what the C oracle computes from the database that
+          holds those 48 genomes alone (other genomes cannot take hits away: forward and reverse-complement prefixes of
+          unrelated random sequence do not coincide),
+      (c) a genome that is not sampled, and no strain of a sampled one, collects nothing at k = 60."""
+    import torch
+    G, n = 2_000_000, 1000
+    free_b, total_b = torch.cuda.mem_get_info()
+    if total_b < 150 * (1 << 30):
+        pytest.skip("needs a 180 GB device")
+    p = synth.params(G=G, n=n, seed=20200529, n_present=500)
+    step = 100_000
+    d_chunk = torch.empty(step * n * 2, dtype=torch.int64, device="cuda")
+
+    def chunks():
+        for g0 in range(0, G, step):
+            c = min(step, G - g0)
+            assert synth.cuda_lib().syn_cuda_gen_sketch_keys_range(C.byref(p), g0, c, d_chunk.data_ptr(), None) == 0
+            yield d_chunk.data_ptr(), g0, c
+    db = Database.from_device_chunks(ctx, chunks(), G, n, 60, KS)
+    rng = random.Random(4)
+    sample = sorted({0, 1, G // 2, G - 2, G - 1} | {rng.randrange(G) for _ in range(43)})
+    sub = np.empty((len(sample) * n, 2), dtype=np.uint64)
+    for i, g in enumerate(sample):
+        assert synth.cuda_lib().syn_cuda_gen_sketch_keys_range(C.byref(p), g, 1, d_chunk.data_ptr(), None) == 0
+        sub[i * n:(i + 1) * n] = d_chunk[: n * 2].cpu().numpy().view(np.uint64).reshape(-1, 2)
+    del d_chunk
+    reads = []
+    for hi, lo in sub:
+        if hi == codec.EMPTY:
+            continue
+        x = codec.key_to_kmer(int(hi), int(lo), 60)
+        for _ in range(2):
+            y = oracle_py.rc(x) if rng.random() < 0.5 else x
+            reads.append("".join(rng.choice("ACGT") for _ in range(rng.randint(0, 40))) + y + "".join(rng.choice("ACGT") for _ in range(rng.randint(0, 40))))
+    rng.shuffle(reads)
+    q = db.query()
+    q.push_reads(reads)
+    res = q.finish()
+    I_gpu = q.intersection()
+    q.close()
+    db.close()
+    ref, I_ref = oracle_c_run(sub, len(sample), n, 60, KS, lambda oq: oq.push_reads(reads))
+    assert np.array_equal(I_gpu, I_ref) and len(I_ref) > 40_000, (len(I_gpu), len(I_ref))
+    idx = np.asarray(sample)
+    assert np.array_equal(res["den"][idx], ref["den"])
+    assert np.array_equal(res["num"][idx], ref["num"]) and np.array_equal(res["ci"][idx], ref["ci"])
+    assert (ref["num"][:, -1] > 0).all()
+    hit60 = set(np.nonzero(res["num"][:, -1])[0].tolist())
+    # strains share sketch positions with their parent genome (synth_core.h): a hit outside the sample is a relative of a sampled genome
+    related = set()
+    for g in sample:
+        related.update(range(max(0, g - p.strain_period), min(G, g + p.strain_period + 1)))
+    assert set(sample) <= hit60 and hit60 <= related, sorted(hit60 - related)[:10]
+
+
 def test_headline_config_against_oracle(ctx):
     """BASELINE.json configs[1] at FULL size -- 2e5 genomes x 1000 slots, 10 M x 150 bp reads, the workload bench.py
     quotes its headline on -- with the complete per-genome tables and the intersection compared with the C oracle
