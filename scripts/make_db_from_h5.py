@@ -4,9 +4,8 @@ hands to StreamingQueryDNADatabase.py, e.g. data/cmash_db_n1000_k60.h5).
 
     python scripts/make_db_from_h5.py cmash_db_n1000_k60.h5 out.mlgdb [--k_range 30-60-10]
 
-Needs h5py (a CMash dependency, so present wherever the reference runs; NOT in this repo's build image -- there
-scripts/make_db.py converts the FASTA dump of local_tests/dump_kmers.py instead, or scripts/make_sketch_db.py builds the
-sketches from the genome files).  Layout read: group `CountEstimators`, one sub-group per genome keyed by
+Reads the file with h5py where it is installed and with the built-in minimal reader (metalign_b200/h5min.py: the HDF5
+flavour h5py writes by default) where it is not -- this repo's build image has no h5py.  Layout read: group `CountEstimators`, one sub-group per genome keyed by
 the basename of its training file, dataset `kmers` (n fixed-length byte strings, '' for an unused slot), attribute `ksize`;
 genomes in sorted-key order, which is the order MinHash.import_multiple_from_single_hdf5 -- and therefore
 dump_kmers.py:7-14 and the query script -- see them in.
@@ -21,26 +20,35 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from metalign_b200 import codec, dbformat  # noqa: E402
 
 
-def read_h5(path):
+def _open(path):
+    """(file object with h5py's mapping interface, function that reads a dataset)"""
     try:
         import h5py
+        return h5py.File(path, "r"), (lambda d: d[...])
     except ImportError:
-        sys.exit("make_db_from_h5.py needs h5py; without it, dump the k-mers with the reference's local_tests/dump_kmers.py and "
-                 "use scripts/make_db.py, or build the database from the genome files with scripts/make_sketch_db.py")
-    with h5py.File(path, "r") as f:
+        from metalign_b200 import h5min
+        return h5min.H5File(path), (lambda d: d.read())
+
+
+def read_h5(path):
+    f, read = _open(path)
+    try:
         grp = f["CountEstimators"]
         names = sorted(grp.keys())
         K = n = None
         slots = []
         for name in names:
             g = grp[name]
-            kmers = [k.decode() if isinstance(k, bytes) else str(k) for k in g["kmers"][...]]
-            k_here = int(g.attrs["ksize"]) if "ksize" in g.attrs else max((len(x) for x in kmers), default=0)
+            kmers = [k.decode() if isinstance(k, bytes) else str(k) for k in read(g["kmers"])]
+            attrs = g.attrs
+            k_here = int(attrs["ksize"]) if "ksize" in attrs else max((len(x) for x in kmers), default=0)
             if K is None:
                 K, n = k_here, len(kmers)
             if k_here != K or len(kmers) != n:
                 sys.exit("sketch %s has ksize %d / %d slots, expected %d / %d" % (name, k_here, len(kmers), K, n))
             slots.append(kmers)
+    finally:
+        f.close()
     return names, slots, K, n
 
 
