@@ -153,8 +153,11 @@ __device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long
     w.s = w.e = w.j0 = w.j1 = 0;
     w.cn.hi = w.cn.lo = 0; w.d0 = w.cn; w.d1 = w.cn;
     if (!on) return;
-    unsigned long long mh, ml;
-    mz_bases64(bsrc, base_words, pm, mh, ml);
+    // the window's 64 bases from p hold its minimizer too: it starts at most 28 bases in (pm - p <= K - 32)
+    key128 F;
+    mz_bases64(bsrc, base_words, p, F.hi, F.lo);
+    const unsigned dsh = 2u * (unsigned)(pm - p);
+    const unsigned long long mh = dsh ? ((F.hi << dsh) | (F.lo >> (64u - dsh))) : F.hi;
     const uint32_t ha = (uint32_t)(mh >> 32), hb = rev2_32(~(uint32_t)mh);
     const uint32_t zhi = mz_ident_hi(ha, hb), zlo = mz_ident_lo(ha, hb);
     const uint32_t bucket = zhi >> (32u - db.bbits);
@@ -167,8 +170,6 @@ __device__ __forceinline__ void mz_window_begin(MzWin& w, bool on, unsigned long
         w.j0 = w.j1 = lo;
         while (w.j1 < db.n_alias && db.alias_z[w.j1] == z) ++w.j1;
     }
-    key128 F;                                                       // 64 bases from p, top-aligned
-    mz_bases64(bsrc, base_words, p, F.hi, F.lo);
     F = key_shr(F, 128 - 2 * SK_K);                                 // the 60-mer, bottom-aligned
     const key128 G = key_rc(F, SK_K);
     w.cn = key_lt(G, F) ? G : F;
@@ -257,9 +258,11 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned long long nreads = a.r_end - a.r_begin;
     const unsigned long long ntiles = (nreads + MZ_TR - 1) / MZ_TR;       // a tile = MZ_TR reads: MZ_TR / 32 warp passes
+    // the hand-out counter: 32 bits are plenty (a tile is >= 32 reads), and the word above it stays zero
+    unsigned int* const tile_ctr = reinterpret_cast<unsigned int*>(a.tile_counter);
     auto next_tile = [&]() -> unsigned long long {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.tile_counter, 1ull);
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(tile_ctr, 1u);
         return __shfl_sync(FULL, t, 0);
     };
     const unsigned long long pol_stream = policy_evict_first();
@@ -528,7 +531,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         }
         }
         __syncwarp();             // every lane is done with this stage's staged bases before it is refilled
-        const unsigned long long t_new = next_tile();
+        const unsigned long long t_new = next_tile();      // (asking for it at the start of the tile instead changes nothing: 2.164 ms either way, r4h)
         if (lane == 0 && t_new < ntiles) issue(stage, t_new);
         t = t_ahead; t_ahead = t_new;
     }
