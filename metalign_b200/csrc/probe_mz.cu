@@ -191,8 +191,15 @@ __device__ __forceinline__ void mz_window_end(const MzWin& w, const DbView& db, 
     }
 }
 // exact compare of every window of every waiting item of one warp, one WINDOW per lane (items have 1..16 windows)
+// `a` and `db` are the kernel's __grid_constant__ parameters: the references point into parameter space, so nothing is
+// copied to the stack for the call (before, every thread kept a 232-byte copy of both structs in local memory and the
+// drain read its fields from there: 5.4 M local loads per 10 M reads, 18-27 % of them missing the L1).  Speed is the same
+// within run-to-run noise (2.15 ms); what is left on the stack are two values parked around the block loop.
 __device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const uint32_t* qc, uint32_t* qb, uint32_t* qoff,
-                                      const unsigned long long* bsrc, unsigned long long base_words, const DbView& db, const CountSink& cs) {
+                                      const ProbeArgs& a, const DbView& db) {
+    const unsigned long long* const bsrc = a.bases;
+    const unsigned long long base_words = a.base_words;
+    const CountSink cs{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = threadIdx.x & 31u;
     __syncwarp();
@@ -243,7 +250,7 @@ __device__ __noinline__ void mz_drain(uint32_t* qn, const uint32_t* qa, const ui
 }
 
 template <bool HAS_NMASK>
-__global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a, DbView db) {
+__global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(const __grid_constant__ ProbeArgs a, const __grid_constant__ DbView db) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MzShared& sm = *reinterpret_cast<MzShared*>(smem_raw);
     MzStage& stg = sm.stg;
@@ -266,7 +273,6 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         return __shfl_sync(FULL, t, 0);
     };
     const unsigned long long pol_stream = policy_evict_first();
-    const CountSink sink{a.cnt8, a.present, a.n_present, a.touched, a.ci_min};
     const uint32_t wm_base = smem_u32(&sm.wm[0][tid]), seq_base = smem_u32(&sm.seq[0][tid]);
     const uint32_t* const MB = db.F;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
         }
     };
 
-    unsigned long long my_valid = 0;
+    unsigned my_valid = 0;                    // per lane: a launch would need > 3e14 windows to overflow it
     unsigned my_fetch = 0;
     if (lane == 0) sm.qn[warp] = 0;
     __syncwarp();
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
     auto drain = [&]() {
         // items carry stream positions and the drain reads the bases from global memory (L2: they were just streamed in), so
         // items survive the tile they come from and a drain always has >= MZ_QDRAIN items' windows to spread over the lanes
-        mz_drain(&sm.qn[warp], &sm.qa[warp][0], &sm.qc[warp][0], &sm.qb[warp][0], &sm.qoff[warp][0], a.bases, a.base_words, db, sink);
+        mz_drain(&sm.qn[warp], &sm.qa[warp][0], &sm.qc[warp][0], &sm.qb[warp][0], &sm.qoff[warp][0], a, db);
     };
     // lanes with p append one item: windows `ik` of the block whose first window is at stream base `pb`, minimizer at base `rel` of the block
     auto push = [&](bool p, unsigned long long pb, uint32_t ik, uint32_t rel) {
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
 
         for (unsigned seg = 0; seg < max_seg; ++seg) {
             const unsigned c = seg < nseg ? (unsigned)((nw - (unsigned long long)seg * WMAX) < WMAX ? (nw - (unsigned long long)seg * WMAX) : WMAX) : 0u;
-            const unsigned long long s = R0 + (unsigned long long)seg * WMAX;
+            const unsigned long long s = bw0_32 + brel0 + (unsigned long long)seg * WMAX;      // = R0 + seg * WMAX
 
             uint32_t loc[SEGW];
             uint32_t nl[5];
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                     nnr = 1u + __popc(nchg);
                     nvm = vwin & ~ovfm;
                     if (__any_sync(FULL, t3 != 0u)) {
-                        const unsigned long long ia = R0 + (unsigned long long)seg * WMAX + blk16;
+                        const unsigned long long ia = s_bw0[warp][stage] * 32ull + brel0 + (unsigned long long)seg * WMAX + blk16;
                         uint32_t rest = t3;
                         unsigned rr = MZ_MAXRUN;
                         while (__any_sync(FULL, rest != 0u)) {
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
                     const uint32_t m0 = (c1 - 1u) & pvm, m1 = (c2 - c1) & pvm, m2 = (c3 - c2) & pvm, m3 = (0x10000u - c3) & pvm;
                     const bool q0 = b0 & (m0 != 0u), q1 = b1 & (m1 != 0u), q2 = b2 & (m2 != 0u), q3 = b3 & (m3 != 0u);
                     if (__any_sync(FULL, q0 | q1 | q2 | q3)) {
-                        const unsigned long long ia = R0 + (unsigned long long)seg * WMAX + pblk;
+                        const unsigned long long ia = s_bw0[warp][stage] * 32ull + brel0 + (unsigned long long)seg * WMAX + pblk;
                         push(q0, ia, m0, pW & 63u);
                         push(q1, ia, m1, (pW >> 8) & 63u);
                         push(q2, ia, m2, (pW >> 16) & 63u);
@@ -537,9 +543,10 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(ProbeArgs a
     }
 
     drain();                      // the items still waiting
-    for (int o = 16; o > 0; o >>= 1) my_valid += __shfl_down_sync(FULL, my_valid, o);
+    unsigned long long warp_valid = my_valid;
+    for (int o = 16; o > 0; o >>= 1) warp_valid += __shfl_down_sync(FULL, warp_valid, o);
     my_fetch = __reduce_add_sync(FULL, my_fetch);
-    if (lane == 0 && my_valid) atomicAdd(a.n_kmers, my_valid);
+    if (lane == 0 && warp_valid) atomicAdd(a.n_kmers, warp_valid);
     if (lane == 0 && my_fetch) atomicAdd(a.n_kmers + 1, (unsigned long long)my_fetch);
 }
 
@@ -553,6 +560,8 @@ int launch_mz_t(const DbView& db, const ProbeArgs& a, cudaStream_t st, unsigned 
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !done[dev]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1MZ_SMEM));
+        // MLG_PROBE_CARVEOUT=<percent of the SM's 228 KB>: shared-memory carve-out (experiments: what is left is the L1)
+        if (const char* e = getenv("MLG_PROBE_CARVEOUT")) { int x = atoi(e); if (x >= 0 && x <= 100) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, x)); }
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
     CUDA_TRY(cudaMemsetAsync(a.tile_counter, 0, 8, st));
