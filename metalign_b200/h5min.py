@@ -27,7 +27,25 @@ class H5Unsupported(ValueError):
     pass
 
 
+def _guard(fn):
+    """damaged input (offsets beyond the file, impossible sizes) surfaces as H5Unsupported, never as struct.error / IndexError"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        try:
+            return fn(*a, **k)
+        except (struct.error, IndexError, OverflowError, MemoryError, TypeError, zlib.error) as e:
+            raise H5Unsupported("damaged or unsupported HDF5 structure: %s" % e) from None
+        except ValueError as e:
+            if isinstance(e, H5Unsupported):
+                raise
+            raise H5Unsupported("damaged or unsupported HDF5 structure: %s" % e) from None
+    return wrapped
+
+
 class H5File:
+    @_guard
     def __init__(self, path: str):
         self._f = open(path, "rb")
         try:
@@ -82,6 +100,7 @@ class H5File:
             raise H5Unsupported("%s: address %d beyond the end of the file (truncated?)" % (self.path, addr))
         return a
 
+    @_guard
     def messages(self, ohdr_addr: int):
         """(type, flags, payload bytes) of every message of a version-1 object header, continuation blocks included"""
         b = self.buf
@@ -94,7 +113,11 @@ class H5File:
         size, = struct.unpack_from("<I", b, a + 8)
         blocks = [(a + 16, size)]
         out = []
+        nblocks = 0
         while blocks and len(out) < nmsg:
+            nblocks += 1
+            if nblocks > 4096:
+                raise H5Unsupported("object header continuation chain too long (damaged file)")
             p, left = blocks.pop(0)
             end = p + left
             while p + 8 <= end and len(out) < nmsg:
@@ -125,6 +148,8 @@ def _parse_datatype(body: bytes):
     """numpy dtype of a datatype message (fixed-point, floating-point, fixed-length string)"""
     cls, bits0 = body[0] & 15, body[1]
     size, = struct.unpack_from("<I", body, 4)
+    if size == 0 or size > (1 << 20):
+        raise H5Unsupported("datatype of %d bytes" % size)
     if cls == 0:
         order = ">" if bits0 & 1 else "<"
         return np.dtype("%s%s%d" % (order, "i" if bits0 & 8 else "u", size))
@@ -151,6 +176,10 @@ class _Object:
 
     @property
     def attrs(self) -> dict:
+        return self._attrs()
+
+    @_guard
+    def _attrs(self) -> dict:
         out = {}
         for t, _, body in self.msgs:
             if t != 0x000C:
@@ -184,6 +213,9 @@ class _Object:
 
 
 class Group(_Object):
+    def read(self):
+        raise H5Unsupported("%s is a group, not a dataset" % self.name)
+
     def _table(self):
         for t, _, body in self.msgs:
             if t == 0x0011:
@@ -192,6 +224,7 @@ class Group(_Object):
                 raise H5Unsupported("new-style group (link messages); CMash files written by h5py's default settings use symbol tables")
         raise H5Unsupported("%s is not a group" % self.name)
 
+    @_guard
     def _entries(self):
         """name -> object header address, from the group's B-tree of symbol-table nodes and its local heap"""
         f, b = self.file, self.file.buf
@@ -202,8 +235,13 @@ class Group(_Object):
         data = f.at(struct.unpack_from("<Q", b, h + 24)[0])
         out = {}
         stack = [btree]
+        seen = set()
         while stack:
-            a = f.at(stack.pop())
+            node = stack.pop()
+            if node in seen or len(seen) > (1 << 24):
+                raise H5Unsupported("group B-tree revisits a node (damaged file)")
+            seen.add(node)
+            a = f.at(node)
             if b[a:a + 4] == b"TREE":
                 ntype, level, used = struct.unpack_from("<BBH", b, a + 4)
                 if ntype != 0:
@@ -232,6 +270,7 @@ class Group(_Object):
         self.keys()
         return name in self._names
 
+    @_guard
     def __getitem__(self, name: str):
         node = self
         for part in [x for x in name.split("/") if x]:
@@ -246,6 +285,13 @@ class Group(_Object):
 
 
 class Dataset(_Object):
+    def keys(self):
+        raise H5Unsupported("%s is a dataset, not a group" % self.name)
+
+    def __getitem__(self, name):
+        raise H5Unsupported("%s is a dataset, not a group" % self.name)
+
+    @_guard
     def _meta(self):
         shape = dtype = layout = None
         filters = []
@@ -285,10 +331,15 @@ class Dataset(_Object):
     def dtype(self):
         return self._meta()[1]
 
+    @_guard
     def read(self) -> np.ndarray:
         f, b = self.file, self.file.buf
         shape, dtype, lay, filters = self._meta()
-        n = int(np.prod(shape)) if shape else 1
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if n * dtype.itemsize > (1 << 40):
+            raise H5Unsupported("%s: dataset of %d elements" % (self.name, n))
         ver = lay[0]
         if ver == 3:
             cls = lay[1]
@@ -334,8 +385,13 @@ class Dataset(_Object):
             return out
         rank = len(shape)
         stack = [btree]
+        seen = set()
         while stack:
-            a = f.at(stack.pop())
+            node = stack.pop()
+            if node in seen:
+                raise H5Unsupported("chunk B-tree revisits a node (damaged file)")
+            seen.add(node)
+            a = f.at(node)
             if b[a:a + 4] != b"TREE":
                 raise H5Unsupported("chunk B-tree node signature missing")
             ntype, level, used = struct.unpack_from("<BBH", b, a + 4)

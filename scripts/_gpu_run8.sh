@@ -1,15 +1,16 @@
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-echo "== stress 8 (configs[4])"; MLG_BENCH_SKIP_CPU=1 timeout 600 $TR --nproc-per-node 8 --master-port 29524 bench.py --gpus 8 --steps 10 --warmup 3 --workload stress > gpurun_out/r4g_bench_8gpu_stress.json 2> gpurun_out/r4g_stress.err; tail -2 gpurun_out/r4g_stress.err | cut -c1-300
-for m in dense sparse; do
-echo "== weak 8 $m"; MLG_EXCHANGE=$m MLG_BENCH_SKIP_CPU=1 timeout 400 $TR --nproc-per-node 8 --master-port 29525 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r4g_bench_8gpu_weak_$m.json 2> gpurun_out/r4g_weak_$m.err; tail -1 gpurun_out/r4g_weak_$m.err | cut -c1-300
+for n in 2 4; do
+echo "== weak $n"; MLG_BENCH_SKIP_CPU=1 timeout 400 $TR --nproc-per-node $n --master-port 2953$n bench.py --gpus $n --steps 20 --warmup 3 > gpurun_out/r4q_bench_${n}gpu_weak.json 2> gpurun_out/r4q_weak_$n.err; tail -1 gpurun_out/r4q_weak_$n.err | cut -c1-200
 done
+echo "== reference arm under torchrun (rank 0 only)"; timeout 400 $TR --nproc-per-node 2 --master-port 29539 bench.py --gpus 2 --impl reference --steps 1 --warmup 1 2>/dev/null | cut -c1-300
 python - <<'PY'
 import json
-for w in ("stress","weak_dense","weak_sparse"):
+for n in (2,4):
     try:
-        txt=open("gpurun_out/r4g_bench_8gpu_%s.json"%w).read()
-        d=json.loads([l for l in txt.splitlines() if l.startswith("{")][-1])
-        print(w, "value %.1f G ms %.3f K1 %.3f nonprobe %.3f e2e %.1f G (%.2f ms) build %.1f s; %s" % (d["value"]/1e9, d["ms_per_step"], d["roofline"]["kernel_ms_per_step"], d["non_probe_ms_per_step"], d["e2e"]["value"]/1e9, d["e2e"]["ms_per_step"], d["config"]["db_build_s"], d["config"]["parallelism"][:90]))
-    except Exception as e: print(w, "failed", e)
+        txt=open("gpurun_out/r4q_bench_%dgpu_weak.json"%n).read()
+        print("stdout lines:", len(txt.strip().splitlines()))
+        d=json.loads(txt.strip().splitlines()[-1])
+        print(n, "value %.1f G ms %.3f K1 %.3f nonprobe %.3f e2e %.1f G (%.2f ms); %s" % (d["value"]/1e9, d["ms_per_step"], d["roofline"]["kernel_ms_per_step"], d["non_probe_ms_per_step"], d["e2e"]["value"]/1e9, d["e2e"]["ms_per_step"], d["config"]["parallelism"][:80]))
+    except Exception as e: print(n, "failed", e)
 PY

@@ -102,3 +102,36 @@ def test_make_db_from_h5_without_h5py(tmp_path):
     h5write.write_cmash_h5(p, bad, K)
     with pytest.raises(SystemExit):
         mod.main([p, out])
+
+
+def test_damaged_files_raise_cleanly(tmp_path):
+    """random byte damage and truncation of a valid file: every outcome is a parsed value, a KeyError for a name that is gone,
+    or H5Unsupported -- never another exception, never a hang (B-tree cycles are detected)"""
+    rng = random.Random(5)
+    K, n = 60, 6
+    sk = _random_sketches(rng, 40, n, K)
+    p = str(tmp_path / "ok.h5")
+    h5write.write_cmash_h5(p, sk, K)
+    good = bytearray(open(p, "rb").read())
+    q = str(tmp_path / "bad.h5")
+    outcomes = {"ok": 0, "refused": 0}
+    for trial in range(300):
+        raw = bytearray(good)
+        if trial % 5 == 0:
+            raw = raw[: rng.randrange(8, len(raw))]
+        else:
+            for _ in range(rng.randint(1, 6)):
+                i = rng.randrange(len(raw))
+                raw[i] = rng.randrange(256) if trial % 2 else raw[i] ^ (1 << rng.randrange(8))
+        open(q, "wb").write(bytes(raw))
+        try:
+            with h5min.H5File(q) as f:
+                grp = f["CountEstimators"]
+                for name in grp.keys()[:12]:
+                    g = grp[name]
+                    g["kmers"].read()
+                    g.attrs
+            outcomes["ok"] += 1
+        except (h5min.H5Unsupported, KeyError):
+            outcomes["refused"] += 1
+    assert outcomes["ok"] > 0 and outcomes["refused"] > 0, outcomes
