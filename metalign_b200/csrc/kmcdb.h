@@ -78,7 +78,7 @@ struct Reader {
         lut_entries = (lut_end - 4) / 8;
         if (lut_entries < 2) { error = prefix + ": empty prefix table"; return false; }
         const size_t rec = (info.k - info.lut_prefix_length) / 4 + info.counter_size;
-        if (8 + info.total * rec != suf.size()) { error = prefix + ": .kmc_suf size does not match total_kmers"; return false; }
+        if (info.total > suf.size() || 8 + info.total * rec != suf.size()) { error = prefix + ": .kmc_suf size does not match total_kmers"; return false; }
         return true;
     }
     // every k-mer as a 2k-bit integer (hi, lo; first base most significant), in file order; counts may be null

@@ -125,3 +125,45 @@ def test_native_kmc_reader_on_the_fixture_databases(tmp_path):
         ingest.read_kmc_database(p)
     with pytest.raises(IOError):
         ingest.read_kmc_database(str(tmp_path / "missing"))
+
+
+def test_native_kmc_reader_survives_damaged_files(tmp_path):
+    """byte damage and truncation of both files of a KMC database: the C++ reader answers or raises IOError, it never reads
+    out of bounds (run in a child process so that a crash would fail this test instead of ending the test run)"""
+    import random
+    import subprocess
+    import sys
+    rng = random.Random(2)
+    kmers = {"".join(rng.choice("ACGT") for _ in range(60)): rng.randint(1, 3) for _ in range(400)}
+    for version in (0, 0x200):
+        kmcdb.write(str(tmp_path / ("good%d" % version)), kmers, 60, counter_size=1, version=version)
+    code = r'''
+import random, sys
+sys.path.insert(0, %r)
+from metalign_b200 import ingest
+rng = random.Random(7)
+ok = bad = 0
+for version in (0, 0x200):
+    pre = bytearray(open(%r + "/good%%d.kmc_pre" %% version, "rb").read())
+    suf = bytearray(open(%r + "/good%%d.kmc_suf" %% version, "rb").read())
+    for trial in range(400):
+        a, b = bytearray(pre), bytearray(suf)
+        which = a if trial %% 3 else b
+        if trial %% 7 == 0:
+            del which[rng.randrange(4, len(which)):]
+        else:
+            for _ in range(rng.randint(1, 4)):
+                i = rng.randrange(len(which))
+                which[i] = rng.randrange(256)
+            if trial %% 11 == 0 and len(a) > 60:          # damage inside the header block at the end of .kmc_pre
+                for _ in range(3):
+                    a[len(a) - 1 - rng.randrange(56)] = rng.randrange(256)
+        open(%r + "/bad.kmc_pre", "wb").write(bytes(a)); open(%r + "/bad.kmc_suf", "wb").write(bytes(b))
+        try:
+            ingest.read_kmc_database(%r + "/bad", with_counts=True); ok += 1
+        except (IOError, MemoryError, ValueError):
+            bad += 1
+print("ok", ok, "refused", bad)
+''' % (ROOT, str(tmp_path), str(tmp_path), str(tmp_path), str(tmp_path), str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "refused" in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-600:])
