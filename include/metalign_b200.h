@@ -183,6 +183,12 @@ int mlg_query_finish(mlg_query* q, int64_t* num, int64_t* den, double* ci, uint6
  * these rows: CMash's tail drops the genomes whose containment at the largest k is 0. */
 int mlg_query_finish_sparse(mlg_query* q, uint32_t* genomes, int64_t* num, int64_t* den, double* ci, uint64_t cap_rows,
                             uint64_t* n_rows, uint64_t* n_intersect);
+/* after finish: for each of the m genomes listed, nk*n bytes, out[(i*nk + ki)*n + j] = 1 where sketch slot j of genomes[i] is
+ * the representative of a (genome, ks[ki]-prefix) class the query hit (one slot per class carries the flag).  This is what
+ * CMash's post-processing works on when --sensitive is NOT given (it re-filters the hits to k-mers unique to one organism;
+ * Metalign always passes --sensitive, select_db.py:76, so the drop-in never calls this); the host side of it is
+ * metalign_b200/cmash_tail.py: refilter_unique. */
+int mlg_query_hit_flags(mlg_query* q, const uint32_t* genomes, uint32_t m, uint8_t* out);
 /* after finish: I as (hi,lo) canonical keys in increasing order; writes at most cap pairs, *n = |I| */
 int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n);
 /* after finish: `kmc_dump <temp>/60mers_intersection <temp>/60mers_intersection_dump` and the FASTA rewrite that follows it

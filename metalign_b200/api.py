@@ -327,6 +327,14 @@ class Query:
         self._keep = []
         return ni, n.value
 
+    def hit_flags(self, genomes) -> np.ndarray:
+        """mlg_query_hit_flags: (m, nk, n) uint8, 1 where the slot is the representative of a hit (genome, k-prefix) class"""
+        g = np.ascontiguousarray(genomes, dtype=np.uint32)
+        out = np.zeros((g.size, len(self.db.ks), self.db.n), dtype=np.uint8)
+        if g.size:
+            check(_lib.lib().mlg_query_hit_flags(self._h, g.ctypes.data, g.size, out.ctypes.data))
+        return out
+
     def intersection(self) -> np.ndarray:
         n = C.c_uint64()
         check(_lib.lib().mlg_query_intersection(self._h, None, 0, C.byref(n)))

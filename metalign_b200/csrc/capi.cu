@@ -737,6 +737,23 @@ MLG_API int mlg_query_exchange_dense(mlg_query* q, uint8_t** d_counts, uint64_t*
     return MLG_OK;
 }
 
+// from the present k-mers to the hit bitmap and the per-genome counts (both zeroed by the caller)
+static int replay_hits(mlg_query* q, uint32_t* hitbits, unsigned long long words_per_k, unsigned long long* d_num) {
+    mlg_db* db = q->db; const DbView& v = db->v;
+    cudaStream_t st = q->ctx->s_comp;
+    if (db->hoff.p) {
+        // replay the precomputed hit records; k-mers without one (only a database that kept P has any) are listed and
+        // expanded on the fly
+        if (v.P_key && !q->fallback.p) MLG_TRY(q->fallback.alloc((size_t)v.nd + 1));
+        MLG_TRY(launch_apply_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits, words_per_k, d_num,
+                                  db->hoff.p, db->hbase.p, db->hits.p, q->fallback.p, q->d_scalar.p + 2, st));
+        q->st.gpu_launches += 1;
+    } else {
+        MLG_TRY(launch_expand_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits, words_per_k, d_num, st));
+    }
+    return MLG_OK;
+}
+
 // the finish stage, shared by the dense and the sparse form of the result
 struct SparseOut { uint32_t* genomes; int64_t* num; int64_t* den; double* ci; uint64_t cap; uint64_t* n_rows; };
 static int finish_impl(mlg_query* q, int64_t* num, int64_t* den, double* ci, const SparseOut* sp, uint64_t* n_intersect) {
@@ -762,16 +779,7 @@ static int finish_impl(mlg_query* q, int64_t* num, int64_t* den, double* ci, con
     const size_t cells = (size_t)v.G * v.nk;
     DevBuf<unsigned long long> d_num; MLG_TRY(d_num.alloc(cells));
     CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
-    if (db->hoff.p) {
-        // replay the precomputed hit records; k-mers without one (only a database that kept P has any) are listed and
-        // expanded on the fly
-        if (v.P_key && !q->fallback.p) MLG_TRY(q->fallback.alloc((size_t)v.nd + 1));
-        MLG_TRY(launch_apply_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p,
-                                  db->hoff.p, db->hbase.p, db->hits.p, q->fallback.p, q->d_scalar.p + 2, st));
-        q->st.gpu_launches += 1;
-    } else {
-        MLG_TRY(launch_expand_hits(v, q->present.p, q->d_scalar.p, q->gate == MLG_GATE_NONE, hitbits.p, words_per_k, d_num.p, st));
-    }
+    MLG_TRY(replay_hits(q, hitbits.p, words_per_k, d_num.p));
     q->st.gpu_launches += 2;
     DevBuf<long long> o_num, o_den; DevBuf<double> o_ci; DevBuf<uint32_t> o_g;
     unsigned long long nrows = 0;
@@ -849,6 +857,35 @@ MLG_API int mlg_query_finish_sparse(mlg_query* q, uint32_t* genomes, int64_t* nu
     if (!n_rows) { mlg_set_error("null n_rows"); return MLG_ERR_ARG; }
     SparseOut sp{genomes, num, den, ci, cap_rows, n_rows};
     return finish_impl(q, nullptr, nullptr, nullptr, &sp, n_intersect);
+}
+
+// which (genome, k-prefix) classes of the given genomes the query hit: the raw material of CMash's post-processing when
+// --sensitive is absent (metalign_b200/cmash_tail.py: refilter_unique).  The bitmap is rebuilt from the present k-mers (the
+// finish stage does not keep it: 0.1 GB per query for something Metalign never asks for).
+MLG_API int mlg_query_hit_flags(mlg_query* q, const uint32_t* genomes, uint32_t m, uint8_t* out) {
+    if (!q || (m && (!genomes || !out))) { mlg_set_error("null argument"); return MLG_ERR_ARG; }
+    if (!q->finished) { mlg_set_error("call mlg_query_finish first"); return MLG_ERR_STATE; }
+    if (!m) return MLG_OK;
+    mlg_ctx* ctx = q->ctx; const DbView& v = q->db->v;
+    MLG_TRY(ensure_device(ctx));
+    for (uint32_t i = 0; i < m; ++i) if (genomes[i] >= v.G) { mlg_set_error("genome %u out of range (G = %u)", genomes[i], v.G); return MLG_ERR_ARG; }
+    cudaStream_t st = ctx->s_comp;
+    const unsigned long long total = (unsigned long long)v.G * v.n, words_per_k = (total + 31) / 32;
+    const size_t cells = (size_t)v.G * v.nk, flags = (size_t)m * v.nk * v.n;
+    DevBuf<uint32_t> hitbits; MLG_TRY(hitbits.alloc(words_per_k * v.nk));
+    DevBuf<unsigned long long> d_num; MLG_TRY(d_num.alloc(cells));
+    DevBuf<uint32_t> d_g; MLG_TRY(d_g.alloc(m));
+    DevBuf<unsigned char> d_out; MLG_TRY(d_out.alloc(flags));
+    CUDA_TRY(cudaMemsetAsync(hitbits.p, 0, words_per_k * v.nk * 4, st));
+    CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
+    CUDA_TRY(cudaMemcpyAsync(d_g.p, genomes, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(q->d_scalar.p + 2, 0, 8, st));          // the fallback list's cursor
+    MLG_TRY(replay_hits(q, hitbits.p, words_per_k, d_num.p));
+    MLG_TRY(launch_gather_hit_flags(hitbits.p, words_per_k, d_g.p, m, v.n, v.nk, d_out.p, st));
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, flags, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
 }
 
 MLG_API int mlg_query_intersection(mlg_query* q, uint64_t* keys_out, uint64_t cap, uint64_t* n) {

@@ -194,5 +194,7 @@ int launch_finalize_sparse(const unsigned long long* num, const long long* den_r
                            unsigned long long* d_counter, cudaStream_t st);
 int launch_clear_touched(unsigned char* cnt8, const uint32_t* touched, const unsigned long long* d_n_touched, cudaStream_t st);
 int launch_gather_keys(const key128* D_key, const uint32_t* present, uint32_t n_present, key128* out, cudaStream_t st);
+int launch_gather_hit_flags(const uint32_t* hitbits, unsigned long long words_per_k, const uint32_t* genomes, uint32_t m, uint32_t n,
+                            uint32_t nk, unsigned char* out, cudaStream_t st);
 int launch_gather_counts(const unsigned char* cnt8, const unsigned char* D_mult, const uint32_t* present, uint32_t n_present, uint32_t cap,
                          unsigned char* out, cudaStream_t st);

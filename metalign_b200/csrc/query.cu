@@ -552,6 +552,17 @@ __global__ void k_gather_present_counts(const unsigned char* cnt8, const unsigne
     if (D_mult) c = min(c, (uint32_t)D_mult[d]);
     out[i] = (unsigned char)min(c, cap);
 }
+// hit flags of whole genomes: out[(i * nk + ki) * n + j] = 1 where slot j of genomes[i] is the representative of a
+// (genome, k-prefix) class that the query hit at ks[ki]
+__global__ void k_gather_hit_flags(const uint32_t* hitbits, unsigned long long words_per_k, const uint32_t* genomes, uint32_t m,
+                                   uint32_t n, uint32_t nk, unsigned char* out) {
+    const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long cells = (unsigned long long)m * nk * n;
+    if (t >= cells) return;
+    const uint32_t j = (uint32_t)(t % n), ki = (uint32_t)((t / n) % nk), i = (uint32_t)(t / ((unsigned long long)n * nk));
+    const unsigned long long slot = (unsigned long long)genomes[i] * n + j;
+    out[t] = (unsigned char)((hitbits[(unsigned long long)ki * words_per_k + (slot >> 5)] >> (slot & 31ull)) & 1u);
+}
 
 }  // namespace
 
@@ -696,6 +707,14 @@ int launch_gather_counts(const unsigned char* cnt8, const unsigned char* D_mult,
                          unsigned char* out, cudaStream_t st) {
     if (!n_present) return MLG_OK;
     k_gather_present_counts<<<(n_present + 255) / 256, 256, 0, st>>>(cnt8, D_mult, present, n_present, cap, out);
+    CUDA_TRY(cudaGetLastError());
+    return MLG_OK;
+}
+int launch_gather_hit_flags(const uint32_t* hitbits, unsigned long long words_per_k, const uint32_t* genomes, uint32_t m, uint32_t n,
+                            uint32_t nk, unsigned char* out, cudaStream_t st) {
+    const unsigned long long cells = (unsigned long long)m * nk * n;
+    if (!cells) return MLG_OK;
+    k_gather_hit_flags<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(hitbits, words_per_k, genomes, m, n, nk, out);
     CUDA_TRY(cudaGetLastError());
     return MLG_OK;
 }

@@ -74,6 +74,24 @@ def read_keys(path: str) -> np.ndarray:
     return np.fromfile(path, dtype="<u8", offset=pos, count=2 * h["G"] * h["n"]).reshape(-1, 2)
 
 
+def read_keys_rows(path: str, genomes) -> np.ndarray:
+    """(m, n, 2) source keys of the listed genomes only (a seek per genome; source-form files)"""
+    h = read_header(path)
+    if h["built"]:
+        raise ValueError("%s is a built database: it does not carry the source keys" % path)
+    pos = h["header_bytes"] + h["names_bytes"]
+    pos += (-pos) % 16
+    n = h["n"]
+    out = np.empty((len(genomes), n, 2), dtype=np.uint64)
+    with open(path, "rb") as f:
+        for i, g in enumerate(genomes):
+            if not 0 <= int(g) < h["G"]:
+                raise ValueError("genome %d out of range" % int(g))
+            f.seek(pos + int(g) * n * 16)
+            out[i] = np.frombuffer(f.read(n * 16), dtype="<u8").reshape(n, 2)
+    return out
+
+
 def keys_from_dump_fasta(path: str, K: int, expect_records: int = 0, chunk_bytes: int = 256 << 20) -> np.ndarray:
     """Keys of the FASTA dump that local_tests/dump_kmers.py:10-14 of the reference writes from the training HDF5:
     one '>seq<i>' header and one sequence line per sketch slot, in CountEstimator order; the sequence line of an

@@ -169,6 +169,40 @@ def containment_table(H: Set[Tuple[int, int, int]], sketches: Sequence[Sequence[
     return num, den, ci
 
 
+# --------------------------------------------------------------------------- R6', only without --sensitive
+def refilter_unique(H: Set[Tuple[int, int, int]], sketches: Sequence[Sequence[str]], ks: Sequence[int], ci,
+                    coverage_threshold: float = 0.0):
+    """CMash's post-processing when --sensitive is ABSENT [UPSTREAM, SURVEY.md A.2: "re-filters to k-mers unique to one
+    organism"; Metalign never takes this branch, select_db.py:76].  UNPINNED restatement, as read here:
+      * the organisms that pass the basic filter (containment at the largest k > threshold) are the candidates;
+      * at every k, a k-prefix of a candidate's sketch is UNIQUE when no other candidate's sketch has a k-mer with that
+        prefix ('' slots take no part);
+      * a candidate's containment is recomputed over its unique prefixes only: hit unique prefixes / unique prefixes
+        (0.0 where it has none).
+    Returns (candidates in genome order, num, den, ci) with one row per candidate."""
+    ks = list(ks)
+    cand = [g for g in range(len(sketches)) if ci[g][len(ks) - 1] > coverage_threshold]
+    num, den, out = [], [], []
+    for ki, k in enumerate(ks):
+        owners: Dict[str, Set[int]] = defaultdict(set)
+        for g in cand:
+            for s in sketches[g]:
+                if s != "":
+                    owners[s[:k]].add(g)
+        hit = defaultdict(set)
+        for (g, kk, j) in H:
+            if kk == k:
+                hit[g].add(sketches[g][j][:k])
+        for row, g in enumerate(cand):
+            if ki == 0:
+                num.append([0] * len(ks)); den.append([0] * len(ks)); out.append([0.0] * len(ks))
+            uniq = {s[:k] for s in sketches[g] if s != "" and len(owners[s[:k]]) == 1}
+            n_hit = len(uniq & hit[g])
+            num[row][ki], den[row][ki] = n_hit, len(uniq)
+            out[row][ki] = (float(n_hit) / float(len(uniq))) if uniq and n_hit else 0.0
+    return cand, num, den, out
+
+
 def run(reads: Iterable[str], sketches: Sequence[Sequence[str]], K: int = 60,
         ks: Sequence[int] = (30, 40, 50, 60), ci_min: int = 2, gate: str = "exact",
         count_empty_in_den: bool = True):
