@@ -70,7 +70,9 @@ class PackedBatches:
             raise IOError(self.L.mlgi_last_error().decode())
         self.max_reads = int(reads_per_batch)
         self.max_bases = int(bases_per_batch) or min(self.max_reads * 160, 0xFFFFFF00)
-        self.max_runs = int(max_runs) or max(1024, self.max_bases // 64)
+        # N runs are rare (real reads: well under one per read); a batch with more than the buffer holds comes back through
+        # mlgi_spilled_runs.  (max_bases // 64 entries were 80 MB of page-locked memory per buffer set, 0.06 s of pinning each; // 256 still holds one run per 1.7 reads.)
+        self.max_runs = int(max_runs) or max(1024, self.max_bases // 256)
         alloc = alloc or (lambda nbytes: np.zeros(nbytes, dtype=np.uint8))
         self.sets = []
         for _ in range(2):
