@@ -146,6 +146,10 @@ struct mlg_query {
     // results kept for mlg_query_intersection
     DevBuf<uint32_t> present, touched;
     uint32_t n_present = 0;
+    // the finish stage's tables (hit bitmap, per-genome counts): allocated and zeroed on the COPY stream at the first push,
+    // so that the 0.1 GB memset runs beside the probe kernel instead of behind it
+    DevBuf<uint32_t> hitbits;
+    DevBuf<unsigned long long> d_num;
 };
 
 namespace {
@@ -166,6 +170,12 @@ int run_probe(mlg_query* q, Staging& s, const unsigned char* d_bases, const unsi
     if (!q->present.p) {                       // first push: room for every database k-mer to become present once
         MLG_TRY(q->present.alloc((size_t)q->db->v.nd + 1));
         MLG_TRY(q->touched.alloc((size_t)q->db->v.nd + 1));
+        const DbView& v = q->db->v;
+        const unsigned long long words_per_k = ((unsigned long long)v.G * v.n + 31) / 32;
+        MLG_TRY(q->hitbits.alloc(words_per_k * v.nk));
+        MLG_TRY(q->d_num.alloc((size_t)v.G * v.nk));
+        CUDA_TRY(cudaMemsetAsync(q->hitbits.p, 0, words_per_k * v.nk * 4, ctx->s_copy));      // joined at the top of the finish stage
+        CUDA_TRY(cudaMemsetAsync(q->d_num.p, 0, (size_t)v.G * v.nk * 8, ctx->s_copy));
     }
     const unsigned long long nwords64 = (nbases + 63) / 64;       // 64-base words: 16 bytes of bases, 8 bytes of mask
     ProbeArgs a{};
@@ -774,11 +784,14 @@ static int finish_impl(mlg_query* q, int64_t* num, int64_t* den, double* ci, con
     // hit bitmap: nk planes of G*n bits; the kernel that sets a bit first also counts it
     const unsigned long long total = (unsigned long long)v.G * v.n;
     const unsigned long long words_per_k = (total + 31) / 32;
-    DevBuf<uint32_t> hitbits; MLG_TRY(hitbits.alloc(words_per_k * v.nk));
-    CUDA_TRY(cudaMemsetAsync(hitbits.p, 0, words_per_k * v.nk * 4, st));
     const size_t cells = (size_t)v.G * v.nk;
-    DevBuf<unsigned long long> d_num; MLG_TRY(d_num.alloc(cells));
-    CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
+    DevBuf<uint32_t>& hitbits = q->hitbits;
+    DevBuf<unsigned long long>& d_num = q->d_num;
+    if (!hitbits.p) {                                  // nothing was pushed: the tables were not set up beside a probe
+        MLG_TRY(hitbits.alloc(words_per_k * v.nk)); MLG_TRY(d_num.alloc(cells));
+        CUDA_TRY(cudaMemsetAsync(hitbits.p, 0, words_per_k * v.nk * 4, st));
+        CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
+    }
     MLG_TRY(replay_hits(q, hitbits.p, words_per_k, d_num.p));
     q->st.gpu_launches += 2;
     DevBuf<long long> o_num, o_den; DevBuf<double> o_ci; DevBuf<uint32_t> o_g;
@@ -819,6 +832,9 @@ static int finish_impl(mlg_query* q, int64_t* num, int64_t* den, double* ci, con
         // some rank had more non-zero counters than a block holds: nothing was merged (on any rank), so the exchange can
         // simply be repeated with larger blocks and finish called again
         q->merged = false; q->ex_pending = nullptr;
+        // the tables of this attempt go back to zero: finish will be called again after the repeated exchange
+        CUDA_TRY(cudaMemsetAsync(hitbits.p, 0, words_per_k * v.nk * 4, st));
+        CUDA_TRY(cudaMemsetAsync(d_num.p, 0, cells * 8, st));
         mlg_set_error("exchange blocks too small: %llu entries needed", xstat[0]);
         return MLG_ERR_RETRY;
     }
