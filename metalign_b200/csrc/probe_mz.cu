@@ -272,7 +272,14 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(const __gri
         if (lane == 0) t = atomicAdd(tile_ctr, 1u);
         return __shfl_sync(FULL, t, 0);
     };
+#ifdef MZ_STREAM_EVICT_LAST
+    const unsigned long long pol_stream = policy_evict_last();
+#elif defined(MZ_STREAM_EVICT_NORMAL)
+    unsigned long long pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
+#else
     const unsigned long long pol_stream = policy_evict_first();
+#endif
     const uint32_t wm_base = smem_u32(&sm.wm[0][tid]), seq_base = smem_u32(&sm.seq[0][tid]);
     const uint32_t* const MB = db.F;
     const uint32_t lt_mask = (1u << lane) - 1u;
