@@ -272,13 +272,16 @@ __global__ void __launch_bounds__(RT, MZ_MINCTAS) k1_minimizer_probe(const __gri
         if (lane == 0) t = atomicAdd(tile_ctr, 1u);
         return __shfl_sync(FULL, t, 0);
     };
-#ifdef MZ_STREAM_EVICT_LAST
+    // The packed reads go through the L2 with NORMAL priority: the drain reads the bases of its items back from global memory
+    // a tile or two later, and with evict_first (the round-1 choice, -DMZ_STREAM_EVICT_FIRST) the level-1 array's random lines
+    // had pushed them out by then: 2.139 ms against 2.112 (evict_last: 2.112).
+#ifdef MZ_STREAM_EVICT_FIRST
+    const unsigned long long pol_stream = policy_evict_first();
+#elif defined(MZ_STREAM_EVICT_LAST)
     const unsigned long long pol_stream = policy_evict_last();
-#elif defined(MZ_STREAM_EVICT_NORMAL)
+#else
     unsigned long long pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_stream));
-#else
-    const unsigned long long pol_stream = policy_evict_first();
 #endif
     const uint32_t wm_base = smem_u32(&sm.wm[0][tid]), seq_base = smem_u32(&sm.seq[0][tid]);
     const uint32_t* const MB = db.F;
